@@ -1,0 +1,151 @@
+/*
+ * gsraster.h -- C ABI of the B200-native differentiable 3D-Gaussian-Splatting rasterizer.
+ *
+ * Drop-in boundary for the reference's native rasterizer
+ *   RAST = submodules/depth-diff-gaussian-rasterization-min   (LucidDreamer @ 76ed990)
+ * Each entry point names the reference interface it replaces.  Plain C: raw device pointers, sizes and
+ * scalars; no torch / C++ types.  Every function returns 0 on success or a negative GS_E* code;
+ * gs_last_error() returns a human-readable message for the calling thread.
+ *
+ * The reference's static C++ API (RAST/cuda_rasterizer/rasterizer.h:20-87) takes three
+ * std::function<char*(size_t)> "resize" callbacks because the size of the binning buffer is only known
+ * after the per-Gaussian pass.  The same two-phase structure is explicit here:
+ *
+ *   gs_forward_preprocess()  enqueue per-Gaussian pass + tile histogram/scan      (no host sync)
+ *   gs_forward_counts()      wait for that pass only; returns num_rendered + #pairs (host sync on an event)
+ *   gs_forward_render()      enqueue pair emission + per-tile depth sort + compositing, given a binning
+ *                            buffer with room for `pair_capacity` pairs.  If the capacity is too small the
+ *                            kernels do nothing (device-side guard) and gs_forward_counts() tells the
+ *                            caller how much is needed -> grow and call gs_forward_render() again.
+ *
+ * A caller may therefore enqueue render() speculatively with the previous frame's capacity *before*
+ * calling counts(): the GPU never idles waiting for the host (the reference blocks on a cudaMemcpy D2H
+ * every forward, RAST/cuda_rasterizer/rasterizer_impl.cu:282).
+ *
+ * All work is enqueued on the caller's stream; the library keeps no mutable global state apart from the
+ * GsContext (pinned status slots + events), which may be shared by calls on different streams.
+ */
+#ifndef GSRASTER_H_
+#define GSRASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+
+/* error codes */
+#define GS_OK 0
+#define GS_EINVAL (-1)   /* bad argument (shape / null pointer / exactly-one-of violated) */
+#define GS_ECUDA (-2)    /* CUDA runtime error (message has cudaGetErrorString) */
+#define GS_ECAPACITY (-3)/* binning buffer too small: see gs_forward_counts */
+#define GS_ENOMEM (-4)
+
+typedef struct GsContext GsContext;
+typedef void* gs_stream_t; /* cudaStream_t */
+
+/*
+ * One view ("frame") of one Gaussian set: the argument list shared by
+ * CudaRasterizer::Rasterizer::forward / ::backward (rasterizer.h:35-58, 61-86).
+ * Device pointers, float32, contiguous.  NULL = absent, i.e. the reference binding's empty-tensor convention
+ * (RAST/depth_diff_gaussian_rasterization_min/__init__.py:198-208): exactly one of shs / colors_precomp and
+ * exactly one of (scales & rotations) / cov3D_precomp must be non-NULL.
+ */
+typedef struct GsFrame {
+    int32_t P;               /* #Gaussians */
+    int32_t D;               /* active SH degree 0..3 */
+    int32_t M;               /* SH coefficients stored per channel (16 at degree 3); 0 if shs == NULL */
+    int32_t W, H;            /* image size */
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int32_t prefiltered;     /* accepted for API parity; see DESIGN.md */
+    int32_t debug;           /* != 0: synchronize + check after every stage (auxiliary.h:166-173) */
+    const float* bg;             /* [3] */
+    const float* means3D;        /* [P,3] */
+    const float* shs;            /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3]   or NULL */
+    const float* opacities;      /* [P,1] */
+    const float* scales;         /* [P,3]   or NULL */
+    const float* rotations;      /* [P,4]   or NULL (r,x,y,z), used un-normalised like forward.cu:127 */
+    const float* cov3D_precomp;  /* [P,6]   or NULL */
+    const float* viewmatrix;     /* [16] m[r+4c] = W2C[r][c]        (scene/cameras.py:58) */
+    const float* projmatrix;     /* [16] (Proj.W2C), same layout    (scene/cameras.py:60) */
+    const float* campos;         /* [3] */
+} GsFrame;
+
+/* Gradient outputs of one backward: the tensors RasterizeGaussiansBackwardCUDA returns
+ * (RAST/rasterize_points.cu:154-199).  Every non-NULL output is FULLY overwritten (rows of invisible
+ * Gaussians get zeros) so the caller may pass uninitialised memory -- no torch::zeros fills needed.
+ * NULL = not wanted. */
+typedef struct GsGrads {
+    float* dL_dmeans3D;   /* [P,3] */
+    float* dL_dmeans2D;   /* [P,3]  x,y = dL/d(NDC mean), z = 0 */
+    float* dL_dsh;        /* [P,M,3] */
+    float* dL_dcolors;    /* [P,3]  gradient w.r.t. colors_precomp (or the SH-derived RGB) */
+    float* dL_dopacity;   /* [P,1] */
+    float* dL_dscales;    /* [P,3] */
+    float* dL_drotations; /* [P,4] */
+    float* dL_dcov3D;     /* [P,6] */
+} GsGrads;
+
+/* Host-visible result of the per-Gaussian pass. */
+typedef struct GsCounts {
+    int64_t num_rendered; /* sum of tile-rect areas == the reference's return value (rasterizer_impl.cu:282) */
+    int64_t num_pairs;    /* (tile, Gaussian) pairs actually binned (== num_rendered unless culling is on) */
+    int64_t num_visible;  /* #{radii > 0} */
+} GsCounts;
+
+int gs_abi_version(void);
+const char* gs_last_error(void);
+
+/* Context: per device.  Holds pinned status slots + events used by gs_forward_counts. */
+int gs_context_create(int device, GsContext** out);
+void gs_context_destroy(GsContext* ctx);
+
+/* Scratch sizing -- replaces required<GeometryState/ImageState/BinningState>() (rasterizer_impl.h:66-73).
+ * The buffers are opaque to the caller and are what the reference round-trips through
+ * ctx.save_for_backward as geomBuffer / binningBuffer / imgBuffer (__init__.py:97). */
+size_t gs_geom_bytes(int32_t P);
+size_t gs_image_bytes(int32_t W, int32_t H);
+size_t gs_binning_bytes(int64_t pair_capacity);
+
+/* replaces the first half of Rasterizer::forward (rasterizer_impl.cu:198-282).
+ * radii [P] int32 is fully written.  *ticket identifies the status slot for gs_forward_counts. */
+int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, void* image_buffer, int32_t* radii,
+                          gs_stream_t stream, int32_t* ticket);
+
+/* Blocks the host until the preprocess of `ticket` has finished (event wait; later work keeps running). */
+int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out);
+
+/* replaces the second half of Rasterizer::forward (rasterizer_impl.cu:284-338).
+ * out_color [3,H,W], out_depth [1,H,W] are fully written.  Returns GS_OK even if the capacity turns out
+ * too small on the device (nothing is rendered then) -- check with gs_forward_counts. */
+int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, void* geom_buffer, void* binning_buffer,
+                      int64_t pair_capacity, void* image_buffer, float* out_color, float* out_depth,
+                      gs_stream_t stream);
+
+/* replaces Rasterizer::backward (rasterizer_impl.cu:343-444) + the nine torch::zeros of its binding.
+ * dL_dout_depth is accepted and ignored: the reference's depth gradient is commented out
+ * (backward.cu:443-469,539-554). */
+int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
+                const void* binning_buffer, int64_t pair_capacity, const void* image_buffer,
+                const float* dL_dout_color, const float* dL_dout_depth, const GsGrads* grads, gs_stream_t stream);
+
+/* replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153): present[i] = (z_view > 0.2) */
+int gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, gs_stream_t stream);
+
+/* Introspection for tests: copies the per-tile exclusive offsets (uint32 [G+1]; tile t owns
+ * [off[t], off[t+1]) -- the reference's `ranges`, rasterizer_impl.cu:116-138) and the depth-sorted Gaussian
+ * index list (uint32 [max_pairs]; the reference's `point_list`) out of the opaque buffers (device -> device). */
+int gs_debug_export_binning(const GsFrame* f, const void* binning_buffer, int64_t pair_capacity,
+                            const void* image_buffer, uint32_t* tile_offsets, uint32_t* point_list,
+                            int64_t max_pairs, gs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSRASTER_H_ */

@@ -1,0 +1,248 @@
+// C ABI of the B200 rasterizer (include/gsraster.h).  Host-side orchestration only: argument checks, scratch
+// carving, kernel launches on the caller's stream, pinned status slots.  Mirrors the structure of the
+// reference's CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// (RAST/cuda_rasterizer/rasterizer_impl.cu:141-153,198-339,343-444) and of its torch binding
+// (RAST/rasterize_points.cu:35-221) without any torch types.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/gsraster.h"
+#include "gs_common.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define GS_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) return fail(GS_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));   \
+    } while (0)
+
+constexpr int kSlots = 64;
+
+int check_frame(const GsFrame* f) {
+    if (!f) return fail(GS_EINVAL, "frame is NULL");
+    if (f->P < 0 || f->W <= 0 || f->H <= 0) return fail(GS_EINVAL, "bad sizes P=%d W=%d H=%d", f->P, f->W, f->H);
+    if (f->P == 0) return GS_OK;
+    if (!f->means3D || !f->opacities || !f->viewmatrix || !f->projmatrix || !f->campos || !f->bg)
+        return fail(GS_EINVAL, "means3D/opacities/viewmatrix/projmatrix/campos/bg must be non-NULL");
+    // RAST/depth_diff_gaussian_rasterization_min/__init__.py:192-196
+    if ((f->shs == nullptr) == (f->colors_precomp == nullptr))
+        return fail(GS_EINVAL, "Please provide excatly one of either SHs or precomputed colors!");
+    const bool has_sr = f->scales != nullptr && f->rotations != nullptr;
+    if (((f->scales == nullptr || f->rotations == nullptr) && f->cov3D_precomp == nullptr) ||
+        ((f->scales != nullptr || f->rotations != nullptr) && f->cov3D_precomp != nullptr))
+        return fail(GS_EINVAL, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    (void)has_sr;
+    if (f->shs && (f->M <= 0 || f->D < 0 || f->D > 3 || (f->D + 1) * (f->D + 1) > f->M))
+        return fail(GS_EINVAL, "SH degree %d needs %d coefficients, M=%d", f->D, (f->D + 1) * (f->D + 1), f->M);
+    return GS_OK;
+}
+
+GsView make_view(const GsFrame* f) {
+    GsView v;
+    v.vm = f->viewmatrix; v.pm = f->projmatrix; v.campos = f->campos; v.bg = f->bg;
+    v.tan_fovx = f->tan_fovx; v.tan_fovy = f->tan_fovy;
+    v.focal_y = f->H / (2.0f * f->tan_fovy);            // rasterizer_impl.cu:223-224
+    v.focal_x = f->W / (2.0f * f->tan_fovx);
+    v.scale_modifier = f->scale_modifier;
+    v.W = f->W; v.H = f->H;
+    v.gx = (f->W + GS_TILE - 1) / GS_TILE; v.gy = (f->H + GS_TILE - 1) / GS_TILE;
+    v.P = f->P; v.D = f->D; v.M = f->shs ? f->M : 0;
+    return v;
+}
+
+int debug_sync(const GsFrame* f, cudaStream_t s, const char* what) {
+    if (!f->debug) {
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) return fail(GS_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+        return GS_OK;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);           // CHECK_CUDA(., debug): auxiliary.h:166-173
+    if (e != cudaSuccess) return fail(GS_ECUDA, "[CUDA ERROR] in %s: %s", what, cudaGetErrorString(e));
+    return GS_OK;
+}
+
+}  // namespace
+
+struct GsContext {
+    int device;
+    GsDevStatus* slots;            // pinned, mapped
+    cudaEvent_t events[kSlots];
+    std::atomic<int> next;
+};
+
+extern "C" {
+
+int gs_abi_version(void) { return GS_ABI_VERSION; }
+const char* gs_last_error(void) { return g_err; }
+
+int gs_context_create(int device, GsContext** out) {
+    if (!out) return fail(GS_EINVAL, "out is NULL");
+    int prev = 0;
+    GS_CUDA(cudaGetDevice(&prev));
+    GS_CUDA(cudaSetDevice(device));
+    GsContext* c = new GsContext();
+    c->device = device;
+    c->next = 0;
+    cudaError_t e = cudaHostAlloc((void**)&c->slots, sizeof(GsDevStatus) * kSlots, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) { delete c; cudaSetDevice(prev); return fail(GS_ECUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
+    memset(c->slots, 0, sizeof(GsDevStatus) * kSlots);
+    for (int i = 0; i < kSlots; i++) {
+        e = cudaEventCreateWithFlags(&c->events[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) { cudaSetDevice(prev); return fail(GS_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+    }
+    cudaSetDevice(prev);
+    *out = c;
+    return GS_OK;
+}
+
+void gs_context_destroy(GsContext* c) {
+    if (!c) return;
+    for (int i = 0; i < kSlots; i++) cudaEventDestroy(c->events[i]);
+    cudaFreeHost(c->slots);
+    delete c;
+}
+
+size_t gs_geom_bytes(int32_t P) { return gs_geom_layout(nullptr, P > 0 ? P : 1).bytes; }
+size_t gs_image_bytes(int32_t W, int32_t H) { return gs_image_layout(nullptr, W, H).bytes; }
+size_t gs_binning_bytes(int64_t cap) { return gs_bin_layout(nullptr, cap > 0 ? cap : 1).bytes; }
+
+int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, void* image_buffer, int32_t* radii,
+                          gs_stream_t stream, int32_t* ticket) {
+    if (!ctx || !ticket) return fail(GS_EINVAL, "ctx/ticket is NULL");
+    int rc = check_frame(f);
+    if (rc) return rc;
+    if (!image_buffer || (f->P > 0 && (!geom_buffer || !radii))) return fail(GS_EINVAL, "scratch/radii is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const GsView v = make_view(f);
+    const int G = v.gx * v.gy;
+    GsImageLayout il = gs_image_layout(image_buffer, f->W, f->H);
+    const int slot = ctx->next.fetch_add(1) % kSlots;
+    GsDevStatus* host_slot = ctx->slots + slot;
+    host_slot->overflow = 0;                             // cleared; kernel writes 0xC0FFEE when done
+    // zero tile histogram + status in one memset (they are adjacent)
+    GS_CUDA(cudaMemsetAsync(il.tile_cnt, 0, (size_t)((char*)il.status - (char*)il.tile_cnt) + sizeof(GsDevStatus), s));
+    if (f->P > 0) {
+        GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
+        gs_launch_preprocess(v, f->means3D, f->shs, f->colors_precomp, f->opacities, f->scales, f->rotations,
+                             f->cov3D_precomp, radii, gl.rec, gl.acc, il.tile_cnt, il.status, s);
+        if ((rc = debug_sync(f, s, "preprocess"))) return rc;
+    }
+    GsDevStatus* dev_slot = nullptr;
+    GS_CUDA(cudaHostGetDevicePointer((void**)&dev_slot, host_slot, 0));
+    gs_launch_tile_scan(G, il.tile_cnt, il.tile_off, il.status, dev_slot, s);
+    if ((rc = debug_sync(f, s, "tile_scan"))) return rc;
+    GS_CUDA(cudaEventRecord(ctx->events[slot], s));
+    *ticket = slot;
+    return GS_OK;
+}
+
+int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out) {
+    if (!ctx || !out || ticket < 0 || ticket >= kSlots) return fail(GS_EINVAL, "bad ctx/ticket/out");
+    GS_CUDA(cudaEventSynchronize(ctx->events[ticket]));
+    const volatile GsDevStatus* h = ctx->slots + ticket;
+    if (h->overflow != 0xC0FFEEu) return fail(GS_ECUDA, "status slot %d was not written by the device", ticket);
+    out->num_rendered = (int64_t)h->num_rendered;
+    out->num_pairs = (int64_t)h->num_pairs;
+    out->num_visible = (int64_t)h->num_visible;
+    return GS_OK;
+}
+
+int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, void* geom_buffer, void* binning_buffer,
+                      int64_t pair_capacity, void* image_buffer, float* out_color, float* out_depth,
+                      gs_stream_t stream) {
+    (void)ctx;
+    int rc = check_frame(f);
+    if (rc) return rc;
+    if (!image_buffer || !out_color || !out_depth) return fail(GS_EINVAL, "image buffer / outputs are NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)f->W * f->H;
+    if (f->P == 0) {                                     // rasterize_points.cu:68-70,82: zero images, no kernels
+        GS_CUDA(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), s));
+        GS_CUDA(cudaMemsetAsync(out_depth, 0, N * sizeof(float), s));
+        return GS_OK;
+    }
+    if (!geom_buffer || !radii || !binning_buffer || pair_capacity < 0) return fail(GS_EINVAL, "scratch/radii is NULL");
+    const GsView v = make_view(f);
+    const int G = v.gx * v.gy;
+    GsImageLayout il = gs_image_layout(image_buffer, f->W, f->H);
+    GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
+    GsBinLayout bl = gs_bin_layout(binning_buffer, pair_capacity > 0 ? pair_capacity : 1);
+    gs_launch_emit(v, radii, gl.rec, il.tile_off, il.tile_cnt, il.status, bl.keys, pair_capacity, s);
+    if ((rc = debug_sync(f, s, "emit"))) return rc;
+    gs_launch_tile_sort(G, il.tile_off, il.tile_cnt, il.status, bl.keys, bl.list, pair_capacity, s);
+    if ((rc = debug_sync(f, s, "tile_sort"))) return rc;
+    gs_launch_blend_fwd(v, il.tile_off, bl.list, gl.rec, il.status, pair_capacity, il.final_T, il.n_contrib, out_color,
+                        out_depth, s);
+    if ((rc = debug_sync(f, s, "blend_fwd"))) return rc;
+    return GS_OK;
+}
+
+int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
+                const void* binning_buffer, int64_t pair_capacity, const void* image_buffer,
+                const float* dL_dout_color, const float* dL_dout_depth, const GsGrads* grads, gs_stream_t stream) {
+    (void)ctx; (void)dL_dout_depth;                      // depth gradient disabled in the reference
+    int rc = check_frame(f);
+    if (rc) return rc;
+    if (!grads) return fail(GS_EINVAL, "grads is NULL");
+    if (f->P == 0) return GS_OK;
+    if (!radii || !geom_buffer || !binning_buffer || !image_buffer || !dL_dout_color)
+        return fail(GS_EINVAL, "radii / scratch / dL_dout_color is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const GsView v = make_view(f);
+    GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
+    GsGeomLayout gl = gs_geom_layout(const_cast<void*>(geom_buffer), f->P);
+    GsBinLayout bl = gs_bin_layout(const_cast<void*>(binning_buffer), pair_capacity > 0 ? pair_capacity : 1);
+    gs_launch_blend_bwd(v, il.tile_off, bl.list, gl.rec, il.final_T, il.n_contrib, dL_dout_color, gl.acc, s);
+    if ((rc = debug_sync(f, s, "blend_bwd"))) return rc;
+    GsGradPtrs g;
+    g.dmeans3D = grads->dL_dmeans3D; g.dmeans2D = grads->dL_dmeans2D; g.dsh = f->shs ? grads->dL_dsh : nullptr;
+    g.dcolors = grads->dL_dcolors; g.dopacity = grads->dL_dopacity;
+    g.dscales = grads->dL_dscales; g.drots = grads->dL_drotations; g.dcov3D = grads->dL_dcov3D;
+    gs_launch_gauss_bwd(v, radii, f->means3D, f->shs, f->cov3D_precomp ? nullptr : f->scales,
+                        f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec, gl.acc, g, s);
+    if ((rc = debug_sync(f, s, "gauss_bwd"))) return rc;
+    // outputs the fused kernel does not produce in this input mode are defined as zeros (reference: torch::zeros)
+    const size_t Ps = (size_t)f->P;
+    if (!f->shs && grads->dL_dsh && f->M > 0) GS_CUDA(cudaMemsetAsync(grads->dL_dsh, 0, Ps * f->M * 3 * sizeof(float), s));
+    return GS_OK;
+}
+
+int gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, gs_stream_t stream) {
+    (void)projmatrix;
+    if (P < 0) return fail(GS_EINVAL, "P < 0");
+    if (P == 0) return GS_OK;
+    if (!means3D || !viewmatrix || !present) return fail(GS_EINVAL, "NULL argument");
+    gs_launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GS_ECUDA, "mark_visible launch: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
+int gs_debug_export_binning(const GsFrame* f, const void* binning_buffer, int64_t pair_capacity,
+                            const void* image_buffer, uint32_t* ranges, uint32_t* point_list, int64_t max_pairs,
+                            gs_stream_t stream) {
+    if (!f || !binning_buffer || !image_buffer) return fail(GS_EINVAL, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
+    GsBinLayout bl = gs_bin_layout(const_cast<void*>(binning_buffer), pair_capacity > 0 ? pair_capacity : 1);
+    const int G = ((f->W + GS_TILE - 1) / GS_TILE) * ((f->H + GS_TILE - 1) / GS_TILE);
+    if (ranges) GS_CUDA(cudaMemcpyAsync(ranges, il.tile_off, (size_t)(G + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    if (point_list && max_pairs > 0)
+        GS_CUDA(cudaMemcpyAsync(point_list, bl.list, (size_t)max_pairs * 4, cudaMemcpyDeviceToDevice, s));
+    return GS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+"""Drop-in host side of the B200 rasterizer: the reference's Python operator API, name for name.
+
+Mirrors RAST/depth_diff_gaussian_rasterization_min/__init__.py (RAST = submodules/depth-diff-gaussian-
+rasterization-min of LucidDreamer):
+
+    GaussianRasterizationSettings   NamedTuple, 12 fields in the reference order      (__init__.py:158-170)
+    GaussianRasterizer              nn.Module: forward(...) -> (color, radii, depth), markVisible(...)  (:172-221)
+    rasterize_gaussians             functional form                                   (:21-42)
+    _RasterizeGaussians             torch.autograd.Function, 8 gradients + None       (:44-156)
+    _C                              rasterize_gaussians / rasterize_gaussians_backward / mark_visible with the
+                                    signatures of the reference's pybind module       (ext.cpp:15-19)
+
+so `gaussian_renderer.render()` (gaussian_renderer/__init__.py:18-104) and `scene.GaussianModel` run unchanged.
+Everything below the argument checks is the C ABI in include/gsraster.h (hand-written sm_100a CUDA); PyTorch is
+used for device memory, streams and autograd only.  There is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+# ---------------------------------------------------------------------------------------------- plumbing
+
+_contexts: dict = {}      # device index -> GsContext*
+_cap_hint: dict = {}      # device index -> last (tile, Gaussian) pair count seen
+
+
+def _ctx(dev_index: int) -> C.c_void_p:
+    c = _contexts.get(dev_index)
+    if c is None:
+        h = C.c_void_p()
+        N.check(N.lib().gs_context_create(int(dev_index), C.byref(h)))
+        _contexts[dev_index] = c = h
+    return c
+
+
+def _round_cap(n: int) -> int:
+    return max(64, (int(n) + 63) // 64 * 64)      # multiples of 64 keep gs_binning_bytes(cap) == 12 * cap
+
+
+def _dev_f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
+    """Reference convention: empty tensor == absent (RAST/.../__init__.py:198-208). Otherwise f32, contiguous,
+    on the compute device (the reference calls .contiguous() on everything, rasterize_points.cu:95-113)."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.device != device or t.dtype != torch.float32:
+        t = t.to(device=device, dtype=torch.float32)
+    return t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class _Prepared(NamedTuple):
+    frame: N.GsFrame
+    keep: tuple
+    device: torch.device
+    P: int
+    M: int
+
+
+def _prepare(bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+             projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug
+             ) -> _Prepared:
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")      # rasterize_points.cu:57-59
+    if not means3D.is_cuda:
+        raise RuntimeError("luciddreamer_b200: tensors must live on a CUDA device (no CPU fallback)")
+    dev = means3D.device
+    P = means3D.size(0)
+    t = [_dev_f32(x, dev) for x in (bg, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                    viewmatrix, projmatrix, campos)]
+    bg_, m3, sh_, col, op, sc, rot, cov, vm, pm, cp = t
+    M = 0 if sh_ is None else sh_.size(1)
+    f = N.GsFrame()
+    f.P, f.D, f.M, f.W, f.H = P, int(degree), int(M), int(image_width), int(image_height)
+    f.tan_fovx, f.tan_fovy, f.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
+    f.prefiltered, f.debug = int(bool(prefiltered)), int(bool(debug))
+    f.bg, f.means3D, f.shs, f.colors_precomp = _p(bg_), _p(m3), _p(sh_), _p(col)
+    f.opacities, f.scales, f.rotations, f.cov3D_precomp = _p(op), _p(sc), _p(rot), _p(cov)
+    f.viewmatrix, f.projmatrix, f.campos = _p(vm), _p(pm), _p(cp)
+    return _Prepared(f, tuple(t), dev, P, M)
+
+
+def _forward_impl(prep: _Prepared):
+    """Returns (num_rendered, color, depth, radii, geom, binning, img, pair_capacity)."""
+    L = N.lib()
+    f, dev, P = prep.frame, prep.device, prep.P
+    H, W = f.H, f.W
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with torch.cuda.device(idx):
+        ctx = _ctx(idx)
+        stream = torch.cuda.current_stream(idx).cuda_stream
+        u8 = dict(dtype=torch.uint8, device=dev)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom = torch.empty((L.gs_geom_bytes(P),), **u8)
+        img = torch.empty((L.gs_image_bytes(W, H),), **u8)
+        ticket = C.c_int32(-1)
+        N.check(L.gs_forward_preprocess(ctx, C.byref(f), geom.data_ptr(), img.data_ptr(), radii.data_ptr(), stream,
+                                        C.byref(ticket)))
+        counts = N.GsCounts()
+        hint = _cap_hint.get(idx)
+        if hint is None:
+            # first frame on this device: learn the pair count (one event wait), then render
+            N.check(L.gs_forward_counts(ctx, ticket, C.byref(counts)))
+            cap = _round_cap(counts.num_pairs * 1.25 + 4096)
+            binning = torch.empty((L.gs_binning_bytes(cap),), **u8)
+            N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
+                                        img.data_ptr(), color.data_ptr(), depth.data_ptr(), stream))
+        else:
+            # speculative: enqueue the render with the previous capacity, *then* wait for the count; the GPU
+            # never idles on the host (reference: blocking cudaMemcpy, rasterizer_impl.cu:282)
+            cap = _round_cap(hint * 1.25 + 4096)
+            binning = torch.empty((L.gs_binning_bytes(cap),), **u8)
+            N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
+                                        img.data_ptr(), color.data_ptr(), depth.data_ptr(), stream))
+            N.check(L.gs_forward_counts(ctx, ticket, C.byref(counts)))
+            if counts.num_pairs > cap:       # device-side guard skipped the render: grow and redo it
+                cap = _round_cap(counts.num_pairs * 1.25 + 4096)
+                binning = torch.empty((L.gs_binning_bytes(cap),), **u8)
+                N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                                            cap, img.data_ptr(), color.data_ptr(), depth.data_ptr(), stream))
+        _cap_hint[idx] = int(counts.num_pairs)
+    return int(counts.num_rendered), color, depth, radii, geom, binning, img, cap
+
+
+def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, want_colors: bool, want_cov: bool):
+    L = N.lib()
+    f, dev, P, M = prep.frame, prep.device, prep.P, prep.M
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with torch.cuda.device(idx):
+        stream = torch.cuda.current_stream(idx).cuda_stream
+        f32 = dict(dtype=torch.float32, device=dev)
+        g = N.GsGrads()
+        dm3 = torch.empty((P, 3), **f32); dm2 = torch.empty((P, 3), **f32)
+        dop = torch.empty((P, 1), **f32)
+        dsh = torch.empty((P, M, 3), **f32)
+        dsc = torch.empty((P, 3), **f32) if f.scales else torch.zeros((P, 3), **f32)
+        drot = torch.empty((P, 4), **f32) if f.rotations else torch.zeros((P, 4), **f32)
+        dcol = torch.empty((P, 3), **f32) if want_colors else None
+        dcov = torch.empty((P, 6), **f32) if want_cov else None
+        g.dL_dmeans3D, g.dL_dmeans2D, g.dL_dopacity = dm3.data_ptr(), dm2.data_ptr(), dop.data_ptr()
+        g.dL_dsh = dsh.data_ptr() if M > 0 else None
+        g.dL_dscales = dsc.data_ptr() if f.scales else None
+        g.dL_drotations = drot.data_ptr() if f.rotations else None
+        g.dL_dcolors = _p(dcol)
+        g.dL_dcov3D = _p(dcov)
+        gc = _dev_f32(grad_color, dev)
+        N.check(L.gs_backward(_ctx(idx), C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
+                              img.data_ptr(), _p(gc), None, C.byref(g), stream))
+    return dm2, dcol, dop, dm3, dcov, dsh, dsc, drot
+
+
+# ------------------------------------------------------------------------- `_C`-compatible module surface
+
+class _C:
+    """Same three entry points, argument order and return tuples as the reference's pybind module
+    (RAST/ext.cpp:15-19, rasterize_points.h:18-68).  The three byte tensors are opaque scratch; capacity of the
+    binning buffer is recovered from its size, so the reference's own __init__.py could sit on top verbatim."""
+
+    @staticmethod
+    def rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                            viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
+                            campos, prefiltered, debug):
+        prep = _prepare(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                        projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered,
+                        debug)
+        nr, color, depth, radii, geom, binning, img, _cap = _forward_impl(prep)
+        return nr, color, depth, radii, geom, binning, img
+
+    @staticmethod
+    def rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                                     viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth, sh,
+                                     degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
+        H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+        prep = _prepare(bg, means3D, colors, torch.empty(0), scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, False, debug)
+        # opacities are not an input of the reference backward; the C ABI only checks non-NULL
+        prep.frame.opacities = means3D.data_ptr()
+        cap = binningBuffer.numel() // 12
+        dm2, dcol, dop, dm3, dcov, dsh, dsc, drot = _backward_impl(prep, radii, geomBuffer, binningBuffer,
+                                                                   imageBuffer, cap, dL_dout_color, True, True)
+        return dm2, dcol, dop, dm3, dcov, dsh, dsc, drot
+
+    @staticmethod
+    def mark_visible(means3D, viewmatrix, projmatrix):
+        dev = means3D.device
+        if not means3D.is_cuda:
+            raise RuntimeError("luciddreamer_b200: tensors must live on a CUDA device (no CPU fallback)")
+        P = means3D.size(0)
+        present = torch.empty((P,), dtype=torch.bool, device=dev)
+        if P:
+            m3, vm, pm = _dev_f32(means3D, dev), _dev_f32(viewmatrix, dev), _dev_f32(projmatrix, dev)
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            with torch.cuda.device(idx):
+                N.check(N.lib().gs_mark_visible(P, m3.data_ptr(), vm.data_ptr(), _p(pm), present.data_ptr(),
+                                                torch.cuda.current_stream(idx).cuda_stream))
+        return present
+
+
+# -------------------------------------------------------------------------------- reference Python surface
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        prep = _prepare(rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+                        cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+                        rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        num_rendered, color, depth, radii, geom, binning, img, cap = _forward_impl(prep)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.pair_capacity = cap
+        ctx.prep = prep                       # keeps the contiguous f32 inputs alive + the filled GsFrame
+        ctx.save_for_backward(radii, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        radii, geom, binning, img = ctx.saved_tensors
+        prep = ctx.prep
+        f = prep.frame
+        want_colors = bool(f.colors_precomp)
+        want_cov = bool(f.cov3D_precomp)
+        dm2, dcol, dop, dm3, dcov, dsh, dsc, drot = _backward_impl(prep, radii, geom, binning, img,
+                                                                   ctx.pair_capacity, grad_out_color, want_colors,
+                                                                   want_cov)
+        # order of __init__.py:144-156; absent inputs get None (the reference returns zero tensors for them,
+        # which autograd discards for inputs that do not require grad)
+        return (dm3, dm2, dsh if f.shs else None, dcol, dop, dsc if f.scales else None,
+                drot if f.rotations else None, dcov, None)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        e = torch.Tensor([])
+        shs = e if shs is None else shs
+        colors_precomp = e if colors_precomp is None else colors_precomp
+        scales = e if scales is None else scales
+        rotations = e if rotations is None else rotations
+        cov3D_precomp = e if cov3D_precomp is None else cov3D_precomp
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, rs)
