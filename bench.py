@@ -1,0 +1,495 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward Mrays/s of the 3DGS rasterizer at BASELINE.json config 3
+(1 M Gaussians, 1920x1080, SH degree 3, synthetic shell scene of SURVEY.md 8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene shell|stress]
+
+One "step" = one forward + one backward of one 1080p view through the public operator API
+(GaussianRasterizer autograd.Function), parameters resident in HBM.  N > 1 (torchrun, one rank per GPU): every
+rank renders its own view of the same replicated model per step (weak scaling over views, no data-path
+collective); value = total rays of all ranks / max-over-ranks device time.  Prints ONE JSON line on rank 0.
+
+--impl reference times the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libref_rasterizer.so, compiled
+from the reference's own sources) on the same GPU, same inputs, same protocol; if that library is absent it
+falls back to the CPU oracle port.  The reference has no CPU implementation of this path, so
+`cpu_baseline` is always the oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from luciddreamer_b200 import synthetic as syn
+
+METRIC = "forward+backward Mrays/s @1080p/1M Gaussians"
+CFG_ID = 3
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def view_pose(rank: int, step: int = 0):
+    """Per-rank camera: identity for rank 0, other ranks yaw around the vertical axis on the
+    rotate360 path (camera at the origin) so every GPU renders a different view of the same shell."""
+    if rank == 0:
+        return None
+    return syn.rotate360_poses(64)[(rank * 8) % 64]
+
+
+def alg_bytes(P, Pv, pairs, N, G, M):
+    """Algorithmic (compulsory) HBM bytes per launch of each kernel -- DESIGN.md section 4 states the model."""
+    vis_in = 12 + 16 + 4 + 12 * M
+    return {
+        "k_preprocess": 12 * P + Pv * vis_in + 4 * P + 96 * Pv + 4 * pairs,
+        "k_tile_scan": 12 * G,
+        "k_emit": 4 * P + 48 * Pv + 8 * pairs + 4 * pairs,
+        "k_tile_sort": 8 * pairs + 4 * pairs,
+        "k_tile_sort_big": 0,
+        "k_blend_fwd": 4 * pairs + 48 * Pv + 24 * N,
+        "k_blend_bwd": 20 * N + 4 * pairs + 48 * Pv + 72 * Pv,
+        "k_gauss_bwd": 4 * P + (12 + 12 + 12 * M + 4 + 12 + 16) * P + Pv * (12 + 12 + 16 + 12 * M + 16 + 96),
+    }
+
+
+def make_workload(args, rank):
+    c = syn.CONFIGS[CFG_ID]
+    P, W, H, D = c["P"], c["W"], c["H"], c["sh_degree"]
+    if args.P:
+        P = args.P
+    if args.W and args.H:
+        W, H = args.W, args.H
+    scale_mult = 4.0 if args.scene == "stress" else 1.0
+    scene = syn.make_scene(P, 1000 + CFG_ID, scale_mult=scale_mult)
+    cam = syn.make_camera(W, H, c2w=view_pose(rank))
+    cot = syn.make_cotangent(H, W, 1000 + CFG_ID)
+    return scene, cam, cot, dict(P=P, W=W, H=H, D=D, scale_mult=scale_mult)
+
+
+# ------------------------------------------------------------------------------------------- implementations
+
+class Ours:
+    name = "ours"
+
+    def __init__(self, scene, cam, dev, D):
+        from luciddreamer_b200 import rasterizer as R
+        self.R, self.dev, self.D = R, dev, D
+        self.leaves = {k: scene[k].to(dev).requires_grad_(True)
+                       for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        self.P = scene["means3D"].shape[0]
+        self.m2 = torch.zeros(self.P, 3, device=dev, requires_grad=True)
+        self.bg = torch.zeros(3, device=dev)
+        self.vm, self.pm, self.cp = cam.viewmatrix.to(dev), cam.projmatrix.to(dev), cam.campos.to(dev)
+        self.cam = cam
+        self.settings = R.GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
+                                                        self.bg, 1.0, self.vm, self.pm, D, self.cp, False, False)
+        self.rast = R.GaussianRasterizer(self.settings)
+        self.kernels_per_step = 8
+        self.last = None
+
+    def step(self, cot):
+        L = self.leaves
+        for t in L.values():
+            t.grad = None
+        self.m2.grad = None
+        color, radii, depth = self.rast(L["means3D"], self.m2, L["opacities"], shs=L["shs"], scales=L["scales"],
+                                        rotations=L["rotations"])
+        torch.autograd.backward(color, grad_tensors=cot)
+        self.last = (color, radii)
+        return color
+
+    def set_camera(self, vm, pm, cp):      # e2e: camera arrives from the host every step
+        self.vm.copy_(vm, non_blocking=True); self.pm.copy_(pm, non_blocking=True); self.cp.copy_(cp, non_blocking=True)
+
+    def stats(self):
+        idx = self.dev.index or 0
+        pairs = self.R._cap_hint.get(idx, 0)
+        radii = self.last[1]
+        return dict(P_vis=int((radii > 0).sum().item()), pairs=int(pairs))
+
+    def profile(self, cot, n=5):
+        import ctypes as C
+        from luciddreamer_b200 import _native as N
+        L = N.lib()
+        ctx = self.R._ctx(self.dev.index or 0)
+        nk = L.gs_profile_num_kernels()
+        names = [L.gs_profile_kernel_name(i).decode() for i in range(nk)]
+        acc = np.zeros(nk)
+        L.gs_profile_enable(ctx, 1)
+        for _ in range(n):
+            self.step(cot)
+            buf = (C.c_float * nk)()
+            N.check(L.gs_profile_read(ctx, buf))
+            acc += np.maximum(np.array(buf[:]), 0.0)
+        L.gs_profile_enable(ctx, 0)
+        return dict(zip(names, (acc / n).tolist()))
+
+
+class RefCuda:
+    """The unmodified reference CUDA rasterizer (oracle/_ref), driven like its torch binding drives it."""
+    name = "reference"
+
+    def __init__(self, scene, cam, dev, D):
+        from oracle import ref_cuda
+        self.rc, self.dev, self.D = ref_cuda, dev, D
+        self.ctx = ref_cuda.RefContext()
+        self.t = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        self.bg = torch.zeros(3, device=dev)
+        self.vm, self.pm, self.cp = cam.viewmatrix.to(dev), cam.projmatrix.to(dev), cam.campos.to(dev)
+        self.cam = cam
+        self.kernels_per_step = 0
+
+    def step(self, cot):
+        t, cam = self.t, self.cam
+        R, color, depth, radii = self.rc.rasterize_gaussians(
+            self.ctx, self.bg, t["means3D"], None, t["opacities"], t["scales"], t["rotations"], 1.0, None, self.vm,
+            self.pm, cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, t["shs"], self.D, self.cp)
+        self.rc.rasterize_gaussians_backward(self.ctx, radii, cot)
+        self.last = (color, radii, R)
+        return color
+
+    def set_camera(self, vm, pm, cp):
+        self.vm.copy_(vm, non_blocking=True); self.pm.copy_(pm, non_blocking=True); self.cp.copy_(cp, non_blocking=True)
+
+    def stats(self):
+        return dict(P_vis=int((self.last[1] > 0).sum().item()), pairs=int(self.last[2]))
+
+
+def time_steps(impl, cot, steps, warmup, world):
+    for _ in range(warmup):
+        impl.step(cot)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        impl.step(cot)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def time_e2e(impl, cam, cot_cpu, steps, warmup, world):
+    """Same metric end to end: every step uploads that step's inputs (camera matrices + the [3,H,W] image-space
+    cotangent, standing in for the ground-truth image of the photometric loss) from pinned host memory and reads
+    the step's scalar result (<color, cotangent>) back.  Uploads of step k+1 overlap the compute of step k on a
+    copy stream; everything is inside the timed region."""
+    dev = impl.dev
+    pin = lambda t: t.contiguous().pin_memory()
+    h_cot, h_vm, h_pm, h_cp = pin(cot_cpu), pin(cam.viewmatrix), pin(cam.projmatrix), pin(cam.campos)
+    d_cot = [torch.empty_like(cot_cpu, device=dev) for _ in range(2)]
+    d_vm = [torch.empty(4, 4, device=dev) for _ in range(2)]
+    d_pm = [torch.empty(4, 4, device=dev) for _ in range(2)]
+    d_cp = [torch.empty(3, device=dev) for _ in range(2)]
+    h_loss = torch.zeros(steps + warmup, dtype=torch.float32).pin_memory()
+    copy_s = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    h2d = (h_cot.numel() + 16 + 16 + 3) * 4
+    d2h = 4
+
+    def upload(k):
+        b = k & 1
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(ev_free[b])
+            d_cot[b].copy_(h_cot, non_blocking=True); d_vm[b].copy_(h_vm, non_blocking=True)
+            d_pm[b].copy_(h_pm, non_blocking=True); d_cp[b].copy_(h_cp, non_blocking=True)
+            ev_up[b].record(copy_s)
+
+    def run(n, base):
+        upload(base)
+        for k in range(base, base + n):
+            b = k & 1
+            if k + 1 < base + n:
+                upload(k + 1)
+            main.wait_event(ev_up[b])
+            impl.set_camera(d_vm[b], d_pm[b], d_cp[b])
+            color = impl.step(d_cot[b])
+            loss = (color.detach() * d_cot[b]).sum()
+            h_loss[k].copy_(loss, non_blocking=True)
+            ev_free[b].record(main)
+
+    for b in range(2):
+        ev_free[b].record(main)
+    run(warmup, 0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    run(steps, warmup)
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        dist.barrier()
+    ms = max(e0.elapsed_time(e1), wall_ms)      # the host-visible result is only there after the final sync
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, h2d, d2h, float(h_loss[-1])
+
+
+def cpu_baseline(scene, cam, cot, D, budget_s=12.0, max_steps=3):
+    """Oracle port (C + OpenMP, fp32 faithful mode) on the host cores: full config-3 forward+backward steps."""
+    from oracle import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    oracle.set_threads(threads)
+    args = (torch.zeros(3), scene["means3D"], None, scene["opacities"], scene["scales"], scene["rotations"], 1.0, None,
+            cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, scene["shs"],
+            D, cam.campos)
+    cotn = cot.numpy()
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_steps and (time.perf_counter() - t_all) < budget_s:
+        t0 = time.perf_counter()
+        f = oracle.rasterize_gaussians(*args)
+        oracle.rasterize_gaussians_backward(f, cotn)
+        times.append(time.perf_counter() - t0)
+        f.free()
+    best = min(times)
+    rays = cam.image_height * cam.image_width
+    return {"value": rays / best / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+            "sample": f"{len(times)} full forward+backward steps of the bench workload (oracle/gs_oracle.c, OpenMP "
+                      f"{threads} threads, fp32), best {best * 1e3:.0f} ms/step"}
+
+
+def shared_model_leg(scene, cam, cot, dev, D, steps, warmup, world):
+    """Config-5 style step: every rank renders its view straight into a flat gradient bucket, then ONE NCCL
+    all-reduce(sum) of the bucket (59 floats/Gaussian)."""
+    from luciddreamer_b200 import multiview as MV
+    from luciddreamer_b200 import rasterizer as R
+    params = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    bg = torch.zeros(3, device=dev)
+    rs = R.GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, bg, 1.0,
+                                         cam.viewmatrix.to(dev), cam.projmatrix.to(dev), D, cam.campos.to(dev), False, False)
+    P, M = params["means3D"].shape[0], params["shs"].shape[1]
+    bucket = MV.GradBucket(P, M, dev)
+    dm2 = torch.empty(P, 3, device=dev)
+
+    def step():
+        MV.view_step(params, rs, cot, bucket=bucket, means2D_grad=dm2)
+        MV.allreduce_bucket(bucket)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"ms_per_step": ms, "value": world * cam.image_height * cam.image_width / ms / 1e3, "unit": "Mrays/s",
+            "allreduce_bytes": bucket.nbytes(), "collective": "nccl all_reduce(sum) of the flat gradient bucket"}
+
+
+# ----------------------------------------------------------------------------------------------------- main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="shell", choices=["shell", "stress"])
+    ap.add_argument("--P", type=int, default=0); ap.add_argument("--W", type=int, default=0); ap.add_argument("--H", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shared-model", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and rank != 0:
+        return 0                                   # rank 0 alone runs the reference arm
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "bench.py needs a GPU (no CPU fallback for the product path)"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and args.impl == "ours":
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        world = 1 if args.impl == "reference" else world
+
+    scene, cam, cot_cpu, wl = make_workload(args, rank)
+    W, H, P, D = wl["W"], wl["H"], wl["P"], wl["D"]
+    rays = W * H
+    cot = cot_cpu.to(dev)
+    peak, peak_src = load_peaks()
+
+    use_ref_cuda = False
+    if args.impl == "reference":
+        from oracle import ref_cuda
+        use_ref_cuda = ref_cuda.available()
+        if not use_ref_cuda:                       # reference CUDA not compiled here: time the oracle port instead
+            cb = cpu_baseline(scene, cam, cot_cpu, D, budget_s=60.0, max_steps=max(1, min(args.steps, 5)))
+            line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Mrays/s", "n_gpus": 0,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": rays / cb["value"] / 1e3,
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                    "data": "synthetic", "config": config_dict(wl, args, 1), "cpu_baseline": cb,
+                    "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+            return 0
+        impl = RefCuda(scene, cam, dev, D)
+    else:
+        impl = Ours(scene, cam, dev, D)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = time_steps(impl, cot, args.steps, args.warmup, world)
+    clocks = sampler.stop() if rank == 0 else None
+    st = impl.stats()
+    value = world * rays * args.steps / ms / 1e3           # Mrays/s, whole job
+    e2e_ms, h2d, d2h, loss = time_e2e(impl, cam, cot_cpu, args.steps, args.warmup, world)
+    e2e_val = world * rays * args.steps / e2e_ms / 1e3
+
+    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(wl, args, world),
+            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "protocol": "per step: H2D camera (35 floats) + [3,H,W] cotangent from pinned memory (copy stream, "
+                                "double buffered), forward+backward via the autograd API, D2H scalar <color,cotangent>"},
+            "clocks": clocks, "scene_stats": {"P_vis": st["P_vis"], "pairs": st["pairs"]}}
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["reference_kind"] = "reference CUDA extension core (oracle/_ref) on the same GPU"
+        line["gpu_launches"] = 0
+    else:
+        line["gpu_launches"] = impl.kernels_per_step * args.steps
+        # ---- roofline of the dominant kernel (CUDA events around every launch, on the launching stream)
+        kt = impl.profile(cot, n=5)
+        N_, G_, M_ = W * H, ((W + 15) // 16) * ((H + 15) // 16), scene["shs"].shape[1]
+        ab = alg_bytes(P, st["P_vis"], st["pairs"], N_, G_, M_)
+        dom = max(kt, key=lambda k: kt[k])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.scene, {}).get(dom)
+            except Exception:
+                traffic = None
+        ach = ab[dom] / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                            "algorithmic_bytes": ab[dom], "kernel_ms": kt[dom]}
+        total_alg = sum(ab.values())
+        line["roofline_step"] = {"algorithmic_bytes": total_alg, "achieved": total_alg / (ms / args.steps * 1e-3) / 1e9,
+                                 "unit": "GB/s", "frac": total_alg / (ms / args.steps * 1e-3) / 1e9 / peak}
+        line["kernels_ms"] = kt
+        line["kernels_frac_of_hbm_peak"] = {k: (ab[k] / (kt[k] * 1e-3) / 1e9 / peak if kt[k] > 0 else None) for k in kt}
+        if world > 1 and not args.no_shared_model:
+            line["shared_model_step"] = shared_model_leg(scene, cam, cot, dev, D, args.steps, args.warmup, world)
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(scene, cam, cot_cpu, D)
+    if rank == 0:
+        print(json.dumps(line))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    return 0
+
+
+def config_dict(wl, args, world):
+    return {"workload": f"BASELINE config {CFG_ID}: {wl['P']} Gaussians, {wl['W']}x{wl['H']}, SH degree {wl['D']}, "
+                        f"forward+backward, one view per GPU per step",
+            "scene": f"{args.scene} (SURVEY.md 8d shell, seed {1000 + CFG_ID}, scale x{wl['scale_mult']})",
+            "views_per_step": world, "parallelism": f"view-parallel x{world}",
+            "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 25 MB cotangent per step)"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

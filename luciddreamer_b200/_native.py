@@ -54,6 +54,10 @@ SYMBOLS = [
     ("gs_mark_visible", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gs_debug_export_binning", C.c_int, [C.POINTER(GsFrame), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p]),
+    ("gs_profile_enable", C.c_int, [C.c_void_p, C.c_int]),
+    ("gs_profile_num_kernels", C.c_int, []),
+    ("gs_profile_kernel_name", C.c_char_p, [C.c_int]),
+    ("gs_profile_read", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
 ]
 
 _lib = None

@@ -75,14 +75,49 @@ int debug_sync(const GsFrame* f, cudaStream_t s, const char* what) {
 
 }  // namespace
 
+constexpr int kNumKernels = GS_NUM_KERNELS;
+static const char* const kKernelNames[kNumKernels] = {"k_preprocess", "k_tile_scan", "k_emit", "k_tile_sort",
+                                                      "k_tile_sort_big", "k_blend_fwd", "k_blend_bwd", "k_gauss_bwd"};
+
 struct GsContext {
     int device;
+    int num_sms;
+    int profile;                   // != 0: bracket every kernel with timing events (gs_profile_*)
+    cudaEvent_t pev[2 * kNumKernels];
+    bool pev_used[kNumKernels];
     GsDevStatus* slots;            // pinned, mapped
     cudaEvent_t events[kSlots];
     std::atomic<int> next;
 };
 
+// Brackets a launch with timing events on the launching stream when profiling is on (bench.py's roofline leg).
+#define GS_TIMED(ctx, k, s, launch)                                   \
+    do {                                                              \
+        if ((ctx) && (ctx)->profile) cudaEventRecord((ctx)->pev[2 * (k)], s);     \
+        launch;                                                       \
+        if ((ctx) && (ctx)->profile) { cudaEventRecord((ctx)->pev[2 * (k) + 1], s); (ctx)->pev_used[k] = true; } \
+    } while (0)
+
 extern "C" {
+
+int gs_profile_enable(GsContext* ctx, int on) {
+    if (!ctx) return fail(GS_EINVAL, "ctx is NULL");
+    ctx->profile = on;
+    for (int i = 0; i < kNumKernels; i++) ctx->pev_used[i] = false;
+    return GS_OK;
+}
+int gs_profile_num_kernels(void) { return kNumKernels; }
+const char* gs_profile_kernel_name(int i) { return (i >= 0 && i < kNumKernels) ? kKernelNames[i] : ""; }
+int gs_profile_read(GsContext* ctx, float* ms) {
+    if (!ctx || !ms) return fail(GS_EINVAL, "NULL argument");
+    for (int k = 0; k < kNumKernels; k++) {
+        ms[k] = -1.f;
+        if (!ctx->pev_used[k]) continue;
+        GS_CUDA(cudaEventSynchronize(ctx->pev[2 * k + 1]));
+        GS_CUDA(cudaEventElapsedTime(&ms[k], ctx->pev[2 * k], ctx->pev[2 * k + 1]));
+    }
+    return GS_OK;
+}
 
 int gs_abi_version(void) { return GS_ABI_VERSION; }
 const char* gs_last_error(void) { return g_err; }
@@ -95,6 +130,12 @@ int gs_context_create(int device, GsContext** out) {
     GsContext* c = new GsContext();
     c->device = device;
     c->next = 0;
+    c->profile = 0;
+    for (int i = 0; i < kNumKernels; i++) c->pev_used[i] = false;
+    for (int i = 0; i < 2 * kNumKernels; i++) cudaEventCreate(&c->pev[i]);
+    c->num_sms = 148;
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    gs_tile_sort_init();
     cudaError_t e = cudaHostAlloc((void**)&c->slots, sizeof(GsDevStatus) * kSlots, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; cudaSetDevice(prev); return fail(GS_ECUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->slots, 0, sizeof(GsDevStatus) * kSlots);
@@ -110,6 +151,7 @@ int gs_context_create(int device, GsContext** out) {
 void gs_context_destroy(GsContext* c) {
     if (!c) return;
     for (int i = 0; i < kSlots; i++) cudaEventDestroy(c->events[i]);
+    for (int i = 0; i < 2 * kNumKernels; i++) cudaEventDestroy(c->pev[i]);
     cudaFreeHost(c->slots);
     delete c;
 }
@@ -135,13 +177,14 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     GS_CUDA(cudaMemsetAsync(il.tile_cnt, 0, (size_t)((char*)il.status - (char*)il.tile_cnt) + sizeof(GsDevStatus), s));
     if (f->P > 0) {
         GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
-        gs_launch_preprocess(v, f->means3D, f->shs, f->colors_precomp, f->opacities, f->scales, f->rotations,
-                             f->cov3D_precomp, radii, gl.rec, gl.acc, il.tile_cnt, il.status, s);
+        GS_TIMED(ctx, 0, s, gs_launch_preprocess(v, f->means3D, f->shs, f->colors_precomp, f->opacities, f->scales,
+                                                 f->rotations, f->cov3D_precomp, radii, gl.rec, gl.acc, il.tile_cnt,
+                                                 il.status, s));
         if ((rc = debug_sync(f, s, "preprocess"))) return rc;
     }
     GsDevStatus* dev_slot = nullptr;
     GS_CUDA(cudaHostGetDevicePointer((void**)&dev_slot, host_slot, 0));
-    gs_launch_tile_scan(G, il.tile_cnt, il.tile_off, il.status, dev_slot, s);
+    GS_TIMED(ctx, 1, s, gs_launch_tile_scan(G, il.tile_cnt, il.tile_off, il.status, dev_slot, s));
     if ((rc = debug_sync(f, s, "tile_scan"))) return rc;
     GS_CUDA(cudaEventRecord(ctx->events[slot], s));
     *ticket = slot;
@@ -162,7 +205,6 @@ int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out) {
 int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, void* geom_buffer, void* binning_buffer,
                       int64_t pair_capacity, void* image_buffer, float* out_color, float* out_depth,
                       gs_stream_t stream) {
-    (void)ctx;
     int rc = check_frame(f);
     if (rc) return rc;
     if (!image_buffer || !out_color || !out_depth) return fail(GS_EINVAL, "image buffer / outputs are NULL");
@@ -179,12 +221,18 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
     GsImageLayout il = gs_image_layout(image_buffer, f->W, f->H);
     GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
     GsBinLayout bl = gs_bin_layout(binning_buffer, pair_capacity > 0 ? pair_capacity : 1);
-    gs_launch_emit(v, radii, gl.rec, il.tile_off, il.tile_cnt, il.status, bl.keys, pair_capacity, s);
+    GS_TIMED(ctx, 2, s, gs_launch_emit(v, radii, gl.rec, il.tile_off, il.tile_cnt, il.status, bl.keys, pair_capacity, s));
     if ((rc = debug_sync(f, s, "emit"))) return rc;
-    gs_launch_tile_sort(G, il.tile_off, il.tile_cnt, il.status, bl.keys, bl.list, pair_capacity, s);
+    {
+        const bool prof = ctx && ctx->profile;
+        cudaEvent_t* pe = prof ? ctx->pev + 2 * 3 : nullptr;   // [start sort, end sort, start big, end big]
+        gs_launch_tile_sort(G, ctx ? ctx->num_sms : 148, il.tile_off, il.tile_cnt, il.status, il.big_list, bl.keys,
+                            bl.list, pair_capacity, s, pe);
+        if (prof) ctx->pev_used[3] = ctx->pev_used[4] = true;
+    }
     if ((rc = debug_sync(f, s, "tile_sort"))) return rc;
-    gs_launch_blend_fwd(v, il.tile_off, bl.list, gl.rec, il.status, pair_capacity, il.final_T, il.n_contrib, out_color,
-                        out_depth, s);
+    GS_TIMED(ctx, 5, s, gs_launch_blend_fwd(v, il.tile_off, bl.list, gl.rec, il.status, pair_capacity, il.final_T,
+                                                il.n_contrib, out_color, out_depth, s));
     if ((rc = debug_sync(f, s, "blend_fwd"))) return rc;
     return GS_OK;
 }
@@ -192,7 +240,7 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
 int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
                 const void* binning_buffer, int64_t pair_capacity, const void* image_buffer,
                 const float* dL_dout_color, const float* dL_dout_depth, const GsGrads* grads, gs_stream_t stream) {
-    (void)ctx; (void)dL_dout_depth;                      // depth gradient disabled in the reference
+    (void)dL_dout_depth;                                 // depth gradient disabled in the reference
     int rc = check_frame(f);
     if (rc) return rc;
     if (!grads) return fail(GS_EINVAL, "grads is NULL");
@@ -204,14 +252,16 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
     GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
     GsGeomLayout gl = gs_geom_layout(const_cast<void*>(geom_buffer), f->P);
     GsBinLayout bl = gs_bin_layout(const_cast<void*>(binning_buffer), pair_capacity > 0 ? pair_capacity : 1);
-    gs_launch_blend_bwd(v, il.tile_off, bl.list, gl.rec, il.final_T, il.n_contrib, dL_dout_color, gl.acc, s);
+    GS_TIMED(ctx, 6, s, gs_launch_blend_bwd(v, il.tile_off, bl.list, gl.rec, il.final_T, il.n_contrib, dL_dout_color,
+                                                gl.acc, s));
     if ((rc = debug_sync(f, s, "blend_bwd"))) return rc;
     GsGradPtrs g;
     g.dmeans3D = grads->dL_dmeans3D; g.dmeans2D = grads->dL_dmeans2D; g.dsh = f->shs ? grads->dL_dsh : nullptr;
     g.dcolors = grads->dL_dcolors; g.dopacity = grads->dL_dopacity;
     g.dscales = grads->dL_dscales; g.drots = grads->dL_drotations; g.dcov3D = grads->dL_dcov3D;
-    gs_launch_gauss_bwd(v, radii, f->means3D, f->shs, f->cov3D_precomp ? nullptr : f->scales,
-                        f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec, gl.acc, g, s);
+    GS_TIMED(ctx, 7, s, gs_launch_gauss_bwd(v, radii, f->means3D, f->shs, f->cov3D_precomp ? nullptr : f->scales,
+                                                f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec,
+                                                gl.acc, g, s));
     if ((rc = debug_sync(f, s, "gauss_bwd"))) return rc;
     // outputs the fused kernel does not produce in this input mode are defined as zeros (reference: torch::zeros)
     const size_t Ps = (size_t)f->P;

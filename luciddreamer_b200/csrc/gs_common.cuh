@@ -4,7 +4,7 @@
 //  geom buffer   rec[P]  : 3 x float4 per Gaussian, written only for visible ones
 //                          q0 = (x_pix, y_pix, conic_a, conic_b)
 //                          q1 = (conic_c, opacity, r, g)
-//                          q2 = (b, depth, clamped-bits, 0)
+//                          q2 = (b, depth, clamped-bits, cull threshold -ln(255 opacity) - slack)
 //                acc[P]  : 3 x float4 gradient accumulator per Gaussian (zeroed for visible ones by the
 //                          forward; consumed and re-zeroed by the backward)
 //                          a0 = (dmean2D.x, dmean2D.y, dconic.a, dconic.b)
@@ -24,8 +24,8 @@ struct GsDevStatus {         // lives at the end of the image buffer
     unsigned long long num_rendered;   // sum of rect areas (reference semantics)
     unsigned long long num_pairs;      // pairs binned
     unsigned long long num_visible;
-    unsigned int overflow;             // set by the scan kernel when num_pairs > capacity at render time
-    unsigned int pad;
+    unsigned int overflow;             // set by k_emit when num_pairs > capacity at render time
+    unsigned int n_big;                // tiles queued for k_tile_sort_big
 };
 
 struct GsImageLayout {
@@ -33,6 +33,7 @@ struct GsImageLayout {
     uint32_t* n_contrib;
     uint32_t* tile_off;      // [G+1] exclusive offsets
     uint32_t* tile_cnt;      // [G]   histogram, then reused as emission cursors
+    uint32_t* big_list;      // [G]   tiles whose bucket exceeds the warp-sort capacity
     GsDevStatus* status;
     size_t bytes;
 };
@@ -48,6 +49,7 @@ __host__ inline GsImageLayout gs_image_layout(void* base, int W, int H) {
     L.final_T = (float*)(p + off);      off = gs_align_up(off + N * 4, 256);
     L.n_contrib = (uint32_t*)(p + off); off = gs_align_up(off + N * 4, 256);
     L.tile_off = (uint32_t*)(p + off);  off = gs_align_up(off + (G + 1) * 4, 256);
+    L.big_list = (uint32_t*)(p + off);  off = gs_align_up(off + G * 4, 256);
     L.tile_cnt = (uint32_t*)(p + off);  off = gs_align_up(off + G * 4, 256);
     L.status = (GsDevStatus*)(p + off); off = gs_align_up(off + sizeof(GsDevStatus), 256);
     L.bytes = off;
@@ -250,8 +252,10 @@ void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevSta
 void gs_launch_emit(const GsView& v, const int* radii, const float4* rec, const uint32_t* tile_off,
                     uint32_t* tile_cur, GsDevStatus* status, unsigned long long* keys, long long capacity,
                     cudaStream_t s);
-void gs_launch_tile_sort(int G, const uint32_t* tile_off, uint32_t* tile_cur, const GsDevStatus* status,
-                         unsigned long long* keys, uint32_t* list, long long capacity, cudaStream_t s);
+void gs_tile_sort_init();
+void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
+                         uint32_t* big_list, unsigned long long* keys, uint32_t* list, long long capacity,
+                         cudaStream_t s, cudaEvent_t* prof);
 void gs_launch_blend_fwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const GsDevStatus* status, long long capacity, float* final_T, uint32_t* n_contrib,
                          float* out_color, float* out_depth, cudaStream_t s);

@@ -29,6 +29,35 @@ __device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, const f
     }
 }
 
+// Expand the staged (basis[16], dRGB[3]) of `rows` Gaussians into their contiguous dL_dsh block with coalesced
+// 128-bit stores.  CM3 > 0: compile-time row length (M*3), so the index arithmetic is mul/shift, not division.
+template <int CM3>
+__device__ __forceinline__ void store_dsh(float* __restrict__ dst, const float* sb, const float* sr, int rows,
+                                          int lane, int rt_m3 = 0) {
+    const int M3 = CM3 > 0 ? CM3 : rt_m3;
+    const int total = rows * M3;
+    if ((M3 & 3) == 0) {
+        const int total4 = total >> 2;
+        for (int f = lane; f < total4; f += 32) {
+            float o[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = 4 * f + u;
+                const int gg = e / M3, rem = e - gg * M3;
+                const int k = rem / 3, ch = rem - 3 * k;
+                o[u] = (k < 16 ? sb[gg * 16 + k] : 0.f) * sr[gg * 3 + ch];
+            }
+            reinterpret_cast<float4*>(dst)[f] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    } else {
+        for (int e = lane; e < total; e += 32) {
+            const int gg = e / M3, rem = e - gg * M3;
+            const int k = rem / 3, ch = rem - 3 * k;
+            dst[e] = (k < 16 ? sb[gg * 16 + k] : 0.f) * sr[gg * 3 + ch];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kT)
 k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restrict__ means3D,
             const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -261,31 +290,10 @@ k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restri
         for (int k = 0; k < 16; k++) sb[lane * 16 + k] = bs[k];
         sr[lane * 3] = dRGB0; sr[lane * 3 + 1] = dRGB1; sr[lane * 3 + 2] = dRGB2;
         __syncwarp();
-        const int M3 = v.M * 3;
         const long long rows = min((long long)32, (long long)P - row0);
         if (rows > 0) {
-            const int total = (int)rows * M3;
-            float* dst = g.dsh + row0 * M3;
-            if ((M3 & 3) == 0) {
-                const int total4 = total >> 2;
-                for (int f = lane; f < total4; f += 32) {
-                    float o[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int e = 4 * f + u;
-                        const int gg = e / M3, rem = e - gg * M3;
-                        const int k = rem / 3, ch = rem - 3 * k;
-                        o[u] = (k < 16 ? sb[gg * 16 + k] : 0.f) * sr[gg * 3 + ch];
-                    }
-                    reinterpret_cast<float4*>(dst)[f] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-            } else {
-                for (int e = lane; e < total; e += 32) {
-                    const int gg = e / M3, rem = e - gg * M3;
-                    const int k = rem / 3, ch = rem - 3 * k;
-                    dst[e] = (k < 16 ? sb[gg * 16 + k] : 0.f) * sr[gg * 3 + ch];
-                }
-            }
+            if (v.M == 16) store_dsh<48>(g.dsh + row0 * 48, sb, sr, (int)rows, lane);
+            else store_dsh<0>(g.dsh + row0 * (v.M * 3), sb, sr, (int)rows, lane, v.M * 3);
         }
     }
 }

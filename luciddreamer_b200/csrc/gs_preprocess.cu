@@ -15,17 +15,57 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kBigRect = 32;   // rects with more tiles than this are walked by the whole warp
 
-// Calls f(tile_id, payload...) for every tile of every lane's rect.  Small rects: each lane on its own.
+// Exact tile culling (parity-safe): a (tile, splat) pair is binned only if the splat can
+// reach alpha >= 1/255 somewhere in the tile.  power(d) = -0.5 (A dx^2 + C dy^2) - B dx dy is concave with its
+// maximum (0) at the mean, so its maximum over the tile's pixel box [x0, x0+15] x [y0, y0+15] is 0 if the mean is
+// inside and otherwise lies on an edge facing the mean; each facing edge is a 1-D concave maximisation (clamp
+// the stationary point).  The pair is kept iff max power >= thr, thr = -ln(255 * opacity) - slack: pairs that are
+// dropped are skipped by every pixel of the tile in the reference too (forward.cu:336-346), so no output changes.
+// __noinline__: the histogram pass (k_preprocess) and the emission pass (k_emit) must take bit-identical
+// decisions, so both call the same machine code on the same stored floats.
+#define GS_CULL_SLACK 0.01f
+__device__ __noinline__ bool gs_tile_hit(float mx, float my, float A, float B, float C, float thr, int tx, int ty) {
+    const float x0 = (float)(tx * GS_TILE), x1 = x0 + (float)(GS_TILE - 1);
+    const float y0 = (float)(ty * GS_TILE), y1 = y0 + (float)(GS_TILE - 1);
+    const bool in_x = mx >= x0 && mx <= x1, in_y = my >= y0 && my <= y1;
+    if (in_x && in_y) return !(thr > 0.f);          // NaN anywhere => keep the pair (conservative)
+    float best = -3.0e38f;
+    if (!in_x) {                                         // facing vertical edge
+        const float ex = mx < x0 ? x0 : x1;
+        const float dx = mx - ex;
+        float py = my + B * dx / C;                      // stationary point along the edge
+        py = fminf(y1, fmaxf(y0, py));
+        const float dy = my - py;
+        best = fmaxf(best, -0.5f * (A * dx * dx + C * dy * dy) - B * dx * dy);
+    }
+    if (!in_y) {                                         // facing horizontal edge
+        const float ey = my < y0 ? y0 : y1;
+        const float dy = my - ey;
+        float px = mx + B * dy / A;
+        px = fminf(x1, fmaxf(x0, px));
+        const float dx = mx - px;
+        best = fmaxf(best, -0.5f * (A * dx * dx + C * dy * dy) - B * dx * dy);
+    }
+    return !(best < thr);
+}
+
+struct GsCullArgs {
+    float mx, my, A, B, C, thr;
+};
+
+// Calls f(tile_id, payload...) for every tile of every lane's rect that passes gs_tile_hit.  Small rects: each lane on its own.
 // Large rects: the warp takes them one at a time, lanes striding over the tiles (avoids one lane looping over
 // hundreds of tiles while 31 wait).  Must be called by all 32 lanes.
 template <typename F>
-__device__ __forceinline__ void gs_for_each_tile(bool vis, int4 rect, int gx, uint32_t p0, uint32_t p1, F f) {
+__device__ __forceinline__ void gs_for_each_tile(bool vis, int4 rect, int gx, GsCullArgs c, uint32_t p0, uint32_t p1,
+                                                 F f) {
     const int w = rect.z - rect.x, h = rect.w - rect.y;
     const int area = vis ? w * h : 0;
     const bool big = area > kBigRect;
     if (area > 0 && !big) {
         for (int y = rect.y; y < rect.w; y++)
-            for (int x = rect.x; x < rect.z; x++) f((uint32_t)(y * gx + x), p0, p1);
+            for (int x = rect.x; x < rect.z; x++)
+                if (gs_tile_hit(c.mx, c.my, c.A, c.B, c.C, c.thr, x, y)) f((uint32_t)(y * gx + x), p0, p1);
     }
     unsigned m = __ballot_sync(0xffffffffu, big);
     const int lane = threadIdx.x & 31;
@@ -35,9 +75,14 @@ __device__ __forceinline__ void gs_for_each_tile(bool vis, int4 rect, int gx, ui
         const int rx = __shfl_sync(0xffffffffu, rect.x, src), ry = __shfl_sync(0xffffffffu, rect.y, src);
         const int rw = __shfl_sync(0xffffffffu, w, src), n = __shfl_sync(0xffffffffu, area, src);
         const uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
+        GsCullArgs d;
+        d.mx = __shfl_sync(0xffffffffu, c.mx, src); d.my = __shfl_sync(0xffffffffu, c.my, src);
+        d.A = __shfl_sync(0xffffffffu, c.A, src); d.B = __shfl_sync(0xffffffffu, c.B, src);
+        d.C = __shfl_sync(0xffffffffu, c.C, src); d.thr = __shfl_sync(0xffffffffu, c.thr, src);
         for (int k = lane; k < n; k += 32) {
             const int yy = k / rw, xx = k - yy * rw;
-            f((uint32_t)((ry + yy) * gx + rx + xx), q0, q1);
+            if (gs_tile_hit(d.mx, d.my, d.A, d.B, d.C, d.thr, rx + xx, ry + yy))
+                f((uint32_t)((ry + yy) * gx + rx + xx), q0, q1);
         }
     }
 }
@@ -54,6 +99,7 @@ k_preprocess(const GsView v, const float* __restrict__ means3D, const float* __r
     bool vis = false;
     int4 rect = make_int4(0, 0, 0, 0);
     int my_radius = 0;
+    GsCullArgs cull = {0.f, 0.f, 1.f, 0.f, 1.f, 0.f};
 
     if (i < v.P) {
         const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
@@ -106,10 +152,14 @@ k_preprocess(const GsView v, const float* __restrict__ means3D, const float* __r
                         clamped = (cr < 0.f ? 1u : 0u) | (cg < 0.f ? 2u : 0u) | (cb < 0.f ? 4u : 0u);
                         r_ = fmaxf(cr, 0.f); g_ = fmaxf(cg, 0.f); b_ = fmaxf(cb, 0.f);
                     }
+                    const float opac = opacities[i];
+                    // alpha >= 1/255  <=>  power >= -ln(255 * opacity); slack keeps the test conservative
+                    const float thr = -logf(255.0f * opac) - GS_CULL_SLACK;
+                    cull.mx = px; cull.my = py; cull.A = conic.x; cull.B = conic.y; cull.C = conic.z; cull.thr = thr;
                     float4* rr = rec + (size_t)3 * i;
                     rr[0] = make_float4(px, py, conic.x, conic.y);
-                    rr[1] = make_float4(conic.z, opacities[i], r_, g_);
-                    rr[2] = make_float4(b_, p_view.z, __uint_as_float(clamped), 0.f);
+                    rr[1] = make_float4(conic.z, opac, r_, g_);
+                    rr[2] = make_float4(b_, p_view.z, __uint_as_float(clamped), thr);
                     float4* aa = acc + (size_t)3 * i;
                     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     aa[0] = z4; aa[1] = z4; aa[2] = z4;
@@ -120,7 +170,8 @@ k_preprocess(const GsView v, const float* __restrict__ means3D, const float* __r
     }
 
     // tile histogram (one RED per pair)
-    gs_for_each_tile(vis, rect, v.gx, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&tile_cnt[tile], 1u); });
+    gs_for_each_tile(vis, rect, v.gx, cull, 0u, 0u,
+                     [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&tile_cnt[tile], 1u); });
 
     // block-level totals -> two atomics per CTA
     const unsigned area = vis ? (unsigned)((rect.z - rect.x) * (rect.w - rect.y)) : 0u;
@@ -193,21 +244,25 @@ k_emit(const GsView v, const int* __restrict__ radii, const float4* __restrict__
         if (blockIdx.x == 0 && threadIdx.x == 0) status->overflow = 1u;
         return;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) status->n_big = 0u;
     const int i = blockIdx.x * kThreads + threadIdx.x;
     bool vis = false;
     int4 rect = make_int4(0, 0, 0, 0);
     uint32_t dbits = 0;
+    GsCullArgs cull = {0.f, 0.f, 1.f, 0.f, 1.f, 0.f};
     if (i < v.P) {
         const int r = radii[i];
         if (r > 0) {
             const float4 q0 = __ldg(rec + (size_t)3 * i);
+            const float4 q1 = __ldg(rec + (size_t)3 * i + 1);
             const float4 q2 = __ldg(rec + (size_t)3 * i + 2);
             rect = gs_rect(q0.x, q0.y, r, v.gx, v.gy);  // same recomputation as rasterizer_impl.cu:91
             dbits = __float_as_uint(q2.y);
+            cull.mx = q0.x; cull.my = q0.y; cull.A = q0.z; cull.B = q0.w; cull.C = q1.x; cull.thr = q2.w;
             vis = true;
         }
     }
-    gs_for_each_tile(vis, rect, v.gx, dbits, (uint32_t)i, [&](uint32_t tile, uint32_t d, uint32_t idx) {
+    gs_for_each_tile(vis, rect, v.gx, cull, dbits, (uint32_t)i, [&](uint32_t tile, uint32_t d, uint32_t idx) {
         const uint32_t pos = tile_off[tile] + atomicAdd(&tile_cur[tile], 1u);
         keys[pos] = ((unsigned long long)d << 32) | idx;
     });

@@ -5,33 +5,38 @@
 // identifyTileRanges (rasterizer_impl.cu:116-138).  Pairs were scattered into their tile's bucket by k_emit,
 // so each tile only has to order its own bucket by key = (depth_bits << 32 | gaussian_idx): identical order
 // to the reference's stable sort, whose ties (same tile, bit-identical depth) resolve by ascending Gaussian
-// index (emission order).  One CTA per tile: bucket -> shared memory, bitonic network for arbitrary n
-// (flip/half-cleaner form, all comparisons ascending, so the virtual +inf padding never moves), sorted
-// Gaussian indices -> list.  Buckets larger than the shared-memory capacity are sorted in place in global
-// memory by the same network (slow path, correctness only).
+// index (emission order).
+//   k_tile_sort      one WARP per tile for buckets up to 1024 keys (shared memory, __syncwarp only);
+//                    larger buckets are queued for
+//   k_tile_sort_big  one CTA per queued tile, up to 16384 keys in shared memory; beyond that the same network
+//                    runs in place in global memory (slow path, correctness only).
+// Sorting network: bitonic for arbitrary n (flip / half-cleaner form, every comparison ascending, so the virtual
+// +inf padding never moves and comparisons against it are simply skipped).
 #include "gs_common.cuh"
 
 namespace {
 
-constexpr int kSortThreads = 256;
-constexpr int kSmemKeys = 4096;     // 32 KB of u64 keys
+constexpr int kWarpsPerCta = 4;
+constexpr int kWarpKeys = 1024;      // 8 KB of u64 keys per warp
+constexpr int kBigThreads = 512;
+constexpr int kBigKeys = 16384;      // 128 KB dynamic shared memory
 
-template <typename Ptr>
-__device__ __forceinline__ void bitonic_sort_any_n(Ptr a, const int n, const int tid, const int nthreads) {
+template <typename Ptr, typename Sync>
+__device__ __forceinline__ void bitonic_sort_any_n(Ptr a, const int n, const int tid, const int nthreads, Sync sync) {
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     const int half = np2 >> 1;
     for (int k = 2; k <= np2; k <<= 1) {
-        // flip step: i pairs with the mirrored element of its k-block
-        for (int t = tid; t < half; t += nthreads) {
-            const int blk = t / (k >> 1), r = t - blk * (k >> 1);
+        const int hk = k >> 1;
+        for (int t = tid; t < half; t += nthreads) {      // flip: i pairs with its mirror inside the k-block
+            const int blk = t / hk, r = t - blk * hk;
             const int i = blk * k + r, j = blk * k + (k - 1 - r);
             if (j < n) {
                 const unsigned long long x = a[i], y = a[j];
                 if (x > y) { a[i] = y; a[j] = x; }
             }
         }
-        __syncthreads();
+        sync();
         for (int d = k >> 2; d >= 1; d >>= 1) {
             for (int t = tid; t < half; t += nthreads) {
                 const int i = ((t / d) * (d << 1)) + (t % d), j = i + d;
@@ -40,38 +45,76 @@ __device__ __forceinline__ void bitonic_sort_any_n(Ptr a, const int n, const int
                     if (x > y) { a[i] = y; a[j] = x; }
                 }
             }
-            __syncthreads();
+            sync();
         }
     }
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-k_tile_sort(const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ tile_cur,
-            const GsDevStatus* __restrict__ status, unsigned long long* __restrict__ keys,
-            uint32_t* __restrict__ list, long long capacity) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_tile_sort(int G, const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ tile_cur,
+            GsDevStatus* __restrict__ status, uint32_t* __restrict__ big_list,
+            const unsigned long long* __restrict__ keys, uint32_t* __restrict__ list, long long capacity) {
     if ((long long)status->num_pairs > capacity) return;
-    __shared__ unsigned long long s_keys[kSmemKeys];
-    const int tile = blockIdx.x;
+    __shared__ unsigned long long s_keys[kWarpsPerCta][kWarpKeys];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tile = blockIdx.x * kWarpsPerCta + wid;
+    if (tile >= G) return;
     const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
     const int n = (int)(end - beg);
-    if (threadIdx.x == 0) tile_cur[tile] = 0u;          // cursors back to zero for a possible re-render
+    if (lane == 0) tile_cur[tile] = 0u;                  // cursors back to zero for a possible re-render
     if (n == 0) return;
-    unsigned long long* g = keys + beg;
-    if (n <= kSmemKeys) {
-        for (int t = threadIdx.x; t < n; t += kSortThreads) s_keys[t] = g[t];
+    if (n > kWarpKeys) {
+        if (lane == 0) big_list[atomicAdd(&status->n_big, 1u)] = (uint32_t)tile;
+        return;
+    }
+    unsigned long long* a = s_keys[wid];
+    const unsigned long long* g = keys + beg;
+    for (int t = lane; t < n; t += 32) a[t] = g[t];
+    __syncwarp();
+    if (n > 1) bitonic_sort_any_n(a, n, lane, 32, [] { __syncwarp(); });
+    for (int t = lane; t < n; t += 32) list[beg + t] = (uint32_t)a[t];
+}
+
+__global__ void __launch_bounds__(kBigThreads)
+k_tile_sort_big(const uint32_t* __restrict__ tile_off, const GsDevStatus* __restrict__ status,
+                const uint32_t* __restrict__ big_list, unsigned long long* __restrict__ keys,
+                uint32_t* __restrict__ list, long long capacity) {
+    if ((long long)status->num_pairs > capacity) return;
+    extern __shared__ unsigned long long s_big[];
+    const unsigned nbig = status->n_big;
+    for (unsigned b = blockIdx.x; b < nbig; b += gridDim.x) {
+        const uint32_t tile = big_list[b];
+        const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
+        const int n = (int)(end - beg);
+        unsigned long long* g = keys + beg;
         __syncthreads();
-        if (n > 1) bitonic_sort_any_n(s_keys, n, threadIdx.x, kSortThreads);
-        for (int t = threadIdx.x; t < n; t += kSortThreads) list[beg + t] = (uint32_t)s_keys[t];
-    } else {
-        __syncthreads();
-        bitonic_sort_any_n(g, n, threadIdx.x, kSortThreads);
-        for (int t = threadIdx.x; t < n; t += kSortThreads) list[beg + t] = (uint32_t)g[t];
+        if (n <= kBigKeys) {
+            for (int t = threadIdx.x; t < n; t += kBigThreads) s_big[t] = g[t];
+            __syncthreads();
+            bitonic_sort_any_n(s_big, n, threadIdx.x, kBigThreads, [] { __syncthreads(); });
+            for (int t = threadIdx.x; t < n; t += kBigThreads) list[beg + t] = (uint32_t)s_big[t];
+        } else {
+            bitonic_sort_any_n(g, n, threadIdx.x, kBigThreads, [] { __syncthreads(); });
+            for (int t = threadIdx.x; t < n; t += kBigThreads) list[beg + t] = (uint32_t)g[t];
+        }
     }
 }
 
 }  // namespace
 
-void gs_launch_tile_sort(int G, const uint32_t* tile_off, uint32_t* tile_cur, const GsDevStatus* status,
-                         unsigned long long* keys, uint32_t* list, long long capacity, cudaStream_t s) {
-    k_tile_sort<<<G, kSortThreads, 0, s>>>(tile_off, tile_cur, status, keys, list, capacity);
+// per device, once (called from gs_context_create with the device current)
+void gs_tile_sort_init() {
+    cudaFuncSetAttribute(k_tile_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigKeys * 8);
+}
+
+void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
+                         uint32_t* big_list, unsigned long long* keys, uint32_t* list, long long capacity,
+                         cudaStream_t s, cudaEvent_t* prof) {
+    if (prof) cudaEventRecord(prof[0], s);
+    k_tile_sort<<<(G + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, s>>>(G, tile_off, tile_cur, status,
+                                                                                 big_list, keys, list, capacity);
+    if (prof) { cudaEventRecord(prof[1], s); cudaEventRecord(prof[2], s); }
+    const int grid = G < num_sms ? G : num_sms;
+    k_tile_sort_big<<<grid, kBigThreads, kBigKeys * 8, s>>>(tile_off, status, big_list, keys, list, capacity);
+    if (prof) cudaEventRecord(prof[3], s);
 }

@@ -1,0 +1,124 @@
+"""View-parallel host logic: the rasterizer path shards over independent camera views.
+
+The reference renders one camera per iteration on one GPU (luciddreamer.py:291-296) and has no multi-GPU code on
+this path; what is here is the natural data-parallel generalisation:
+
+  * `shard_views`      round-robin partition of a view list over ranks (no data-path collective)
+  * `GradBucket`       ONE flat per-Gaussian gradient buffer [xyz 3 | sh 3M | opacity 1 | scaling 3 | rotation 4]
+                       (59 floats at M = 16); the C ABI writes final gradients straight into views of it, so the
+                       shared-model step needs exactly one all-reduce and no packing copy
+  * `view_step`        forward+backward of one view through the C ABI, gradients into a bucket (no autograd)
+  * `allreduce_bucket` the single exchange step of a shared-model optimisation step (NCCL on GPUs, gloo in tests)
+  * `DensifyStats`     the statistics scene/gaussian_model.py:405-407 accumulates per view; norms do not commute
+                       with a gradient all-reduce, so the per-view norm is taken locally and only the [P,1]
+                       accumulators are reduced (sum / sum / max)
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Views {v : v mod world == rank} -- GPU g renders views g, g+world, ..."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    return list(range(rank, n_views, world))
+
+
+class GradBucket:
+    """Flat gradient bucket; `.flat` is what gets all-reduced, the named views are what the kernels write."""
+
+    def __init__(self, P: int, M: int, device, dtype=torch.float32):
+        self.P, self.M = int(P), int(M)
+        self.width = 3 + 3 * self.M + 1 + 3 + 4
+        self.flat = torch.zeros(self.P * self.width, dtype=dtype, device=device)
+        o = 0
+
+        def take(w, shape):
+            nonlocal o
+            v = self.flat[o:o + self.P * w].view(*shape)
+            o += self.P * w
+            return v
+
+        self.means3D = take(3, (self.P, 3))
+        self.shs = take(3 * self.M, (self.P, self.M, 3))
+        self.opacities = take(1, (self.P, 1))
+        self.scales = take(3, (self.P, 3))
+        self.rotations = take(4, (self.P, 4))
+
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+
+class DensifyStats:
+    """xyz_gradient_accum / denom / max_radii2D of scene/gaussian_model.py:151-155,405-407 and
+    luciddreamer.py:306-312, kept so that they can be reduced across ranks."""
+
+    def __init__(self, P: int, device):
+        self.xyz_gradient_accum = torch.zeros(P, 1, device=device)
+        self.denom = torch.zeros(P, 1, device=device)
+        self.max_radii2D = torch.zeros(P, device=device)
+
+    def add_view(self, dL_dmeans2D: torch.Tensor, radii: torch.Tensor) -> None:
+        vis = radii > 0
+        self.max_radii2D[vis] = torch.max(self.max_radii2D[vis], radii[vis].to(self.max_radii2D.dtype))
+        self.xyz_gradient_accum[vis] += torch.norm(dL_dmeans2D[vis, :2], dim=-1, keepdim=True)
+        self.denom[vis] += 1
+
+    def allreduce(self, group=None) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.xyz_gradient_accum, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.denom, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+
+def allreduce_bucket(bucket: GradBucket, group=None, average: bool = False, async_op: bool = False):
+    """Sum (or mean) of the per-rank gradient buckets: the only collective of a shared-model step."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    if average and not async_op:
+        bucket.flat.div_(dist.get_world_size(group))
+    return work
+
+
+def view_step(params: dict, settings, cotangent: torch.Tensor, bucket: Optional[GradBucket] = None,
+              means2D_grad: Optional[torch.Tensor] = None):
+    """Forward + backward of ONE view straight through the C ABI (no autograd graph).
+
+    params: dict(means3D, shs, opacities, scales, rotations) of CUDA tensors (activated values, like the
+    reference's render() passes them).  settings: GaussianRasterizationSettings.  Gradients of the five
+    parameter tensors are written into `bucket` (allocated if None).  Returns (color, depth, radii, bucket,
+    dL_dmeans2D)."""
+    from . import rasterizer as R
+
+    rs = settings
+    e = torch.empty(0)
+    prep = R._prepare(rs.bg, params["means3D"], e, params["opacities"], params["scales"], params["rotations"],
+                      rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+                      rs.image_width, params["shs"], rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+    _nr, color, depth, radii, geom, binning, img, cap = R._forward_impl(prep)
+    if bucket is None:
+        bucket = GradBucket(prep.P, prep.M, prep.device)
+    dm2 = means2D_grad if means2D_grad is not None else torch.empty((prep.P, 3), device=prep.device)
+    R._backward_impl(prep, radii, geom, binning, img, cap, cotangent, False, False,
+                     out=dict(dm3=bucket.means3D, dm2=dm2, dop=bucket.opacities, dsh=bucket.shs, dsc=bucket.scales,
+                              drot=bucket.rotations))
+    return color, depth, radii, bucket, dm2
+
+
+def render_views(params: dict, settings_list: Sequence, rank: int = 0, world: int = 1):
+    """Forward-only batch render of this rank's share of `settings_list` (config 4).  Returns {view: (color, depth)}."""
+    from . import rasterizer as R
+
+    out = {}
+    with torch.no_grad():
+        for v in shard_views(len(settings_list), rank, world):
+            rast = R.GaussianRasterizer(settings_list[v])
+            color, _radii, depth = rast(params["means3D"], torch.empty(0), params["opacities"], shs=params["shs"],
+                                        scales=params["scales"], rotations=params["rotations"])
+            out[v] = (color, depth)
+    return out

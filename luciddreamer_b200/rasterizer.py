@@ -132,19 +132,31 @@ def _forward_impl(prep: _Prepared):
     return int(counts.num_rendered), color, depth, radii, geom, binning, img, cap
 
 
-def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, want_colors: bool, want_cov: bool):
+def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, want_colors: bool, want_cov: bool,
+                   out: Optional[dict] = None):
+    """`out` (optional): pre-allocated contiguous f32 destinations keyed dm3/dm2/dop/dsh/dsc/drot -- e.g. views of
+    a flat multiview.GradBucket -- that the kernels write instead of fresh tensors (every row is overwritten)."""
     L = N.lib()
+    out = out or {}
     f, dev, P, M = prep.frame, prep.device, prep.P, prep.M
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     with torch.cuda.device(idx):
         stream = torch.cuda.current_stream(idx).cuda_stream
         f32 = dict(dtype=torch.float32, device=dev)
         g = N.GsGrads()
-        dm3 = torch.empty((P, 3), **f32); dm2 = torch.empty((P, 3), **f32)
-        dop = torch.empty((P, 1), **f32)
-        dsh = torch.empty((P, M, 3), **f32)
-        dsc = torch.empty((P, 3), **f32) if f.scales else torch.zeros((P, 3), **f32)
-        drot = torch.empty((P, 4), **f32) if f.rotations else torch.zeros((P, 4), **f32)
+        def dst(key, shape, zero=False):
+            t = out.get(key)
+            if t is not None:
+                if tuple(t.shape) != tuple(shape) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+                    raise RuntimeError(f"gradient sink '{key}' must be a contiguous f32 {tuple(shape)} tensor on {dev}")
+                return t.zero_() if zero else t
+            return torch.zeros(shape, **f32) if zero else torch.empty(shape, **f32)
+
+        dm3 = dst("dm3", (P, 3)); dm2 = dst("dm2", (P, 3))
+        dop = dst("dop", (P, 1))
+        dsh = dst("dsh", (P, M, 3))
+        dsc = dst("dsc", (P, 3), zero=not f.scales)
+        drot = dst("drot", (P, 4), zero=not f.rotations)
         dcol = torch.empty((P, 3), **f32) if want_colors else None
         dcov = torch.empty((P, 6), **f32) if want_cov else None
         g.dL_dmeans3D, g.dL_dmeans2D, g.dL_dopacity = dm3.data_ptr(), dm2.data_ptr(), dop.data_ptr()
@@ -229,12 +241,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.prep = prep                       # keeps the contiguous f32 inputs alive + the filled GsFrame
         ctx.save_for_backward(radii, geom, binning, img)
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)      # no zero-fill kernels for the unused grad_radii / grad_depth
         return color, radii, depth
 
     @staticmethod
     def backward(ctx, grad_out_color, grad_radii, grad_depth):
         radii, geom, binning, img = ctx.saved_tensors
         prep = ctx.prep
+        if grad_out_color is None:            # only depth was used downstream: depth carries no gradient
+            grad_out_color = torch.zeros((3, prep.frame.H, prep.frame.W), dtype=torch.float32, device=prep.device)
         f = prep.frame
         want_colors = bool(f.colors_precomp)
         want_cov = bool(f.cov3D_precomp)

@@ -1,0 +1,255 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the reference-shaped
+operator API / `_C` surface (which sits directly on the C ABI), against
+  (1) the golden vectors of the reference CUDA rasterizer,   (2) the CPU oracle on the same seeded inputs,
+  (3) the reference CUDA library itself when oracle/_ref travelled with the repo,
+plus size-independent properties at the full BASELINE config-3 size."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import util
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = [c for c in cases.CASES if c.golden]
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def run_C(inp, cot=None):
+    """Through the `_C`-compatible surface (reference binding signatures)."""
+    from luciddreamer_b200.rasterizer import _C
+    d = dev()
+    args = cases.binding_args(inp, d)
+    nr, color, depth, radii, geom, binning, img = _C.rasterize_gaussians(*args)
+    out = dict(num_rendered=nr, color=color, depth=depth, radii=radii, bufs=(geom, binning, img))
+    if cot is not None:
+        (bg, means3D, colors, opacity, scales, rotations, mod, cov, vm, pm, tfx, tfy, H, W, sh, D, campos, _p, dbg) = args
+        g = _C.rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rotations, mod, cov, vm, pm, tfx, tfy,
+                                            cot.to(d), torch.zeros(1, H, W, device=d), sh, D, campos, geom, nr,
+                                            binning, img, dbg)
+        out["grads"] = dict(zip(cases.GRAD_NAMES, [t.cpu().numpy() for t in g]))
+    torch.cuda.synchronize()
+    return out
+
+
+def grad_names(case):
+    names = set(cases.GRAD_NAMES)
+    if case.precomp:
+        names -= {"dL_dsh", "dL_dscales", "dL_drotations"}
+    else:
+        names -= {"dL_dcov3D", "dL_dcolors"} if False else set()
+    return names
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[c.name for c in GOLDEN])
+def test_cuda_matches_reference_golden(case):
+    gold = util.load_golden(case.name)
+    inp = cases.build_inputs(case)
+    r = run_C(inp, inp["cot"])
+    assert r["num_rendered"] == gold["num_rendered"]
+    util.assert_forward_close(r["color"].cpu().numpy(), r["depth"].cpu().numpy(), r["radii"].cpu().numpy(), gold,
+                              what=case.name)
+    util.assert_grads_close(r["grads"], gold["grads"], names=grad_names(case), what=case.name)
+
+
+@pytest.mark.parametrize("case", GOLDEN[:6], ids=[c.name for c in GOLDEN[:6]])
+def test_cuda_matches_cpu_oracle(case):
+    from oracle import oracle
+    inp = cases.build_inputs(case)
+    f = oracle.rasterize_gaussians(*cases.binding_args(inp))
+    og = dict(zip(cases.GRAD_NAMES, oracle.rasterize_gaussians_backward(f, inp["cot"].numpy())[:8]))
+    r = run_C(inp, inp["cot"])
+    gold = dict(color=f.color, depth=f.depth, radii=f.radii)
+    util.assert_forward_close(r["color"].cpu().numpy(), r["depth"].cpu().numpy(), r["radii"].cpu().numpy(), gold,
+                              what=case.name)
+    util.assert_grads_close(r["grads"], og, names=grad_names(case), what=case.name)
+    inv = f.radii == 0
+    for k, a in r["grads"].items():
+        if a.size:
+            assert not np.any(a.reshape(a.shape[0], -1)[inv]), f"{k}: invisible rows must be exactly zero"
+
+
+def test_autograd_api_matches_golden_and_reference_semantics():
+    """Through GaussianRasterizer (the call gaussian_renderer.render() makes), incl. non-contiguous inputs."""
+    from luciddreamer_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    case = cases.BY_NAME["rot40_5k_128x72"]
+    gold = util.load_golden(case.name)
+    inp = cases.build_inputs(case)
+    d = dev()
+    cam = inp["cam"]
+    rs = GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, inp["bg"].to(d),
+                                       case.scale_modifier, cam.viewmatrix.to(d), cam.projmatrix.to(d), case.D,
+                                       cam.campos.to(d), False, False)
+    # non-contiguous means (transposed storage) must be accepted like the reference's .contiguous()
+    means = inp["means3D"].to(d).t().contiguous().t().requires_grad_(True)
+    assert not means.is_contiguous()
+    leaves = {k: inp[k].to(d).requires_grad_(True) for k in ("shs", "opacities", "scales", "rotations")}
+    m2 = torch.zeros(case.P, 3, device=d, requires_grad=True)
+    screenspace = m2 + 0
+    screenspace.retain_grad()
+    color, radii, depth = GaussianRasterizer(rs)(means3D=means, means2D=screenspace, opacities=leaves["opacities"],
+                                                 shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+    assert color.shape == (3, case.H, case.W) and depth.shape == (1, case.H, case.W) and radii.dtype == torch.int32
+    assert not radii.requires_grad
+    (color * inp["cot"].to(d)).sum().backward()
+    util.assert_forward_close(color.detach().cpu().numpy(), depth.detach().cpu().numpy(), radii.cpu().numpy(), gold)
+    got = {"dL_dmeans3D": means.grad, "dL_dmeans2D": screenspace.grad, "dL_dsh": leaves["shs"].grad,
+           "dL_dopacity": leaves["opacities"].grad, "dL_dscales": leaves["scales"].grad,
+           "dL_drotations": leaves["rotations"].grad}
+    util.assert_grads_close({k: v.cpu().numpy() for k, v in got.items()}, gold["grads"])
+    assert float(screenspace.grad[:, 2].abs().max()) == 0.0          # z column of dL_dmeans2D is 0 (A.8)
+
+
+def test_backward_twice_and_linearity():
+    """retain_graph double backward re-arms the accumulators; gradients are linear in the cotangent."""
+    from luciddreamer_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    case = cases.BY_NAME["stress_4k_96_x6"]
+    inp = cases.build_inputs(case)
+    d = dev()
+    cam = inp["cam"]
+    rs = GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, inp["bg"].to(d), 1.0,
+                                       cam.viewmatrix.to(d), cam.projmatrix.to(d), case.D, cam.campos.to(d), False, False)
+    op = inp["opacities"].to(d).requires_grad_(True)
+    sh = inp["shs"].to(d).requires_grad_(True)
+    color, _, _ = GaussianRasterizer(rs)(inp["means3D"].to(d), torch.zeros(case.P, 3, device=d), op, shs=sh,
+                                         scales=inp["scales"].to(d), rotations=inp["rotations"].to(d))
+    w = inp["cot"].to(d)
+    g1 = torch.autograd.grad(color, [op, sh], grad_outputs=w, retain_graph=True)
+    g2 = torch.autograd.grad(color, [op, sh], grad_outputs=2 * w, retain_graph=True)
+    g3 = torch.autograd.grad(color, [op, sh], grad_outputs=w)
+    for a, b, c in zip(g1, g2, g3):
+        assert util.rel_err(b.cpu().numpy(), 2 * a.cpu().numpy()) < 1e-5
+        assert util.rel_err(c.cpu().numpy(), a.cpu().numpy()) < 1e-5
+
+
+def test_zero_gaussians():
+    from luciddreamer_b200.rasterizer import _C
+    d = dev()
+    cam = cases.build_inputs(cases.BY_NAME["micro_1k_64"])["cam"]
+    e = torch.zeros(0, 3, device=d)
+    nr, color, depth, radii, *_ = _C.rasterize_gaussians(
+        torch.ones(3, device=d), e, torch.empty(0), torch.zeros(0, 1, device=d), e, torch.zeros(0, 4, device=d), 1.0,
+        torch.empty(0), cam.viewmatrix.to(d), cam.projmatrix.to(d), cam.tanfovx, cam.tanfovy, 64, 64,
+        torch.zeros(0, 16, 3, device=d), 3, cam.campos.to(d), False, False)
+    assert nr == 0 and radii.numel() == 0
+    assert float(color.abs().max()) == 0.0 and float(depth.abs().max()) == 0.0
+
+
+def test_mark_visible():
+    from luciddreamer_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    from oracle import oracle
+    inp = cases.build_inputs(cases.BY_NAME["llff_5k_128x72"])
+    d = dev()
+    cam = inp["cam"]
+    rs = GaussianRasterizationSettings(72, 128, cam.tanfovx, cam.tanfovy, inp["bg"].to(d), 1.0, cam.viewmatrix.to(d),
+                                       cam.projmatrix.to(d), 3, cam.campos.to(d), False, False)
+    vis = GaussianRasterizer(rs).markVisible(inp["means3D"].to(d))
+    assert vis.dtype == torch.bool
+    assert np.array_equal(vis.cpu().numpy(), oracle.mark_visible(inp["means3D"], cam.viewmatrix))
+
+
+def test_binning_order_matches_oracle():
+    """Integer pipeline, bit-exact: per-tile lists of the CUDA path are the oracle's lists minus pairs that cannot
+    contribute (exact tile culling), in the same (depth, index) order."""
+    import ctypes as C
+    from luciddreamer_b200 import _native as N
+    from luciddreamer_b200 import rasterizer as R
+    from oracle import oracle
+    case = cases.BY_NAME["stress_4k_96_x6"]
+    inp = cases.build_inputs(case)
+    d = dev()
+    f = oracle.rasterize_gaussians(*cases.binding_args(inp))
+    prep = R._prepare(*cases.binding_args(inp, d))
+    nr, color, depth, radii, geom, binning, img, cap = R._forward_impl(prep)
+    assert nr == f.num_rendered
+    G = ((case.W + 15) // 16) * ((case.H + 15) // 16)
+    off = torch.empty(G + 1, dtype=torch.int32, device=d)
+    lst = torch.empty(cap, dtype=torch.int32, device=d)
+    N.check(N.lib().gs_debug_export_binning(C.byref(prep.frame), binning.data_ptr(), cap, img.data_ptr(), off.data_ptr(),
+                                            lst.data_ptr(), cap, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    off = off.cpu().numpy().astype(np.int64); lst = lst.cpu().numpy().astype(np.int64)
+    assert off[-1] <= nr
+    opl, orng = f.point_list.astype(np.int64), f.ranges.astype(np.int64)
+    depths = f.geom("depths", 1)[:, 0]
+    for t in range(G):
+        mine = lst[off[t]:off[t + 1]]
+        ref = opl[orng[t, 0]:orng[t, 1]]
+        assert set(mine) <= set(ref)
+        # same relative order as the reference list
+        pos = {g: i for i, g in enumerate(ref)}
+        idx = [pos[g] for g in mine]
+        assert idx == sorted(idx)
+        key = [(depths[g], g) for g in mine]
+        assert key == sorted(key)
+
+
+def test_capacity_growth_and_many_views_in_flight():
+    """Small scene then a much larger one (speculative capacity too small -> device guard -> re-render), and several
+    views enqueued back to back on two streams without host syncs in between."""
+    from luciddreamer_b200.rasterizer import _C
+    d = dev()
+    small = cases.build_inputs(cases.BY_NAME["micro_1k_64"])
+    big = cases.build_inputs(cases.BY_NAME["cfg2_100k_512"])
+    gold = util.load_golden("cfg2_100k_512")
+    _C.rasterize_gaussians(*cases.binding_args(small, d))
+    nr, color, depth, radii, *_ = _C.rasterize_gaussians(*cases.binding_args(big, d))
+    torch.cuda.synchronize()
+    assert nr == gold["num_rendered"]
+    util.assert_forward_close(color.cpu().numpy(), depth.cpu().numpy(), radii.cpu().numpy(), gold)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    args = cases.binding_args(big, d)
+    torch.cuda.synchronize()
+    for k in range(6):
+        with torch.cuda.stream(s1 if k % 2 == 0 else s2):
+            outs.append(_C.rasterize_gaussians(*args)[1])
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])            # forward is deterministic, bit for bit
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_cuda", fromlist=["x"]).available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scale_mult", [1.0, 4.0])
+def test_full_size_against_live_reference(scale_mult):
+    """BASELINE config 3 (1 M Gaussians, 1080p, SH 3) against the reference CUDA library on the same GPU."""
+    from luciddreamer_b200 import synthetic as syn
+    from luciddreamer_b200.rasterizer import _C
+    from oracle import ref_cuda
+    d = dev()
+    P, W, H, D = 1_000_000, 1920, 1080, 3
+    sc = {k: v.to(d) for k, v in syn.make_scene(P, 1003, scale_mult=scale_mult).items()}
+    cam = syn.make_camera(W, H)
+    cot = syn.make_cotangent(H, W, 1003).to(d)
+    bg = torch.zeros(3, device=d)
+    vm, pm, cp = cam.viewmatrix.to(d), cam.projmatrix.to(d), cam.campos.to(d)
+    e = torch.empty(0)
+    nr, color, depth, radii, geom, binning, img = _C.rasterize_gaussians(
+        bg, sc["means3D"], e, sc["opacities"], sc["scales"], sc["rotations"], 1.0, e, vm, pm, cam.tanfovx, cam.tanfovy,
+        H, W, sc["shs"], D, cp, False, False)
+    g = _C.rasterize_gaussians_backward(bg, sc["means3D"], radii, e, sc["scales"], sc["rotations"], 1.0, e, vm, pm,
+                                        cam.tanfovx, cam.tanfovy, cot, torch.zeros(1, H, W, device=d), sc["shs"], D, cp,
+                                        geom, nr, binning, img, False)
+    rc = ref_cuda.RefContext()
+    R, rcol, rdep, rrad = ref_cuda.rasterize_gaussians(rc, bg, sc["means3D"], None, sc["opacities"], sc["scales"],
+                                                       sc["rotations"], 1.0, None, vm, pm, cam.tanfovx, cam.tanfovy, H, W,
+                                                       sc["shs"], D, cp)
+    rg = ref_cuda.rasterize_gaussians_backward(rc, rrad, cot)
+    torch.cuda.synchronize()
+    assert nr == R
+    gold = dict(color=rcol.cpu().numpy(), depth=rdep.cpu().numpy(), radii=rrad.cpu().numpy())
+    info = util.assert_forward_close(color.cpu().numpy(), depth.cpu().numpy(), radii.cpu().numpy(), gold, what="config 3")
+    print("config-3 forward parity:", info)
+    mine = dict(zip(cases.GRAD_NAMES, [t.cpu().numpy() for t in g]))
+    ref = dict(zip(cases.GRAD_NAMES, [t.cpu().numpy() for t in rg[:8]]))
+    errs = util.assert_grads_close(mine, ref, names={"dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dscales",
+                                                     "dL_drotations"}, what="config 3")
+    print("config-3 gradient rel errors:", errs)
+    inv = gold["radii"] == 0
+    for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity"):
+        assert not np.any(mine[k].reshape(P, -1)[inv])
