@@ -239,7 +239,37 @@ __device__ __forceinline__ void gs_sh_basis(int deg, float x, float y, float z, 
     }
 }
 
-__device__ __forceinline__ float4 gs_ldg4(const float4* p) { return __ldg(p); }
+#define GS_REC_V4 3          // float4s per splat record
+#define GS_CULL_SLACK 0.01f  // in units of `power` (~1 % in alpha): keeps the culling tests conservative
+
+// Can a splat reach alpha >= 1/255 at some pixel of the box [x0,x1] x [y0,y1] (pixel-centre coordinates)?
+// power(d) = -0.5 (A dx^2 + C dy^2) - B dx dy is concave with maximum 0 at the mean (mx,my): its maximum over the
+// box is 0 if the mean is inside, otherwise it lies on an edge facing the mean, and each facing edge is a 1-D
+// concave maximisation (clamp the stationary point to the edge).  thr = -ln(255 * opacity) - GS_CULL_SLACK, so
+// "max power >= thr" is a conservative superset of "some pixel has alpha >= 1/255".  NaNs answer true (keep).
+__device__ __forceinline__ bool gs_box_hit(float mx, float my, float A, float B, float C, float thr, float x0,
+                                           float y0, float x1, float y1) {
+    const bool in_x = mx >= x0 && mx <= x1, in_y = my >= y0 && my <= y1;
+    if (in_x && in_y) return !(thr > 0.f);
+    float best = -3.0e38f;
+    if (!in_x) {                                         // facing vertical edge
+        const float ex = mx < x0 ? x0 : x1;
+        const float dx = mx - ex;
+        float py = my + B * dx / C;                      // stationary point along the edge
+        py = fminf(y1, fmaxf(y0, py));
+        const float dy = my - py;
+        best = fmaxf(best, -0.5f * (A * dx * dx + C * dy * dy) - B * dx * dy);
+    }
+    if (!in_y) {                                         // facing horizontal edge
+        const float ey = my < y0 ? y0 : y1;
+        const float dy = my - ey;
+        float px = mx + B * dy / A;
+        px = fminf(x1, fmaxf(x0, px));
+        const float dx = mx - px;
+        best = fmaxf(best, -0.5f * (A * dx * dx + C * dy * dy) - B * dx * dy);
+    }
+    return !(best < thr);
+}
 
 // launchers (defined in the .cu files, used by gs_api.cu)
 struct GsFrame;

@@ -23,30 +23,9 @@ constexpr int kBigRect = 32;   // rects with more tiles than this are walked by 
 // dropped are skipped by every pixel of the tile in the reference too (forward.cu:336-346), so no output changes.
 // __noinline__: the histogram pass (k_preprocess) and the emission pass (k_emit) must take bit-identical
 // decisions, so both call the same machine code on the same stored floats.
-#define GS_CULL_SLACK 0.01f
 __device__ __noinline__ bool gs_tile_hit(float mx, float my, float A, float B, float C, float thr, int tx, int ty) {
-    const float x0 = (float)(tx * GS_TILE), x1 = x0 + (float)(GS_TILE - 1);
-    const float y0 = (float)(ty * GS_TILE), y1 = y0 + (float)(GS_TILE - 1);
-    const bool in_x = mx >= x0 && mx <= x1, in_y = my >= y0 && my <= y1;
-    if (in_x && in_y) return !(thr > 0.f);          // NaN anywhere => keep the pair (conservative)
-    float best = -3.0e38f;
-    if (!in_x) {                                         // facing vertical edge
-        const float ex = mx < x0 ? x0 : x1;
-        const float dx = mx - ex;
-        float py = my + B * dx / C;                      // stationary point along the edge
-        py = fminf(y1, fmaxf(y0, py));
-        const float dy = my - py;
-        best = fmaxf(best, -0.5f * (A * dx * dx + C * dy * dy) - B * dx * dy);
-    }
-    if (!in_y) {                                         // facing horizontal edge
-        const float ey = my < y0 ? y0 : y1;
-        const float dy = my - ey;
-        float px = mx + B * dy / A;
-        px = fminf(x1, fmaxf(x0, px));
-        const float dx = mx - px;
-        best = fmaxf(best, -0.5f * (A * dx * dx + C * dy * dy) - B * dx * dy);
-    }
-    return !(best < thr);
+    const float x0 = (float)(tx * GS_TILE), y0 = (float)(ty * GS_TILE);
+    return gs_box_hit(mx, my, A, B, C, thr, x0, y0, x0 + (float)(GS_TILE - 1), y0 + (float)(GS_TILE - 1));
 }
 
 struct GsCullArgs {
