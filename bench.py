@@ -112,16 +112,17 @@ def view_pose(rank: int, step: int = 0):
 
 def alg_bytes(P, Pv, pairs, N, G, M):
     """Algorithmic (compulsory) HBM bytes per launch of each kernel -- DESIGN.md section 4 states the model."""
-    vis_in = 12 + 16 + 4 + 12 * M
     return {
-        "k_preprocess": 12 * P + Pv * vis_in + 4 * P + 96 * Pv + 4 * pairs,
+        "k_project": 12 * P + 4 * P + Pv * (12 + 16 + 4 + 32 + 4),
+        "k_shade_count": Pv * (4 + 32 + 12 + 12 * M + 4 + 32 + 48) + 4 * pairs,
         "k_tile_scan": 12 * G,
-        "k_emit": 4 * P + 48 * Pv + 8 * pairs + 4 * pairs,
+        "k_emit": Pv * (4 + 48 + 4) + 8 * pairs + 4 * pairs,
         "k_tile_sort": 8 * pairs + 4 * pairs,
         "k_tile_sort_big": 0,
         "k_blend_fwd": 4 * pairs + 48 * Pv + 24 * N,
         "k_blend_bwd": 20 * N + 4 * pairs + 48 * Pv + 72 * Pv,
-        "k_gauss_bwd": 4 * P + (12 + 12 + 12 * M + 4 + 12 + 16) * P + Pv * (12 + 12 + 16 + 12 * M + 16 + 96),
+        "k_grad_vis": Pv * (4 + 96 + 16 + 12 + 12 + 16 + 12 * M + 176),
+        "k_grad_write": 4 * P + (12 + 12 + 12 * M + 4 + 12 + 16) * P + Pv * (16 + 176),
     }
 
 
@@ -157,7 +158,7 @@ class Ours:
         self.settings = R.GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
                                                         self.bg, 1.0, self.vm, self.pm, D, self.cp, False, False)
         self.rast = R.GaussianRasterizer(self.settings)
-        self.kernels_per_step = 8
+        self.kernels_per_step = 10
         self.last = None
 
     def step(self, cot):

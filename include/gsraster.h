@@ -130,9 +130,11 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
 /* replaces Rasterizer::backward (rasterizer_impl.cu:343-444) + the nine torch::zeros of its binding.
  * dL_dout_depth is accepted and ignored: the reference's depth gradient is commented out
  * (backward.cu:443-469,539-554). */
+size_t gs_backward_scratch_bytes(int64_t num_visible);   /* num_visible from gs_forward_counts (or P as a bound) */
 int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
-                const void* binning_buffer, int64_t pair_capacity, const void* image_buffer,
-                const float* dL_dout_color, const float* dL_dout_depth, const GsGrads* grads, gs_stream_t stream);
+                const void* binning_buffer, int64_t pair_capacity, const void* image_buffer, void* grad_scratch,
+                size_t grad_scratch_bytes, const float* dL_dout_color, const float* dL_dout_depth,
+                const GsGrads* grads, gs_stream_t stream);
 
 /* replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153): present[i] = (z_view > 0.2) */
 int gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
@@ -149,7 +151,7 @@ int gs_debug_export_binning(const GsFrame* f, const void* binning_buffer, int64_
  * SURVEY.md section 5).  When enabled, every kernel launch is bracketed by CUDA events on the launching stream;
  * gs_profile_read waits for them and returns the duration in ms of each kernel of the most recent forward /
  * backward (-1 = not launched).  Kernel i is named gs_profile_kernel_name(i), i < gs_profile_num_kernels(). */
-#define GS_NUM_KERNELS 8
+#define GS_NUM_KERNELS 10
 int gs_profile_enable(GsContext* ctx, int on);
 int gs_profile_num_kernels(void);
 const char* gs_profile_kernel_name(int i);

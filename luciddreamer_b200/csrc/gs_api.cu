@@ -76,8 +76,9 @@ int debug_sync(const GsFrame* f, cudaStream_t s, const char* what) {
 }  // namespace
 
 constexpr int kNumKernels = GS_NUM_KERNELS;
-static const char* const kKernelNames[kNumKernels] = {"k_preprocess", "k_tile_scan", "k_emit", "k_tile_sort",
-                                                      "k_tile_sort_big", "k_blend_fwd", "k_blend_bwd", "k_gauss_bwd"};
+static const char* const kKernelNames[kNumKernels] = {"k_project", "k_tile_scan", "k_emit", "k_tile_sort",
+                                                      "k_tile_sort_big", "k_blend_fwd", "k_blend_bwd", "k_grad_vis",
+                                                      "k_shade_count", "k_grad_write"};
 
 struct GsContext {
     int device;
@@ -136,6 +137,7 @@ int gs_context_create(int device, GsContext** out) {
     c->num_sms = 148;
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     gs_tile_sort_init();
+    gs_grad_write_init();
     cudaError_t e = cudaHostAlloc((void**)&c->slots, sizeof(GsDevStatus) * kSlots, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; cudaSetDevice(prev); return fail(GS_ECUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->slots, 0, sizeof(GsDevStatus) * kSlots);
@@ -177,10 +179,12 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     GS_CUDA(cudaMemsetAsync(il.tile_cnt, 0, (size_t)((char*)il.status - (char*)il.tile_cnt) + sizeof(GsDevStatus), s));
     if (f->P > 0) {
         GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
-        GS_TIMED(ctx, 0, s, gs_launch_preprocess(v, f->means3D, f->shs, f->colors_precomp, f->opacities, f->scales,
-                                                 f->rotations, f->cov3D_precomp, radii, gl.rec, gl.acc, il.tile_cnt,
-                                                 il.status, s));
-        if ((rc = debug_sync(f, s, "preprocess"))) return rc;
+        GS_TIMED(ctx, 0, s, gs_launch_project(v, f->means3D, f->opacities, f->scales, f->rotations, f->cov3D_precomp,
+                                              radii, gl.rec, gl.vis_list, il.status, s));
+        if ((rc = debug_sync(f, s, "project"))) return rc;
+        GS_TIMED(ctx, 8, s, gs_launch_shade_count(v, ctx->num_sms, f->means3D, f->shs, f->colors_precomp, radii, gl.rec,
+                                                  gl.acc, gl.vis_list, il.tile_cnt, il.status, s));
+        if ((rc = debug_sync(f, s, "shade_count"))) return rc;
     }
     GsDevStatus* dev_slot = nullptr;
     GS_CUDA(cudaHostGetDevicePointer((void**)&dev_slot, host_slot, 0));
@@ -221,7 +225,8 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
     GsImageLayout il = gs_image_layout(image_buffer, f->W, f->H);
     GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
     GsBinLayout bl = gs_bin_layout(binning_buffer, pair_capacity > 0 ? pair_capacity : 1);
-    GS_TIMED(ctx, 2, s, gs_launch_emit(v, radii, gl.rec, il.tile_off, il.tile_cnt, il.status, bl.keys, pair_capacity, s));
+    GS_TIMED(ctx, 2, s, gs_launch_emit(v, ctx ? ctx->num_sms : 148, radii, gl.rec, gl.vis_list, il.tile_off, il.tile_cnt,
+                                       il.status, bl.keys, pair_capacity, s));
     if ((rc = debug_sync(f, s, "emit"))) return rc;
     {
         const bool prof = ctx && ctx->profile;
@@ -237,16 +242,22 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
     return GS_OK;
 }
 
+size_t gs_backward_scratch_bytes(int64_t num_visible) {
+    return gs_align_up((size_t)(num_visible > 0 ? num_visible : 1) * GS_GOUT_FLOATS * sizeof(float), 256);
+}
+
 int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
-                const void* binning_buffer, int64_t pair_capacity, const void* image_buffer,
-                const float* dL_dout_color, const float* dL_dout_depth, const GsGrads* grads, gs_stream_t stream) {
+                const void* binning_buffer, int64_t pair_capacity, const void* image_buffer, void* grad_scratch,
+                size_t grad_scratch_bytes, const float* dL_dout_color, const float* dL_dout_depth,
+                const GsGrads* grads, gs_stream_t stream) {
     (void)dL_dout_depth;                                 // depth gradient disabled in the reference
     int rc = check_frame(f);
     if (rc) return rc;
     if (!grads) return fail(GS_EINVAL, "grads is NULL");
     if (f->P == 0) return GS_OK;
-    if (!radii || !geom_buffer || !binning_buffer || !image_buffer || !dL_dout_color)
+    if (!radii || !geom_buffer || !binning_buffer || !image_buffer || !dL_dout_color || !grad_scratch)
         return fail(GS_EINVAL, "radii / scratch / dL_dout_color is NULL");
+    (void)grad_scratch_bytes;   // sized by the caller with gs_backward_scratch_bytes(num_visible)
     cudaStream_t s = (cudaStream_t)stream;
     const GsView v = make_view(f);
     GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
@@ -259,10 +270,14 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
     g.dmeans3D = grads->dL_dmeans3D; g.dmeans2D = grads->dL_dmeans2D; g.dsh = f->shs ? grads->dL_dsh : nullptr;
     g.dcolors = grads->dL_dcolors; g.dopacity = grads->dL_dopacity;
     g.dscales = grads->dL_dscales; g.drots = grads->dL_drotations; g.dcov3D = grads->dL_dcov3D;
-    GS_TIMED(ctx, 7, s, gs_launch_gauss_bwd(v, radii, f->means3D, f->shs, f->cov3D_precomp ? nullptr : f->scales,
-                                                f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec,
-                                                gl.acc, g, s));
-    if ((rc = debug_sync(f, s, "gauss_bwd"))) return rc;
+    float* gout = (float*)grad_scratch;
+    GS_TIMED(ctx, 7, s, gs_launch_grad_vis(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs,
+                                           f->cov3D_precomp ? nullptr : f->scales,
+                                           f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec, gl.acc,
+                                           gl.vis_list, il.status, gout, s));
+    if ((rc = debug_sync(f, s, "grad_vis"))) return rc;
+    GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, s));
+    if ((rc = debug_sync(f, s, "grad_write"))) return rc;
     // outputs the fused kernel does not produce in this input mode are defined as zeros (reference: torch::zeros)
     const size_t Ps = (size_t)f->P;
     if (!f->shs && grads->dL_dsh && f->M > 0) GS_CUDA(cudaMemsetAsync(grads->dL_dsh, 0, Ps * f->M * 3 * sizeof(float), s));

@@ -57,8 +57,9 @@ __host__ inline GsImageLayout gs_image_layout(void* base, int W, int H) {
 }
 
 struct GsGeomLayout {
-    float4* rec;   // [P][3]
-    float4* acc;   // [P][3]
+    float4* rec;          // [P][3]
+    float4* acc;          // [P][3]
+    uint32_t* vis_list;   // [P] compact list of visible Gaussian indices (first num_visible entries valid)
     size_t bytes;
 };
 __host__ inline GsGeomLayout gs_geom_layout(void* base, int P) {
@@ -67,9 +68,12 @@ __host__ inline GsGeomLayout gs_geom_layout(void* base, int P) {
     size_t off = 0;
     L.rec = (float4*)(p + off); off = gs_align_up(off + (size_t)P * 48, 256);
     L.acc = (float4*)(p + off); off = gs_align_up(off + (size_t)P * 48, 256);
+    L.vis_list = (uint32_t*)(p + off); off = gs_align_up(off + (size_t)P * 4, 256);
     L.bytes = off;
     return L;
 }
+
+#define GS_GOUT_FLOATS 44    // compact per-visible-Gaussian gradient row (gs_gauss_bwd.cu)
 
 struct GsBinLayout {
     unsigned long long* keys;
@@ -272,16 +276,20 @@ __device__ __forceinline__ bool gs_box_hit(float mx, float my, float A, float B,
 }
 
 // launchers (defined in the .cu files, used by gs_api.cu)
-struct GsFrame;
-void gs_launch_preprocess(const GsView& v, const float* means3D, const float* shs, const float* colors_precomp,
-                          const float* opacities, const float* scales, const float* rotations,
-                          const float* cov3D_precomp, int* radii, float4* rec, float4* acc, uint32_t* tile_cnt,
-                          GsDevStatus* status, cudaStream_t s);
+struct GsGradPtrs {
+    float *dmeans3D, *dmeans2D, *dsh, *dcolors, *dopacity, *dscales, *drots, *dcov3D;
+};
+void gs_launch_project(const GsView& v, const float* means3D, const float* opacities, const float* scales,
+                       const float* rotations, const float* cov3D_precomp, int* radii, float4* rec,
+                       uint32_t* vis_list, GsDevStatus* status, cudaStream_t s);
+void gs_launch_shade_count(const GsView& v, int num_sms, const float* means3D, const float* shs,
+                           const float* colors_precomp, const int* radii, float4* rec, float4* acc,
+                           const uint32_t* vis_list, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s);
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status,
                          GsDevStatus* host_slot, cudaStream_t s);
-void gs_launch_emit(const GsView& v, const int* radii, const float4* rec, const uint32_t* tile_off,
-                    uint32_t* tile_cur, GsDevStatus* status, unsigned long long* keys, long long capacity,
-                    cudaStream_t s);
+void gs_launch_emit(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
+                    const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status, unsigned long long* keys,
+                    long long capacity, cudaStream_t s);
 void gs_tile_sort_init();
 void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
                          uint32_t* big_list, unsigned long long* keys, uint32_t* list, long long capacity,
@@ -292,10 +300,10 @@ void gs_launch_blend_fwd(const GsView& v, const uint32_t* tile_off, const uint32
 void gs_launch_blend_bwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float4* acc,
                          cudaStream_t s);
-struct GsGradPtrs {
-    float *dmeans3D, *dmeans2D, *dsh, *dcolors, *dopacity, *dscales, *drots, *dcov3D;
-};
-void gs_launch_gauss_bwd(const GsView& v, const int* radii, const float* means3D, const float* shs,
-                         const float* scales, const float* rotations, const float* cov3D_precomp,
-                         const float4* rec, float4* acc, GsGradPtrs g, cudaStream_t s);
+void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
+                        const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
+                        const uint32_t* vis_list, const GsDevStatus* status, float* gout, cudaStream_t s);
+void gs_grad_write_init();
+void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
+                          cudaStream_t s);
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);

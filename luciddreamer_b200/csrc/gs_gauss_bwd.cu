@@ -1,101 +1,43 @@
-// Per-Gaussian backward (sm_100a): one streaming kernel that turns the 9-float accumulator of the tile pass
-// into the FINAL dense gradient tensors.
+// Per-Gaussian backward (sm_100a), two kernels:
 //
-// Replaces, fused:  computeCov2DCUDA   RAST/cuda_rasterizer/backward.cu:144-274
-//                   preprocessCUDA bwd backward.cu:346-396 (+ SH backward :20-139, cov3D backward :278-341)
-//                   the nine torch::zeros fills of the binding (RAST/rasterize_points.cu:154-162)
-// Every output row is written exactly once (zeros for invisible Gaussians), so the caller passes
-// uninitialised memory; dL_dconic / dL_dcov3D / dL_dcolor never exist as dense [P,*] tensors unless asked for.
-// HBM-bound: ~248 B written + 4 B read per Gaussian (+ ~290 B read per visible one).  All stores are coalesced:
-// per-thread results are staged in shared memory and written by the warp as contiguous 128-bit rows
-// (a warp's 32 SH-gradient rows are one contiguous 6 KB block of dL_dsh).
+//   k_grad_vis    dense over the compact visible list: turns the 9-float accumulator of the tile pass into the
+//                 per-Gaussian gradients.  Replaces, fused: computeCov2DCUDA (RAST/cuda_rasterizer/backward.cu:
+//                 144-274) and preprocessCUDA bwd (:346-396, with the SH backward :20-139 and the cov3D backward
+//                 :278-341).  Result: one 44-float row per visible Gaussian in a compact scratch buffer (the
+//                 dL_dsh block is kept factored as basis[16] x dRGB[3]).
+//   k_grad_write  streaming over all P rows: expands / copies the compact rows into the FINAL dense gradient
+//                 tensors and writes zeros for invisible Gaussians.  Replaces the nine torch::zeros fills of the
+//                 binding (RAST/rasterize_points.cu:154-162) and every read-modify-write the reference does on
+//                 dense [P,*] intermediates (dL_dconic, dL_dcov3D, dL_dcolors never exist as dense tensors unless
+//                 the caller asks for them).  HBM-bound: ~248 B written + 4 B read per Gaussian; every store is a
+//                 fully coalesced 128-bit (dL_dsh, rotations) or 32-bit row-contiguous store.
 #include "gs_common.cuh"
 
 namespace {
 
 constexpr int kT = 256;
-constexpr int kWarps = kT / 32;
-
-// write 32 rows x NF floats, staged in s[32*NF] (row-major), to dst[(row0 + r) * NF + c]; coalesced
-template <int NF>
-__device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, const float* s, long long row0, long long P,
-                                                int lane) {
-    const long long base = row0 * NF;
-    const long long lim = P * NF;
-#pragma unroll
-    for (int k = 0; k < NF; k++) {
-        const long long e = base + lane + 32 * k;
-        if (e < lim) dst[e] = s[lane + 32 * k];
-    }
-}
-
-// Expand the staged (basis[16], dRGB[3]) of `rows` Gaussians into their contiguous dL_dsh block with coalesced
-// 128-bit stores.  CM3 > 0: compile-time row length (M*3), so the index arithmetic is mul/shift, not division.
-template <int CM3>
-__device__ __forceinline__ void store_dsh(float* __restrict__ dst, const float* sb, const float* sr, int rows,
-                                          int lane, int rt_m3 = 0) {
-    const int M3 = CM3 > 0 ? CM3 : rt_m3;
-    const int total = rows * M3;
-    if ((M3 & 3) == 0) {
-        const int total4 = total >> 2;
-        for (int f = lane; f < total4; f += 32) {
-            float o[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = 4 * f + u;
-                const int gg = e / M3, rem = e - gg * M3;
-                const int k = rem / 3, ch = rem - 3 * k;
-                o[u] = (k < 16 ? sb[gg * 16 + k] : 0.f) * sr[gg * 3 + ch];
-            }
-            reinterpret_cast<float4*>(dst)[f] = make_float4(o[0], o[1], o[2], o[3]);
-        }
-    } else {
-        for (int e = lane; e < total; e += 32) {
-            const int gg = e / M3, rem = e - gg * M3;
-            const int k = rem / 3, ch = rem - 3 * k;
-            dst[e] = (k < 16 ? sb[gg * 16 + k] : 0.f) * sr[gg * 3 + ch];
-        }
-    }
-}
+// compact gradient row (floats): 0-2 dmean3D, 3-4 dmean2D, 5 dopacity, 6-8 dscale, 9-12 drot, 13-15 dRGB (clamp
+// masked), 16-31 SH basis, 32-34 dcolor (raw), 35-40 dcov3D, 41-43 pad
+constexpr int kRow = GS_GOUT_FLOATS;
 
 __global__ void __launch_bounds__(kT)
-k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restrict__ means3D,
-            const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,
-            const float* __restrict__ cov3D_precomp, const float4* __restrict__ rec, float4* __restrict__ acc,
-            const GsGradPtrs g) {
-    __shared__ float s_basis[kWarps][32 * 16];
-    __shared__ float s_rgb[kWarps][32 * 3];
-    __shared__ float s_stage[kWarps][32 * 6];
+k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
+           const float* __restrict__ scales, const float* __restrict__ rotations,
+           const float* __restrict__ cov3D_precomp, const float4* __restrict__ rec, float4* __restrict__ acc,
+           const uint32_t* __restrict__ vis_list, const GsDevStatus* __restrict__ status, float* __restrict__ gout) {
     __shared__ GsCam cam;
     gs_load_cam(v, &cam);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long row0 = (long long)blockIdx.x * kT + wid * 32;
-    const long long i = row0 + lane;
-    const int P = v.P;
-
-    bool vis = false;
-    if (i < P) vis = radii[i] > 0;
-
-    float dm3x = 0.f, dm3y = 0.f, dm3z = 0.f, dm2x = 0.f, dm2y = 0.f, dop = 0.f;
-    float dsx = 0.f, dsy = 0.f, dsz = 0.f;
-    float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
-    float dcol0 = 0.f, dcol1 = 0.f, dcol2 = 0.f;
-    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float bs[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) bs[k] = 0.f;
-    float dRGB0 = 0.f, dRGB1 = 0.f, dRGB2 = 0.f;
-
-    if (vis) {
+    const uint32_t nvis = (uint32_t)status->num_visible;
+    for (uint32_t c = blockIdx.x * kT + threadIdx.x; c < nvis; c += gridDim.x * kT) {
+        const uint32_t i = vis_list[c];
         float4* aa = acc + (size_t)3 * i;
-        const float4 a0 = aa[0], a1 = aa[1];
-        const float a2x = reinterpret_cast<const float*>(aa + 2)[0];
+        const float4 a0 = aa[0], a1 = aa[1], a2 = aa[2];
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        aa[0] = z4; aa[1] = z4; aa[2] = z4;                 // re-arm the accumulator for the next backward
-        dm2x = a0.x; dm2y = a0.y; dop = a1.y;
+        aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, 0.f, 0.f, a2.w);   // re-arm, keep the compact slot
+        const float dm2x = a0.x, dm2y = a0.y, dop = a1.y;
         const float dcx = a0.z, dcy = a0.w, dcz = a1.x;     // dL_dconic (a, b, c)
-        dcol0 = a1.z; dcol1 = a1.w; dcol2 = a2x;
-        const uint32_t clamped = __float_as_uint(__ldg(reinterpret_cast<const float*>(rec + (size_t)3 * i + 2) + 2));
+        const float dcol0 = a1.z, dcol1 = a1.w, dcol2 = a2.x;
+        const uint32_t clamped = __float_as_uint(__ldg(reinterpret_cast<const float*>(rec + (size_t)GS_REC_V4 * i + 2) + 2));
 
         const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
         float c6[6];
@@ -112,15 +54,16 @@ k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restri
         // ---- computeCov2DCUDA (backward.cu:144-274)
         GsCov2D cc;
         gs_cov2d(p, v, cam.vm, c6, cc);
-        const float a = cc.a, b = cc.b, c = cc.c;
-        const float denom = a * c - b * b;
+        const float a = cc.a, b = cc.b, cq = cc.c;
+        const float denom = a * cq - b * b;
         float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
         const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
         const float (*Tm)[3] = cc.A;
+        float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (denom2inv != 0.f) {
-            dL_da = denom2inv * (-c * c * dcx + 2 * b * c * dcy + (denom - a * c) * dcz);
-            dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c) * dcx);
-            dL_db = denom2inv * 2 * (b * c * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
+            dL_da = denom2inv * (-cq * cq * dcx + 2 * b * cq * dcy + (denom - a * cq) * dcz);
+            dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * cq) * dcx);
+            dL_db = denom2inv * 2 * (b * cq * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
             dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
             dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
             dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
@@ -147,9 +90,9 @@ k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restri
         const float dty = cc.ymul * -v.focal_y * tz2 * dJ12;
         const float dtz = -v.focal_x * tz2 * dJ00 - v.focal_y * tz2 * dJ11 + (2 * v.focal_x * cc.tx) * tz3 * dJ02 +
                           (2 * v.focal_y * cc.ty) * tz3 * dJ12;
-        dm3x = vm[0] * dtx + vm[1] * dty + vm[2] * dtz;     // assignment (backward.cu:273)
-        dm3y = vm[4] * dtx + vm[5] * dty + vm[6] * dtz;
-        dm3z = vm[8] * dtx + vm[9] * dty + vm[10] * dtz;
+        float dm3x = vm[0] * dtx + vm[1] * dty + vm[2] * dtz;     // assignment (backward.cu:273)
+        float dm3y = vm[4] * dtx + vm[5] * dty + vm[6] * dtz;
+        float dm3z = vm[8] * dtx + vm[9] * dty + vm[10] * dtz;
 
         // ---- preprocessCUDA backward (backward.cu:346-396): projection Jacobian
         const float* pj = cam.pm;
@@ -162,6 +105,10 @@ k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restri
         dm3z += (pj[8] * m_w - pj[11] * mul1) * dm2x + (pj[9] * m_w - pj[11] * mul2) * dm2y;
 
         // ---- SH backward (backward.cu:20-139)
+        float bs[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) bs[k] = 0.f;
+        float dRGB0 = 0.f, dRGB1 = 0.f, dRGB2 = 0.f;
         if (shs) {
             const float3 d0 = make_float3(p.x - cam.campos[0], p.y - cam.campos[1], p.z - cam.campos[2]);
             const float len = sqrtf(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
@@ -170,16 +117,21 @@ k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restri
             dRGB1 = dcol1 * ((clamped & 2u) ? 0.f : 1.f);
             dRGB2 = dcol2 * ((clamped & 4u) ? 0.f : 1.f);
             gs_sh_basis(v.D, x, y, z, bs);
-            const float* sh = shs + (size_t)i * v.M * 3;
-            float ddx = 0.f, ddy = 0.f, ddz = 0.f;          // dL_ddir
             const int D = v.D;
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;          // dL_ddir
             if (D > 0) {
+                // all active coefficients in flight before use (scalar loads: rows need not be 16-byte aligned)
+                const float* sh = shs + (size_t)i * v.M * 3;
+                float cf[48];
+                const int na3 = (D + 1) * (D + 1) * 3;
+#pragma unroll
+                for (int k = 0; k < 48; k++) cf[k] = k < na3 ? __ldg(sh + k) : 0.f;
                 const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
                 const float dR[3] = {dRGB0, dRGB1, dRGB2};
                 float ax[3], ay[3], az[3];
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
-#define SHK(k) __ldg(sh + 3 * (k) + ch)
+#define SHK(k) cf[3 * (k) + ch]
                     float vx = -GS_C1 * SHK(3), vy = -GS_C1 * SHK(1), vz = GS_C1 * SHK(2);
                     if (D > 1) {
                         vx += GS_C2_0 * y * SHK(4) + GS_C2_2 * 2.f * -x * SHK(6) + GS_C2_3 * z * SHK(7) + GS_C2_4 * 2.f * x * SHK(8);
@@ -212,6 +164,8 @@ k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restri
         }
 
         // ---- cov3D backward (backward.cu:278-341)
+        float dsx = 0.f, dsy = 0.f, dsz = 0.f;
+        float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
         if (scales) {
             float R[3][3], M[3][3];
             gs_quat_R(q, R);
@@ -243,66 +197,137 @@ k_gauss_bwd(const GsView v, const int* __restrict__ radii, const float* __restri
             drot.z = 2 * x * (Q[1][0] + Q[0][1]) + 2 * r * (Q[2][0] - Q[0][2]) + 2 * z * (Q[1][2] + Q[2][1]) - 4 * y * (Q[2][2] + Q[0][0]);
             drot.w = 2 * r * (Q[0][1] - Q[1][0]) + 2 * x * (Q[2][0] + Q[0][2]) + 2 * y * (Q[1][2] + Q[2][1]) - 4 * z * (Q[1][1] + Q[0][0]);
         }
-    }
 
-    // ------------------------------------------------------------------ coalesced stores
-    float* st = s_stage[wid];
-    if (g.dmeans3D) {
-        st[3 * lane] = dm3x; st[3 * lane + 1] = dm3y; st[3 * lane + 2] = dm3z;
-        __syncwarp();
-        warp_store_rows<3>(g.dmeans3D, st, row0, P, lane);
-        __syncwarp();
+        float4* o = reinterpret_cast<float4*>(gout + (size_t)c * kRow);
+        o[0] = make_float4(dm3x, dm3y, dm3z, dm2x);
+        o[1] = make_float4(dm2y, dop, dsx, dsy);
+        o[2] = make_float4(dsz, drot.x, drot.y, drot.z);
+        o[3] = make_float4(drot.w, dRGB0, dRGB1, dRGB2);
+        o[4] = make_float4(bs[0], bs[1], bs[2], bs[3]);
+        o[5] = make_float4(bs[4], bs[5], bs[6], bs[7]);
+        o[6] = make_float4(bs[8], bs[9], bs[10], bs[11]);
+        o[7] = make_float4(bs[12], bs[13], bs[14], bs[15]);
+        o[8] = make_float4(dcol0, dcol1, dcol2, dcov[0]);
+        o[9] = make_float4(dcov[1], dcov[2], dcov[3], dcov[4]);
+        o[10] = make_float4(dcov[5], 0.f, 0.f, 0.f);
     }
+}
+
+// one CTA = 256 consecutive rows; s_slot[row] = CTA-local index of the row's staged gradient, or -1
+template <int NF>
+__device__ __forceinline__ void cta_store_rows(float* __restrict__ dst, const float* s_row, const int* s_slot, int off,
+                                               long long row0, long long P) {
+    const long long base = row0 * NF, lim = P * NF;
+#pragma unroll
+    for (int k = 0; k < NF; k++) {
+        const int e = threadIdx.x + kT * k;
+        const int row = e / NF, comp = e - row * NF;
+        const int cl = s_slot[row];
+        if (base + e < lim) dst[base + e] = cl < 0 ? 0.f : s_row[cl * kRow + off + comp];
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+k_grad_write(const int P, const int M, const int* __restrict__ radii, const float4* __restrict__ acc,
+             const float* __restrict__ gout, const GsGradPtrs g) {
+    extern __shared__ __align__(16) float s_row[];       // kT * kRow floats: staged compact rows of this CTA
+    __shared__ int s_slot[kT];
+    __shared__ int s_count;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * kT;
+    const long long i = row0 + tid;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const bool vis = i < P && radii[i] > 0;
+    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    int cl = -1;
+    if (m) {
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&s_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (vis) cl = base + __popc(m & ((1u << lane) - 1u));
+    }
+    s_slot[tid] = cl;
+    if (vis) {
+        const uint32_t slot = __float_as_uint(__ldg(reinterpret_cast<const float*>(acc + (size_t)3 * i + 2) + 3));
+        const float4* src = reinterpret_cast<const float4*>(gout + (size_t)slot * kRow);
+        float4* dstr = reinterpret_cast<float4*>(s_row + cl * kRow);
+#pragma unroll
+        for (int k = 0; k < kRow / 4; k++) dstr[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    if (g.dmeans3D) cta_store_rows<3>(g.dmeans3D, s_row, s_slot, 0, row0, P);
     if (g.dmeans2D) {
-        st[3 * lane] = dm2x; st[3 * lane + 1] = dm2y; st[3 * lane + 2] = 0.f;
-        __syncwarp();
-        warp_store_rows<3>(g.dmeans2D, st, row0, P, lane);
-        __syncwarp();
-    }
-    if (g.dscales) {
-        st[3 * lane] = dsx; st[3 * lane + 1] = dsy; st[3 * lane + 2] = dsz;
-        __syncwarp();
-        warp_store_rows<3>(g.dscales, st, row0, P, lane);
-        __syncwarp();
-    }
-    if (g.dcolors) {
-        st[3 * lane] = dcol0; st[3 * lane + 1] = dcol1; st[3 * lane + 2] = dcol2;
-        __syncwarp();
-        warp_store_rows<3>(g.dcolors, st, row0, P, lane);
-        __syncwarp();
-    }
-    if (g.dcov3D) {
+        const long long base = row0 * 3, lim = (long long)P * 3;
 #pragma unroll
-        for (int k = 0; k < 6; k++) st[6 * lane + k] = dcov[k];
-        __syncwarp();
-        warp_store_rows<6>(g.dcov3D, st, row0, P, lane);
-        __syncwarp();
+        for (int k = 0; k < 3; k++) {
+            const int e = tid + kT * k;
+            const int row = e / 3, comp = e - row * 3;
+            const int c2 = s_slot[row];
+            if (base + e < lim) g.dmeans2D[base + e] = (c2 < 0 || comp == 2) ? 0.f : s_row[c2 * kRow + 3 + comp];
+        }
     }
+    if (g.dscales) cta_store_rows<3>(g.dscales, s_row, s_slot, 6, row0, P);
+    if (g.dcolors) cta_store_rows<3>(g.dcolors, s_row, s_slot, 32, row0, P);
+    if (g.dcov3D) cta_store_rows<6>(g.dcov3D, s_row, s_slot, 35, row0, P);
     if (i < P) {
-        if (g.dopacity) g.dopacity[i] = dop;
-        if (g.drots) reinterpret_cast<float4*>(g.drots)[i] = drot;
+        if (g.dopacity) g.dopacity[i] = cl < 0 ? 0.f : s_row[cl * kRow + 5];
+        if (g.drots) {
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cl >= 0) { const float* q = s_row + cl * kRow + 9; r = make_float4(q[0], q[1], q[2], q[3]); }
+            reinterpret_cast<float4*>(g.drots)[i] = r;
+        }
     }
-    if (g.dsh && v.M > 0) {
-        // dL_dsh[g][k][ch] = basis_k(dir_g) * dL_dRGB_g[ch]: stage 19 floats per Gaussian, expand while storing
-        float* sb = s_basis[wid];
-        float* sr = s_rgb[wid];
+    if (g.dsh && M > 0) {
+        const int M3 = M * 3;
+        const long long rows = min((long long)kT, (long long)P - row0);
+        float* dst = g.dsh + row0 * M3;
+        const int total = (int)rows * M3;
+        if (M3 == 48) {                                  // M = 16: 12 float4 per row, compile-time index maths
+            const int total4 = total >> 2;
+            for (int f = tid; f < total4; f += kT) {
+                const int row = f / 12, j = f - row * 12;
+                const int c2 = s_slot[row];
+                float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c2 >= 0) {
+                    const float* sb = s_row + c2 * kRow + 16;
+                    const float* sr = s_row + c2 * kRow + 13;
+                    float o[4];
 #pragma unroll
-        for (int k = 0; k < 16; k++) sb[lane * 16 + k] = bs[k];
-        sr[lane * 3] = dRGB0; sr[lane * 3 + 1] = dRGB1; sr[lane * 3 + 2] = dRGB2;
-        __syncwarp();
-        const long long rows = min((long long)32, (long long)P - row0);
-        if (rows > 0) {
-            if (v.M == 16) store_dsh<48>(g.dsh + row0 * 48, sb, sr, (int)rows, lane);
-            else store_dsh<0>(g.dsh + row0 * (v.M * 3), sb, sr, (int)rows, lane, v.M * 3);
+                    for (int u = 0; u < 4; u++) {
+                        const int e = 4 * j + u;
+                        const int k = e / 3, ch = e - 3 * k;
+                        o[u] = sb[k] * sr[ch];
+                    }
+                    o4 = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                reinterpret_cast<float4*>(dst)[f] = o4;
+            }
+        } else {
+            for (int e = tid; e < total; e += kT) {
+                const int row = e / M3, rem = e - row * M3;
+                const int k = rem / 3, ch = rem - 3 * k;
+                const int c2 = s_slot[row];
+                dst[e] = (c2 < 0 || k >= 16) ? 0.f : s_row[c2 * kRow + 16 + k] * s_row[c2 * kRow + 13 + ch];
+            }
         }
     }
 }
 
 }  // namespace
 
-void gs_launch_gauss_bwd(const GsView& v, const int* radii, const float* means3D, const float* shs,
-                         const float* scales, const float* rotations, const float* cov3D_precomp,
-                         const float4* rec, float4* acc, GsGradPtrs g, cudaStream_t s) {
-    const int grid = (v.P + kT - 1) / kT;
-    k_gauss_bwd<<<grid, kT, 0, s>>>(v, radii, means3D, shs, scales, rotations, cov3D_precomp, rec, acc, g);
+void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
+                        const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
+                        const uint32_t* vis_list, const GsDevStatus* status, float* gout, cudaStream_t s) {
+    const int need = (v.P + kT - 1) / kT;
+    const int grid = need < num_sms * 2 ? need : num_sms * 2;
+    k_grad_vis<<<grid, kT, 0, s>>>(v, means3D, shs, scales, rotations, cov3D_precomp, rec, acc, vis_list, status, gout);
+}
+void gs_grad_write_init() {
+    cudaFuncSetAttribute(k_grad_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kRow * (int)sizeof(float));
+}
+void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
+                          cudaStream_t s) {
+    const int grid = (P + kT - 1) / kT;
+    k_grad_write<<<grid, kT, kT * kRow * sizeof(float), s>>>(P, M, radii, acc, gout, g);
 }

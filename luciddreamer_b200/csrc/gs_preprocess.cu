@@ -1,84 +1,92 @@
-// Per-Gaussian forward pass, tile histogram scan and (tile, Gaussian) pair emission for sm_100a.
+// Per-Gaussian forward passes, tile histogram scan and (tile, Gaussian) pair emission for sm_100a.
 //
 // Replaces (RAST = reference rasterizer):
-//   k_preprocess   RAST/cuda_rasterizer/forward.cu:155-256 (preprocessCUDA) + auxiliary.h:139-164 (in_frustum)
+//   k_project      the geometric half of preprocessCUDA (RAST/cuda_rasterizer/forward.cu:155-232,249-255) +
+//                  in_frustum (auxiliary.h:139-164): streaming pass over all P Gaussians, one thread each; visible
+//                  ones are appended to a compact list (warp-aggregated atomic) so that every later per-Gaussian
+//                  kernel runs densely over P_vis instead of divergently over P
+//   k_shade_count  the colour half (computeColorFromSH, forward.cu:20-71,236-246) on the compact list, 128-bit
+//                  SH loads all in flight at once, + the tile histogram that replaces tiles_touched / InclusiveSum
 //   k_tile_scan    cub::DeviceScan::InclusiveSum over P Gaussians + blocking D2H of num_rendered
-//                  (rasterizer_impl.cu:278-282): here a scan over the G tiles only, result mirrored to pinned
+//                  (rasterizer_impl.cu:278-282): here a scan over the G tiles only, totals mirrored to pinned
 //                  host memory so the host never blocks the stream
 //   k_emit         duplicateWithKeys (rasterizer_impl.cu:70-111): pairs go straight into their tile's bucket
 //                  (per-tile cursors), keyed by (depth bits, Gaussian index) for the per-tile sort
 //   k_mark_visible checkFrustum (rasterizer_impl.cu:54-66)
+// Histogram and emission spread the (Gaussian, tile) candidates of a CTA's 256 Gaussians evenly over its threads
+// (block scan of the rect areas + binary search), so a splat covering thousands of tiles costs the same per thread
+// as one covering four.
 #include "gs_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kBigRect = 32;   // rects with more tiles than this are walked by the whole warp
 
 // Exact tile culling (parity-safe): a (tile, splat) pair is binned only if the splat can
-// reach alpha >= 1/255 somewhere in the tile.  power(d) = -0.5 (A dx^2 + C dy^2) - B dx dy is concave with its
-// maximum (0) at the mean, so its maximum over the tile's pixel box [x0, x0+15] x [y0, y0+15] is 0 if the mean is
-// inside and otherwise lies on an edge facing the mean; each facing edge is a 1-D concave maximisation (clamp
-// the stationary point).  The pair is kept iff max power >= thr, thr = -ln(255 * opacity) - slack: pairs that are
-// dropped are skipped by every pixel of the tile in the reference too (forward.cu:336-346), so no output changes.
-// __noinline__: the histogram pass (k_preprocess) and the emission pass (k_emit) must take bit-identical
+// reach alpha >= 1/255 somewhere in the tile (gs_box_hit).  Pairs that are dropped are skipped by every pixel of
+// the tile in the reference too (forward.cu:336-346), so no output changes.
+// __noinline__: the histogram pass (k_shade_count) and the emission pass (k_emit) must take bit-identical
 // decisions, so both call the same machine code on the same stored floats.
 __device__ __noinline__ bool gs_tile_hit(float mx, float my, float A, float B, float C, float thr, int tx, int ty) {
     const float x0 = (float)(tx * GS_TILE), y0 = (float)(ty * GS_TILE);
     return gs_box_hit(mx, my, A, B, C, thr, x0, y0, x0 + (float)(GS_TILE - 1), y0 + (float)(GS_TILE - 1));
 }
 
-struct GsCullArgs {
-    float mx, my, A, B, C, thr;
+struct CandShared {                   // per-CTA candidate table (one entry per Gaussian of the chunk)
+    float mx[kThreads], my[kThreads], A[kThreads], B[kThreads], C[kThreads], thr[kThreads];
+    int rx[kThreads], ry[kThreads], rw[kThreads];
+    uint32_t p0[kThreads], p1[kThreads];
+    uint32_t cum[kThreads + 1];
+    uint32_t warp_tot[kThreads / 32];
 };
 
-// Calls f(tile_id, payload...) for every tile of every lane's rect that passes gs_tile_hit.  Small rects: each lane on its own.
-// Large rects: the warp takes them one at a time, lanes striding over the tiles (avoids one lane looping over
-// hundreds of tiles while 31 wait).  Must be called by all 32 lanes.
+// Block-wide exclusive scan of `area` into s.cum[0..256]; returns the total.  All 256 threads must call.
+__device__ __forceinline__ uint32_t cta_scan_areas(CandShared& s, uint32_t area) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t x = area;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s.warp_tot[wid] = x;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) { const uint32_t t = s.warp_tot[w]; if (w < wid) wbase += t; total += t; }
+    s.cum[tid] = wbase + x - area;
+    if (tid == kThreads - 1) s.cum[kThreads] = total;
+    __syncthreads();
+    return total;
+}
+
+// Visits every (Gaussian, tile) candidate of the chunk that passes the culling test: f(tile, p0, p1).
 template <typename F>
-__device__ __forceinline__ void gs_for_each_tile(bool vis, int4 rect, int gx, GsCullArgs c, uint32_t p0, uint32_t p1,
-                                                 F f) {
-    const int w = rect.z - rect.x, h = rect.w - rect.y;
-    const int area = vis ? w * h : 0;
-    const bool big = area > kBigRect;
-    if (area > 0 && !big) {
-        for (int y = rect.y; y < rect.w; y++)
-            for (int x = rect.x; x < rect.z; x++)
-                if (gs_tile_hit(c.mx, c.my, c.A, c.B, c.C, c.thr, x, y)) f((uint32_t)(y * gx + x), p0, p1);
-    }
-    unsigned m = __ballot_sync(0xffffffffu, big);
-    const int lane = threadIdx.x & 31;
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const int rx = __shfl_sync(0xffffffffu, rect.x, src), ry = __shfl_sync(0xffffffffu, rect.y, src);
-        const int rw = __shfl_sync(0xffffffffu, w, src), n = __shfl_sync(0xffffffffu, area, src);
-        const uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
-        GsCullArgs d;
-        d.mx = __shfl_sync(0xffffffffu, c.mx, src); d.my = __shfl_sync(0xffffffffu, c.my, src);
-        d.A = __shfl_sync(0xffffffffu, c.A, src); d.B = __shfl_sync(0xffffffffu, c.B, src);
-        d.C = __shfl_sync(0xffffffffu, c.C, src); d.thr = __shfl_sync(0xffffffffu, c.thr, src);
-        for (int k = lane; k < n; k += 32) {
-            const int yy = k / rw, xx = k - yy * rw;
-            if (gs_tile_hit(d.mx, d.my, d.A, d.B, d.C, d.thr, rx + xx, ry + yy))
-                f((uint32_t)((ry + yy) * gx + rx + xx), q0, q1);
+__device__ __forceinline__ void cta_for_each_hit(const CandShared& s, uint32_t total, int gx, F f) {
+    for (uint32_t q = threadIdx.x; q < total; q += kThreads) {
+        int lo = 0, hi = kThreads;                       // largest c with cum[c] <= q
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s.cum[mid] <= q) lo = mid; else hi = mid;
         }
+        const int c = lo;
+        const int r = (int)(q - s.cum[c]);
+        const int w = s.rw[c];
+        const int yy = r / w, xx = r - yy * w;
+        const int tx = s.rx[c] + xx, ty = s.ry[c] + yy;
+        if (gs_tile_hit(s.mx[c], s.my[c], s.A[c], s.B[c], s.C[c], s.thr[c], tx, ty)) f((uint32_t)(ty * gx + tx), s.p0[c], s.p1[c]);
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_preprocess(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
-             const float* __restrict__ colors_precomp, const float* __restrict__ opacities,
-             const float* __restrict__ scales, const float* __restrict__ rotations,
-             const float* __restrict__ cov3D_precomp, int* __restrict__ radii, float4* __restrict__ rec,
-             float4* __restrict__ acc, uint32_t* __restrict__ tile_cnt, GsDevStatus* __restrict__ status) {
+k_project(const GsView v, const float* __restrict__ means3D, const float* __restrict__ opacities,
+          const float* __restrict__ scales, const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
+          int* __restrict__ radii, float4* __restrict__ rec, uint32_t* __restrict__ vis_list,
+          GsDevStatus* __restrict__ status) {
     __shared__ GsCam cam;
     gs_load_cam(v, &cam);
     const int i = blockIdx.x * kThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     bool vis = false;
-    int4 rect = make_int4(0, 0, 0, 0);
     int my_radius = 0;
-    GsCullArgs cull = {0.f, 0.f, 1.f, 0.f, 1.f, 0.f};
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
 
     if (i < v.P) {
         const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
@@ -107,71 +115,125 @@ k_preprocess(const GsView v, const float* __restrict__ means3D, const float* __r
                 const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
                 const float rad = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
                 const float px = gs_ndc2pix(ppx, v.W), py = gs_ndc2pix(ppy, v.H);
-                rect = gs_rect(px, py, (int)rad, v.gx, v.gy);
+                const int4 rect = gs_rect(px, py, (int)rad, v.gx, v.gy);
                 if ((rect.z - rect.x) * (rect.w - rect.y) != 0) {
                     vis = true;
                     my_radius = (int)rad;
-                    float r_, g_, b_;
-                    uint32_t clamped = 0;
-                    if (colors_precomp) {
-                        r_ = colors_precomp[3 * i]; g_ = colors_precomp[3 * i + 1]; b_ = colors_precomp[3 * i + 2];
-                    } else {                           // forward.cu:20-71
-                        float3 d = make_float3(p.x - cam.campos[0], p.y - cam.campos[1], p.z - cam.campos[2]);
-                        const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-                        d.x = d.x / len; d.y = d.y / len; d.z = d.z / len;
-                        float bs[16];
-                        gs_sh_basis(v.D, d.x, d.y, d.z, bs);
-                        const float* sh = shs + (size_t)i * v.M * 3;
-                        float cr = bs[0] * sh[0], cg = bs[0] * sh[1], cb = bs[0] * sh[2];
-                        const int na = (v.D + 1) * (v.D + 1);
-                        for (int k = 1; k < na; k++) {
-                            cr = cr + bs[k] * sh[3 * k]; cg = cg + bs[k] * sh[3 * k + 1]; cb = cb + bs[k] * sh[3 * k + 2];
-                        }
-                        cr += 0.5f; cg += 0.5f; cb += 0.5f;
-                        clamped = (cr < 0.f ? 1u : 0u) | (cg < 0.f ? 2u : 0u) | (cb < 0.f ? 4u : 0u);
-                        r_ = fmaxf(cr, 0.f); g_ = fmaxf(cg, 0.f); b_ = fmaxf(cb, 0.f);
-                    }
                     const float opac = opacities[i];
                     // alpha >= 1/255  <=>  power >= -ln(255 * opacity); slack keeps the test conservative
                     const float thr = -logf(255.0f * opac) - GS_CULL_SLACK;
-                    cull.mx = px; cull.my = py; cull.A = conic.x; cull.B = conic.y; cull.C = conic.z; cull.thr = thr;
-                    float4* rr = rec + (size_t)3 * i;
-                    rr[0] = make_float4(px, py, conic.x, conic.y);
-                    rr[1] = make_float4(conic.z, opac, r_, g_);
-                    rr[2] = make_float4(b_, p_view.z, __uint_as_float(clamped), thr);
-                    float4* aa = acc + (size_t)3 * i;
-                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    aa[0] = z4; aa[1] = z4; aa[2] = z4;
+                    q0 = make_float4(px, py, conic.x, conic.y);
+                    q1 = make_float4(conic.z, opac, p_view.z, thr);      // k_shade_count re-packs q1/q2
                 }
             }
         }
         radii[i] = my_radius;
     }
+    // warp-aggregated append to the compact visible list
+    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    if (m) {
+        unsigned long long base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&status->num_visible, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (vis) {
+            const uint32_t slot = (uint32_t)base + __popc(m & ((1u << lane) - 1u));
+            vis_list[slot] = (uint32_t)i;
+            float4* rr = rec + (size_t)GS_REC_V4 * i;
+            rr[0] = q0;
+            rr[1] = q1;
+        }
+    }
+}
 
-    // tile histogram (one RED per pair)
-    gs_for_each_tile(vis, rect, v.gx, cull, 0u, 0u,
-                     [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&tile_cnt[tile], 1u); });
-
-    // block-level totals -> two atomics per CTA
-    const unsigned area = vis ? (unsigned)((rect.z - rect.x) * (rect.w - rect.y)) : 0u;
-    unsigned a = area, c = vis ? 1u : 0u;
+// Loads one Gaussian's SH coefficients with every load in flight before the first use, evaluates the colour.
+template <int D>
+__device__ __forceinline__ void sh_to_rgb(const float* __restrict__ sh, float x, float y, float z, float& cr,
+                                          float& cg, float& cb) {
+    constexpr int NA = (D + 1) * (D + 1);                // active coefficients
+    constexpr int NV = (NA * 3 + 3) / 4;                 // float4 loads (rows are 16-byte aligned when M*3 % 4 == 0)
+    float c[NV * 4];
+    const float4* s4 = reinterpret_cast<const float4*>(sh);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
-    __shared__ unsigned s_a[kThreads / 32], s_c[kThreads / 32];
-    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_c[threadIdx.x >> 5] = c; }
+    for (int k = 0; k < NV; k++) {
+        const float4 t = __ldg(s4 + k);
+        c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
+    }
+    float bs[16];
+    gs_sh_basis(D, x, y, z, bs);
+    cr = bs[0] * c[0]; cg = bs[0] * c[1]; cb = bs[0] * c[2];
+#pragma unroll
+    for (int k = 1; k < NA; k++) { cr = cr + bs[k] * c[3 * k]; cg = cg + bs[k] * c[3 * k + 1]; cb = cb + bs[k] * c[3 * k + 2]; }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_shade_count(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
+              const float* __restrict__ colors_precomp, const int* __restrict__ radii, float4* __restrict__ rec,
+              float4* __restrict__ acc, const uint32_t* __restrict__ vis_list, uint32_t* __restrict__ tile_cnt,
+              GsDevStatus* __restrict__ status) {
+    __shared__ CandShared S;
+    __shared__ float s_campos[3];
+    if (threadIdx.x < 3) s_campos[threadIdx.x] = __ldg(v.campos + threadIdx.x);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long ta = 0, tc = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; w++) { ta += s_a[w]; tc += s_c[w]; }
-        if (ta) atomicAdd(&status->num_rendered, ta);
-        if (tc) atomicAdd(&status->num_visible, tc);
+    const uint32_t nvis = (uint32_t)status->num_visible;
+    const bool aligned = ((v.M * 3) & 3) == 0;
+    for (uint32_t chunk = blockIdx.x * kThreads; chunk < nvis; chunk += gridDim.x * kThreads) {
+        const uint32_t c = chunk + threadIdx.x;
+        uint32_t area = 0;
+        if (c < nvis) {
+            const uint32_t i = vis_list[c];
+            float4* rr = rec + (size_t)GS_REC_V4 * i;
+            const float4 q0 = rr[0], q1 = rr[1];         // written by k_project: (x,y,A,B), (C, opacity, depth, thr)
+            float r_, g_, b_;
+            uint32_t clamped = 0;
+            if (colors_precomp) {
+                r_ = colors_precomp[3 * i]; g_ = colors_precomp[3 * i + 1]; b_ = colors_precomp[3 * i + 2];
+            } else {                                     // forward.cu:20-71
+                const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+                float3 d = make_float3(p.x - s_campos[0], p.y - s_campos[1], p.z - s_campos[2]);
+                const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+                d.x = d.x / len; d.y = d.y / len; d.z = d.z / len;
+                const float* sh = shs + (size_t)i * v.M * 3;
+                float cr, cg, cb;
+                if (aligned) {
+                    switch (v.D) {
+                        case 0: sh_to_rgb<0>(sh, d.x, d.y, d.z, cr, cg, cb); break;
+                        case 1: sh_to_rgb<1>(sh, d.x, d.y, d.z, cr, cg, cb); break;
+                        case 2: sh_to_rgb<2>(sh, d.x, d.y, d.z, cr, cg, cb); break;
+                        default: sh_to_rgb<3>(sh, d.x, d.y, d.z, cr, cg, cb); break;
+                    }
+                } else {
+                    float bs[16];
+                    gs_sh_basis(v.D, d.x, d.y, d.z, bs);
+                    cr = bs[0] * sh[0]; cg = bs[0] * sh[1]; cb = bs[0] * sh[2];
+                    const int na = (v.D + 1) * (v.D + 1);
+                    for (int k = 1; k < na; k++) { cr = cr + bs[k] * sh[3 * k]; cg = cg + bs[k] * sh[3 * k + 1]; cb = cb + bs[k] * sh[3 * k + 2]; }
+                }
+                cr += 0.5f; cg += 0.5f; cb += 0.5f;
+                clamped = (cr < 0.f ? 1u : 0u) | (cg < 0.f ? 2u : 0u) | (cb < 0.f ? 4u : 0u);
+                r_ = fmaxf(cr, 0.f); g_ = fmaxf(cg, 0.f); b_ = fmaxf(cb, 0.f);
+            }
+            rr[1] = make_float4(q1.x, q1.y, r_, g_);
+            rr[2] = make_float4(b_, q1.z, __uint_as_float(clamped), q1.w);
+            float4* aa = acc + (size_t)3 * i;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));   // a2.w = compact slot
+            const int4 rect = gs_rect(q0.x, q0.y, radii[i], v.gx, v.gy);
+            area = (uint32_t)((rect.z - rect.x) * (rect.w - rect.y));
+            const int t = threadIdx.x;
+            S.mx[t] = q0.x; S.my[t] = q0.y; S.A[t] = q0.z; S.B[t] = q0.w; S.C[t] = q1.x; S.thr[t] = q1.w;
+            S.rx[t] = rect.x; S.ry[t] = rect.y; S.rw[t] = rect.z - rect.x; S.p0[t] = 0; S.p1[t] = 0;
+        }
+        const uint32_t total = cta_scan_areas(S, area);
+        cta_for_each_hit(S, total, v.gx, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&tile_cnt[tile], 1u); });
+        if (threadIdx.x == 0 && total) atomicAdd(&status->num_rendered, (unsigned long long)total);
+        __syncthreads();
     }
 }
 
 // Exclusive scan of the G tile counts (single CTA: G is ~8k at 1080p).  Resets the counts to zero so the same
 // array serves as the emission cursors, and mirrors the totals to a pinned host slot.
-__global__ void __launch_bounds__(1024)
+constexpr int kScanT = 1024, kScanK = 8;
+__global__ void __launch_bounds__(kScanT)
 k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_off, GsDevStatus* __restrict__ status,
             GsDevStatus* host_slot) {
     __shared__ uint32_t s_warp[32];
@@ -179,27 +241,38 @@ k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < G; base += 1024) {
-        const int t = base + tid;
-        const uint32_t c = t < G ? tile_cnt[t] : 0u;
-        uint32_t x = c;
+    for (int base = 0; base < G; base += kScanT * kScanK) {
+        uint32_t cv[kScanK];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-            s_warp[lane] = w;                           // inclusive over warps
+        for (int k = 0; k < kScanK; k++) {               // all loads in flight before the first scan step
+            const int t = base + k * kScanT + tid;
+            cv[k] = t < G ? tile_cnt[t] : 0u;
         }
-        __syncthreads();
-        const uint32_t carry = s_carry;
-        const uint32_t incl = x + (wid ? s_warp[wid - 1] : 0u);
-        if (t < G) { tile_off[t] = carry + incl - c; tile_cnt[t] = 0u; }
-        __syncthreads();
-        if (tid == 1023) s_carry = carry + incl;
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kScanK; k++) {
+            const int t = base + k * kScanT + tid;
+            if (base + k * kScanT < G) {
+                const uint32_t c = cv[k];
+                uint32_t x = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                if (lane == 31) s_warp[wid] = x;
+                __syncthreads();
+                if (wid == 0) {
+                    uint32_t w = s_warp[lane];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+                    s_warp[lane] = w;                    // inclusive over warps
+                }
+                __syncthreads();
+                const uint32_t carry = s_carry;
+                const uint32_t incl = x + (wid ? s_warp[wid - 1] : 0u);
+                if (t < G) { tile_off[t] = carry + incl - c; tile_cnt[t] = 0u; }
+                __syncthreads();
+                if (tid == kScanT - 1) s_carry = carry + incl;
+                __syncthreads();
+            }
+        }
     }
     if (tid == 0) {
         const uint32_t total = s_carry;
@@ -217,34 +290,36 @@ k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_
 
 __global__ void __launch_bounds__(kThreads)
 k_emit(const GsView v, const int* __restrict__ radii, const float4* __restrict__ rec,
-       const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ tile_cur, GsDevStatus* __restrict__ status,
-       unsigned long long* __restrict__ keys, long long capacity) {
+       const uint32_t* __restrict__ vis_list, const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ tile_cur,
+       GsDevStatus* __restrict__ status, unsigned long long* __restrict__ keys, long long capacity) {
     if ((long long)status->num_pairs > capacity) {      // device-side guard: nothing is binned, host re-renders
         if (blockIdx.x == 0 && threadIdx.x == 0) status->overflow = 1u;
         return;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) status->n_big = 0u;
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    bool vis = false;
-    int4 rect = make_int4(0, 0, 0, 0);
-    uint32_t dbits = 0;
-    GsCullArgs cull = {0.f, 0.f, 1.f, 0.f, 1.f, 0.f};
-    if (i < v.P) {
-        const int r = radii[i];
-        if (r > 0) {
-            const float4 q0 = __ldg(rec + (size_t)3 * i);
-            const float4 q1 = __ldg(rec + (size_t)3 * i + 1);
-            const float4 q2 = __ldg(rec + (size_t)3 * i + 2);
-            rect = gs_rect(q0.x, q0.y, r, v.gx, v.gy);  // same recomputation as rasterizer_impl.cu:91
-            dbits = __float_as_uint(q2.y);
-            cull.mx = q0.x; cull.my = q0.y; cull.A = q0.z; cull.B = q0.w; cull.C = q1.x; cull.thr = q2.w;
-            vis = true;
+    __shared__ CandShared S;
+    const uint32_t nvis = (uint32_t)status->num_visible;
+    for (uint32_t chunk = blockIdx.x * kThreads; chunk < nvis; chunk += gridDim.x * kThreads) {
+        const uint32_t c = chunk + threadIdx.x;
+        uint32_t area = 0;
+        if (c < nvis) {
+            const uint32_t i = vis_list[c];
+            const float4* rr = rec + (size_t)GS_REC_V4 * i;
+            const float4 q0 = __ldg(rr), q1 = __ldg(rr + 1), q2 = __ldg(rr + 2);
+            const int4 rect = gs_rect(q0.x, q0.y, radii[i], v.gx, v.gy);   // same recomputation as rasterizer_impl.cu:91
+            area = (uint32_t)((rect.z - rect.x) * (rect.w - rect.y));
+            const int t = threadIdx.x;
+            S.mx[t] = q0.x; S.my[t] = q0.y; S.A[t] = q0.z; S.B[t] = q0.w; S.C[t] = q1.x; S.thr[t] = q2.w;
+            S.rx[t] = rect.x; S.ry[t] = rect.y; S.rw[t] = rect.z - rect.x;
+            S.p0[t] = __float_as_uint(q2.y); S.p1[t] = i;
         }
+        const uint32_t total = cta_scan_areas(S, area);
+        cta_for_each_hit(S, total, v.gx, [&](uint32_t tile, uint32_t d, uint32_t idx) {
+            const uint32_t pos = tile_off[tile] + atomicAdd(&tile_cur[tile], 1u);
+            keys[pos] = ((unsigned long long)d << 32) | idx;
+        });
+        __syncthreads();
     }
-    gs_for_each_tile(vis, rect, v.gx, cull, dbits, (uint32_t)i, [&](uint32_t tile, uint32_t d, uint32_t idx) {
-        const uint32_t pos = tile_off[tile] + atomicAdd(&tile_cur[tile], 1u);
-        keys[pos] = ((unsigned long long)d << 32) | idx;
-    });
 }
 
 __global__ void k_mark_visible(int P, const float* __restrict__ means3D, const float* __restrict__ vm,
@@ -258,23 +333,30 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means3D, const f
 
 }  // namespace
 
-void gs_launch_preprocess(const GsView& v, const float* means3D, const float* shs, const float* colors_precomp,
-                          const float* opacities, const float* scales, const float* rotations,
-                          const float* cov3D_precomp, int* radii, float4* rec, float4* acc, uint32_t* tile_cnt,
-                          GsDevStatus* status, cudaStream_t s) {
+void gs_launch_project(const GsView& v, const float* means3D, const float* opacities, const float* scales,
+                       const float* rotations, const float* cov3D_precomp, int* radii, float4* rec,
+                       uint32_t* vis_list, GsDevStatus* status, cudaStream_t s) {
     const int grid = (v.P + kThreads - 1) / kThreads;
-    k_preprocess<<<grid, kThreads, 0, s>>>(v, means3D, shs, colors_precomp, opacities, scales, rotations,
-                                          cov3D_precomp, radii, rec, acc, tile_cnt, status);
+    k_project<<<grid, kThreads, 0, s>>>(v, means3D, opacities, scales, rotations, cov3D_precomp, radii, rec, vis_list,
+                                       status);
+}
+void gs_launch_shade_count(const GsView& v, int num_sms, const float* means3D, const float* shs,
+                           const float* colors_precomp, const int* radii, float4* rec, float4* acc,
+                           const uint32_t* vis_list, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s) {
+    const int need = (v.P + kThreads - 1) / kThreads;
+    const int grid = need < num_sms * 4 ? need : num_sms * 4;
+    k_shade_count<<<grid, kThreads, 0, s>>>(v, means3D, shs, colors_precomp, radii, rec, acc, vis_list, tile_cnt, status);
 }
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status, GsDevStatus* host_slot,
                          cudaStream_t s) {
-    k_tile_scan<<<1, 1024, 0, s>>>(G, tile_cnt, tile_off, status, host_slot);
+    k_tile_scan<<<1, kScanT, 0, s>>>(G, tile_cnt, tile_off, status, host_slot);
 }
-void gs_launch_emit(const GsView& v, const int* radii, const float4* rec, const uint32_t* tile_off,
-                    uint32_t* tile_cur, GsDevStatus* status, unsigned long long* keys, long long capacity,
-                    cudaStream_t s) {
-    const int grid = (v.P + kThreads - 1) / kThreads;
-    k_emit<<<grid, kThreads, 0, s>>>(v, radii, rec, tile_off, tile_cur, status, keys, capacity);
+void gs_launch_emit(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
+                    const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status, unsigned long long* keys,
+                    long long capacity, cudaStream_t s) {
+    const int need = (v.P + kThreads - 1) / kThreads;
+    const int grid = need < num_sms * 4 ? need : num_sms * 4;
+    k_emit<<<grid, kThreads, 0, s>>>(v, radii, rec, vis_list, tile_off, tile_cur, status, keys, capacity);
 }
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s) {
     k_mark_visible<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, vm, present);

@@ -129,7 +129,7 @@ def _forward_impl(prep: _Prepared):
                 N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
                                             cap, img.data_ptr(), color.data_ptr(), depth.data_ptr(), stream))
         _cap_hint[idx] = int(counts.num_pairs)
-    return int(counts.num_rendered), color, depth, radii, geom, binning, img, cap
+    return int(counts.num_rendered), color, depth, radii, geom, binning, img, (cap, int(counts.num_visible))
 
 
 def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, want_colors: bool, want_cov: bool,
@@ -139,6 +139,7 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
     L = N.lib()
     out = out or {}
     f, dev, P, M = prep.frame, prep.device, prep.P, prep.M
+    cap, nvis = cap if isinstance(cap, tuple) else (cap, P)   # `_C` path: num_visible unknown -> bound by P
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     with torch.cuda.device(idx):
         stream = torch.cuda.current_stream(idx).cuda_stream
@@ -166,8 +167,10 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
         g.dL_dcolors = _p(dcol)
         g.dL_dcov3D = _p(dcov)
         gc = _dev_f32(grad_color, dev)
+        nscr = L.gs_backward_scratch_bytes(nvis)
+        scratch = torch.empty((nscr,), dtype=torch.uint8, device=dev)
         N.check(L.gs_backward(_ctx(idx), C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
-                              img.data_ptr(), _p(gc), None, C.byref(g), stream))
+                              img.data_ptr(), scratch.data_ptr(), nscr, _p(gc), None, C.byref(g), stream))
     return dm2, dcol, dop, dm3, dcov, dsh, dsc, drot
 
 
@@ -185,7 +188,7 @@ class _C:
         prep = _prepare(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                         projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered,
                         debug)
-        nr, color, depth, radii, geom, binning, img, _cap = _forward_impl(prep)
+        nr, color, depth, radii, geom, binning, img, _capnv = _forward_impl(prep)
         return nr, color, depth, radii, geom, binning, img
 
     @staticmethod

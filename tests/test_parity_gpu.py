@@ -165,7 +165,7 @@ def test_binning_order_matches_oracle():
     d = dev()
     f = oracle.rasterize_gaussians(*cases.binding_args(inp))
     prep = R._prepare(*cases.binding_args(inp, d))
-    nr, color, depth, radii, geom, binning, img, cap = R._forward_impl(prep)
+    nr, color, depth, radii, geom, binning, img, (cap, _nvis) = R._forward_impl(prep)
     assert nr == f.num_rendered
     G = ((case.W + 15) // 16) * ((case.H + 15) // 16)
     off = torch.empty(G + 1, dtype=torch.int32, device=d)
