@@ -1,32 +1,36 @@
 // Tile compositing, forward and backward (sm_100a).
 //
 // k_blend_fwd replaces RAST/cuda_rasterizer/forward.cu:261-391 (renderCUDA): front-to-back alpha compositing of
-//   colour + depth per 16x16 tile, same arithmetic per (pixel, splat).
-// k_blend_bwd replaces backward.cu:399-586 (renderCUDA backward), same arithmetic per (pixel, splat).
+//   colour + depth per 16x16 tile, same formulas per (pixel, splat).
+// k_blend_bwd replaces backward.cu:399-586 (renderCUDA backward), same formulas per (pixel, splat).
 //
-// Both kernels are FP32-issue bound (ncu: >90 % issue-slot utilisation, <2 % DRAM), so the design minimises
+// Both kernels are FP32-issue bound (ncu: ~90 % issue-slot utilisation, <2 % DRAM), so the design minimises
 // instructions per (pixel, splat) evaluation and skips evaluations that cannot contribute:
-//  * one CTA of 128 threads per tile; a warp owns an 8x8 pixel block and every thread TWO pixels (x, y) and
-//    (x, y+4): the shared-memory record fetch, the loop bookkeeping, the dx terms of the quadratic form and -- in
-//    the backward -- the cross-lane reduction are paid once per pixel pair;
+//  * one CTA of 64 threads per tile; a warp owns a 16x8 pixel block and every thread FOUR pixels of one column
+//    (x, y), (x, y+2), (x, y+4), (x, y+6): the shared-memory record fetch, the loop bookkeeping, the dx terms of
+//    the quadratic form and -- in the backward -- the cross-lane reduction are paid once per four pixels;
 //  * the per-splat record (xy, conic, opacity, rgb, depth) is fetched ONCE per (tile, splat) with 128-bit loads
 //    into shared memory; the reference gathers colour and depth from global memory per contributing
 //    (pixel, splat) (forward.cu:359,364);
-//  * while a batch of 128 splats is staged, the staging thread tests its splat against the four 8x8 blocks of
+//  * while a batch of 128 splats is staged, the staging thread tests its splats against the two 16x8 blocks of
 //    the tile (exact ellipse-vs-box test, gs_box_hit) and the warps ballot the results into a 128-bit mask per
 //    block.  A warp whose mask is sparse walks only the set bits; a dense mask falls back to the plain loop.
 //    Skipped splats cannot reach alpha >= 1/255 anywhere in the block (every pixel would skip them in the
 //    reference too, forward.cu:336-346), so no output changes;
+//  * exp(): ex2.approx of power*log2(e) (2 instructions instead of the 10 of expf).  Its ~5e-7 relative error is
+//    far inside the 1e-4 colour tolerance, but alpha is compared against 1/255; inside a band of 1e-7 around
+//    that threshold alpha is re-evaluated with expf so the skip decision is the reference's;
 //  * backward: the reference issues 9 global float atomicAdds per contributing (pixel, splat); here the 9 partials
-//    of the two pixels are summed in registers, reduced across the warp with a value-halving shuffle butterfly
-//    (12 shuffles for 9 values), across the 4 warps in shared memory, and leave the CTA as 128-bit vector
+//    of the four pixels are summed in registers, reduced across the warp with a value-halving shuffle butterfly
+//    (12 shuffles for 9 values), across the 2 warps in shared memory, and leave the CTA as 128-bit vector
 //    reductions: one per (tile, splat).  Warps start the reverse traversal at max(n_contrib) over their pixels.
 #include "gs_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 128;         // 4 warps; warp w -> 8x8 pixel block (w & 1, w >> 1)
-constexpr int kBatch = 128;           // splats staged per round (one per thread)
+constexpr int kThreads = 64;          // 2 warps; warp w -> pixel rows [8w, 8w+8) of the tile, 16 wide
+constexpr int kPix = 4;               // pixels per thread: (x, y0 + 2q), q = 0..3
+constexpr int kBatch = 128;           // splats staged per round (two per thread)
 constexpr int kWords = kBatch / 32;
 
 struct __align__(16) SRec {           // shared-memory copy of a splat record
@@ -37,127 +41,168 @@ struct __align__(16) SRec {           // shared-memory copy of a splat record
     uint32_t pad;
 };
 
-// 4-bit mask: which of the tile's four 8x8 pixel blocks the splat can touch
+// 2-bit mask: which of the tile's two 16x8 pixel blocks the splat can touch
 __device__ __forceinline__ uint32_t block_mask(const float4 a, const float4 b, const float thr, int tx0, int ty0) {
     uint32_t m = 0;
 #pragma unroll
-    for (int w = 0; w < 4; w++) {
-        const float x0 = (float)(tx0 + 8 * (w & 1)), y0 = (float)(ty0 + 8 * (w >> 1));
-        if (gs_box_hit(a.x, a.y, a.z, a.w, b.x, thr, x0, y0, x0 + 7.f, y0 + 7.f)) m |= 1u << w;
+    for (int w = 0; w < 2; w++) {
+        const float x0 = (float)tx0, y0 = (float)(ty0 + 8 * w);
+        if (gs_box_hit(a.x, a.y, a.z, a.w, b.x, thr, x0, y0, x0 + 15.f, y0 + 7.f)) m |= 1u << w;
     }
     return m;
 }
 
-struct FwdPix {
-    float T, C0, C1, C2, D, acc;
-    uint32_t last;
-    bool done;
-};
-
-// forward.cu:330-369 for one pixel.  qx = conic_a*dx*dx term etc. are formed exactly like the reference expression
-// power = -0.5f * (a*dx*dx + c*dy*dy) - b*dx*dy.
-__device__ __forceinline__ void fwd_eval(FwdPix& p, const SRec& r, const float dx, const float dy, const uint32_t pos1) {
-    const float power = -0.5f * (r.a.z * dx * dx + r.b.x * dy * dy) - r.a.w * dx * dy;
-    if (power > 0.0f) return;
-    const float alpha = fminf(0.99f, r.b.y * expf(power));
-    if (alpha < 1.0f / 255.0f) return;
-    const float test_T = p.T * (1.f - alpha);
-    if (test_T < 0.0001f) { p.done = true; return; }
-    p.C0 += r.b.z * alpha * p.T;
-    p.C1 += r.b.w * alpha * p.T;
-    p.C2 += r.c.x * alpha * p.T;
-    p.D += r.c.y * alpha * p.T;
-    p.acc += alpha * p.T;
-    p.T = test_T;
-    p.last = pos1;
+// opacity * exp(power): fast exponential, exact re-evaluation where the 1/255 decision could differ
+__device__ __forceinline__ float alpha_of(const float opacity, const float power, float& G) {
+    float g;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(power * 1.4426950408889634f));
+    float al = opacity * g;
+    if (fabsf(al - 1.0f / 255.0f) < 1e-7f) { g = expf(power); al = opacity * g; }
+    G = g;
+    return al;
 }
 
-__global__ void __launch_bounds__(kThreads)
+// Stages up to two splats per thread into shared memory and publishes the per-block hit masks.
+// slot j of the batch holds list position pos(j); returns nothing, fills sRec / sMask.  All threads must call.
+template <typename PosFn>
+__device__ __forceinline__ void stage_batch(SRec* sRec, uint32_t (*sMask)[kWords], const uint32_t* __restrict__ list,
+                                            const float4* __restrict__ rec, uint32_t beg, int cnt, int tx0, int ty0,
+                                            PosFn pos_of) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int h = 0; h < kBatch / kThreads; h++) {
+        const int j = tid + h * kThreads;
+        uint32_t m = 0;
+        if (j < cnt) {
+            const uint32_t id = list[beg + pos_of(j)];
+            const float4* r = rec + (size_t)GS_REC_V4 * id;
+            const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+            SRec s; s.a = a; s.b = b; s.c = make_float2(c.x, c.y); s.id = id; s.pad = 0;
+            sRec[j] = s;
+            m = block_mask(a, b, c.w, tx0, ty0);
+        }
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            const uint32_t bits = __ballot_sync(0xffffffffu, (m >> w) & 1u);
+            if (lane == 0) sMask[w][wid + 2 * h] = bits;      // word index = j / 32
+        }
+    }
+}
+
+struct FwdPix {
+    float T;                          // > 0: live transmittance; <= 0: pixel terminated (|T| is the value to report)
+    float C0, C1, C2, D, acc;         //      or outside the image
+    uint32_t last;
+};
+
+// forward.cu:330-369 for the thread's four pixels, written branch-free (predicated updates) so that the four
+// independent dependency chains interleave; the arithmetic of every taken update is the reference's.
+__device__ __forceinline__ void fwd_eval4(FwdPix* P, const SRec& r, const float dx, const float* dy, const uint32_t pos1) {
+    float power[kPix], alpha[kPix];
+    bool band = false;
+#pragma unroll
+    for (int q = 0; q < kPix; q++) {
+        power[q] = -0.5f * (r.a.z * dx * dx + r.b.x * dy[q] * dy[q]) - r.a.w * dx * dy[q];
+        float g;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(power[q] * 1.4426950408889634f));
+        alpha[q] = r.b.y * g;
+        band = band || (fabsf(alpha[q] - 1.0f / 255.0f) < 1e-7f);
+    }
+    if (band) {                       // rare: decide the 1/255 test with the reference's expf
+#pragma unroll
+        for (int q = 0; q < kPix; q++) alpha[q] = r.b.y * expf(power[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kPix; q++) {
+        FwdPix& p = P[q];
+        const float al = fminf(0.99f, alpha[q]);
+        const bool ok = !(power[q] > 0.0f) && !(al < 1.0f / 255.0f);
+        const float test_T = p.T * (1.f - al);
+        const bool term = ok && (test_T < 0.0001f);       // forward.cu:348-352 (also true for T <= 0)
+        const bool upd = ok && !term;
+        if (upd) {
+            p.C0 += r.b.z * al * p.T;
+            p.C1 += r.b.w * al * p.T;
+            p.C2 += r.c.x * al * p.T;
+            p.D += r.c.y * al * p.T;
+            p.acc += al * p.T;
+            p.last = pos1;
+        }
+        p.T = upd ? test_T : (term ? -fabsf(p.T) : p.T);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 16)
 k_blend_fwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ list,
             const float4* __restrict__ rec, const GsDevStatus* __restrict__ status, long long capacity,
             float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
             float* __restrict__ out_depth) {
     if ((long long)status->num_pairs > capacity) return;
     __shared__ SRec sRec[kBatch];
-    __shared__ uint32_t sMask[4][kWords];                // [pixel block][32-splat word]
+    __shared__ uint32_t sMask[2][kWords];                // [pixel block][32-splat word]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float bg0 = __ldg(v.bg), bg1 = __ldg(v.bg + 1), bg2 = __ldg(v.bg + 2);
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int tx0 = blockIdx.x * GS_TILE, ty0 = blockIdx.y * GS_TILE;
-    const uint32_t px = tx0 + 8 * (wid & 1) + (lane & 7);
-    const uint32_t py0 = ty0 + 8 * (wid >> 1) + (lane >> 3), py1 = py0 + 4;
-    const bool in0 = px < (uint32_t)v.W && py0 < (uint32_t)v.H;
-    const bool in1 = px < (uint32_t)v.W && py1 < (uint32_t)v.H;
-    const float pixx = (float)px, pixy0 = (float)py0, pixy1 = (float)py1;
+    const uint32_t px = tx0 + (lane & 15);
+    const uint32_t pyb = ty0 + 8 * wid + (lane >> 4);    // rows pyb + 2q
+    const float pixx = (float)px;
     const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
     const int n = (int)(end - beg);
 
-    FwdPix P0 = {1.0f, 0.f, 0.f, 0.f, 0.f, 0.000001f, 0u, !in0};
-    FwdPix P1 = {1.0f, 0.f, 0.f, 0.f, 0.f, 0.000001f, 0u, !in1};
+    FwdPix P[kPix];
+#pragma unroll
+    for (int q = 0; q < kPix; q++) {
+        const bool in = px < (uint32_t)v.W && (pyb + 2 * q) < (uint32_t)v.H;
+        P[q].T = in ? 1.0f : -1.0f;
+        P[q].C0 = P[q].C1 = P[q].C2 = P[q].D = 0.f; P[q].acc = 0.000001f; P[q].last = 0u;
+    }
 
     for (int base = 0; base < n; base += kBatch) {
-        if (__syncthreads_and(P0.done && P1.done)) break;
-        uint32_t m = 0;
-        if (base + tid < n) {
-            const uint32_t id = list[beg + base + tid];
-            const float4* r = rec + (size_t)GS_REC_V4 * id;
-            const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-            SRec s; s.a = a; s.b = b; s.c = make_float2(c.x, c.y); s.id = id; s.pad = 0;
-            sRec[tid] = s;
-            m = block_mask(a, b, c.w, tx0, ty0);
-        }
+        bool alldone = true;
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            const uint32_t bits = __ballot_sync(0xffffffffu, (m >> w) & 1u);
-            if (lane == 0) sMask[w][wid] = bits;
-        }
-        __syncthreads();
+        for (int q = 0; q < kPix; q++) alldone = alldone && (P[q].T <= 0.f);
+        if (__syncthreads_and(alldone)) break;
         const int cnt = min(kBatch, n - base);
+        stage_batch(sRec, sMask, list, rec, beg, cnt, tx0, ty0, [&](int j) { return base + j; });
+        __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < kWords; k++) {
             uint32_t bits = sMask[wid][k];
             if (bits == 0) continue;
-            if (__all_sync(0xffffffffu, P0.done && P1.done)) break;
+            alldone = true;
+#pragma unroll
+            for (int q = 0; q < kPix; q++) alldone = alldone && (P[q].T <= 0.f);
+            if (__all_sync(0xffffffffu, alldone)) break;
             const int wcnt = min(32, cnt - 32 * k);
-            if (__popc(bits) * 4 >= wcnt * 3) {
-                // dense: plain loop over the word, no bit scanning
-                for (int jj = 0; jj < wcnt; jj++) {
-                    const int j = 32 * k + jj;
-                    const SRec& r = sRec[j];
-                    const float dx = r.a.x - pixx;
-                    if (!P0.done) fwd_eval(P0, r, dx, r.a.y - pixy0, (uint32_t)(base + j + 1));
-                    if (!P1.done) fwd_eval(P1, r, dx, r.a.y - pixy1, (uint32_t)(base + j + 1));
-                }
-            } else {
-                while (bits) {
-                    const int j = 32 * k + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const SRec& r = sRec[j];
-                    const float dx = r.a.x - pixx;
-                    if (!P0.done) fwd_eval(P0, r, dx, r.a.y - pixy0, (uint32_t)(base + j + 1));
-                    if (!P1.done) fwd_eval(P1, r, dx, r.a.y - pixy1, (uint32_t)(base + j + 1));
-                }
+            // dense mask: visit every splat of the word (the per-pixel tests skip the misses anyway)
+            if (__popc(bits) * 4 >= wcnt * 3) bits = wcnt >= 32 ? 0xffffffffu : ((1u << wcnt) - 1u);
+            while (bits) {
+                const int j = 32 * k + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const SRec& r = sRec[j];
+                const float dx = r.a.x - pixx;
+                float dy[kPix];
+#pragma unroll
+                for (int q = 0; q < kPix; q++) dy[q] = r.a.y - (float)(pyb + 2 * q);
+                fwd_eval4(P, r, dx, dy, (uint32_t)(base + j + 1));
             }
         }
     }
     const size_t HW = (size_t)v.H * v.W;
-    if (in0) {
-        const uint32_t pix_id = (uint32_t)v.W * py0 + px;
-        final_T[pix_id] = P0.T;
-        n_contrib[pix_id] = P0.last;
-        out_color[pix_id] = P0.C0 + P0.T * bg0;
-        out_color[HW + pix_id] = P0.C1 + P0.T * bg1;
-        out_color[2 * HW + pix_id] = P0.C2 + P0.T * bg2;
-        out_depth[pix_id] = (P0.acc > 0.5f) ? P0.D / P0.acc : 0.f;
-    }
-    if (in1) {
-        const uint32_t pix_id = (uint32_t)v.W * py1 + px;
-        final_T[pix_id] = P1.T;
-        n_contrib[pix_id] = P1.last;
-        out_color[pix_id] = P1.C0 + P1.T * bg0;
-        out_color[HW + pix_id] = P1.C1 + P1.T * bg1;
-        out_color[2 * HW + pix_id] = P1.C2 + P1.T * bg2;
-        out_depth[pix_id] = (P1.acc > 0.5f) ? P1.D / P1.acc : 0.f;
+#pragma unroll
+    for (int q = 0; q < kPix; q++) {
+        const uint32_t py = pyb + 2 * q;
+        if (px < (uint32_t)v.W && py < (uint32_t)v.H) {
+            const uint32_t pix_id = (uint32_t)v.W * py + px;
+            const float T = fabsf(P[q].T);
+            final_T[pix_id] = T;
+            n_contrib[pix_id] = P[q].last;
+            out_color[pix_id] = P[q].C0 + T * bg0;
+            out_color[HW + pix_id] = P[q].C1 + T * bg1;
+            out_color[2 * HW + pix_id] = P[q].C2 + T * bg2;
+            out_depth[pix_id] = (P[q].acc > 0.5f) ? P[q].D / P[q].acc : 0.f;
+        }
     }
 }
 
@@ -187,91 +232,114 @@ __device__ __forceinline__ void warp_reduce9(float* v, const int lane) {
 }
 
 struct BwdPix {
-    float T, T_final, last_alpha;
-    float ar0, ar1, ar2;              // accum_rec
-    float lc0, lc1, lc2;              // last_color
-    float g0, g1, g2, bg_dot;         // dL_dpixel, bg . dL_dpixel
+    float T;
+    float tb;                         // -T_final * (bg . dL_dpixel)
+    float ar0, ar1, ar2;              // accum_rec, already advanced past the last contributing splat
+    float g0, g1, g2;                 // dL_dpixel
     int last_contributor;
 };
 
-// backward.cu:487-584 for one pixel: returns false if this (pixel, splat) does not contribute, else adds its 9
-// partial derivatives to vv[]
-__device__ __forceinline__ bool bwd_eval(BwdPix& p, const SRec& r, const float dx, const float dy, const int pos,
-                                         const float ddelx_dx, const float ddely_dy, float* vv) {
-    if (!(pos < p.last_contributor)) return false;
-    const float power = -0.5f * (r.a.z * dx * dx + r.b.x * dy * dy) - r.a.w * dx * dy;
-    if (power > 0.0f) return false;
-    const float G = expf(power);
-    const float alpha = fminf(0.99f, r.b.y * G);
-    if (alpha < 1.0f / 255.0f) return false;
-    p.T = p.T / (1.f - alpha);
-    const float dchannel_dcolor = alpha * p.T;
-    float dL_dalpha = 0.0f;
-    const float c0 = r.b.z, c1 = r.b.w, c2 = r.c.x;
-    p.ar0 = p.last_alpha * p.lc0 + (1.f - p.last_alpha) * p.ar0; p.lc0 = c0;
-    dL_dalpha += (c0 - p.ar0) * p.g0;
-    p.ar1 = p.last_alpha * p.lc1 + (1.f - p.last_alpha) * p.ar1; p.lc1 = c1;
-    dL_dalpha += (c1 - p.ar1) * p.g1;
-    p.ar2 = p.last_alpha * p.lc2 + (1.f - p.last_alpha) * p.ar2; p.lc2 = c2;
-    dL_dalpha += (c2 - p.ar2) * p.g2;
-    vv[0] += dchannel_dcolor * p.g0; vv[1] += dchannel_dcolor * p.g1; vv[2] += dchannel_dcolor * p.g2;
-    dL_dalpha *= p.T;
-    p.last_alpha = alpha;
-    dL_dalpha += (-p.T_final / (1.f - alpha)) * p.bg_dot;
-    const float dL_dG = r.b.y * dL_dalpha;
-    const float gdx = G * dx, gdy = G * dy;
-    const float dG_ddelx = -gdx * r.a.z - gdy * r.a.w;
-    const float dG_ddely = -gdy * r.b.x - gdx * r.a.w;
-    vv[3] += dL_dG * dG_ddelx * ddelx_dx;
-    vv[4] += dL_dG * dG_ddely * ddely_dy;
-    vv[5] += -0.5f * gdx * dx * dL_dG;
-    vv[6] += -0.5f * gdx * dy * dL_dG;
-    vv[7] += -0.5f * gdy * dy * dL_dG;
-    vv[8] += G * dL_dalpha;
-    return true;
+// backward.cu:487-584 for the thread's four pixels, branch-free: every pixel evaluates the full expression and a
+// predicate zeroes what a skipped (pixel, splat) would add.  Returns whether any of the four contributed.
+// 1/(1-alpha) is formed once (reciprocal) for both quotients: the gradient tolerance is 1e-3 relative, the
+// difference to two IEEE divisions is ~1e-7.
+__device__ __forceinline__ bool bwd_eval4(BwdPix* Q, const SRec& r, const float dx, const float* dy, const int pos,
+                                          const float ddelx_dx, const float ddely_dy, float* vv) {
+    float power[kPix], G[kPix], alpha[kPix];
+    bool band = false;
+#pragma unroll
+    for (int q = 0; q < kPix; q++) {
+        power[q] = -0.5f * (r.a.z * dx * dx + r.b.x * dy[q] * dy[q]) - r.a.w * dx * dy[q];
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G[q]) : "f"(power[q] * 1.4426950408889634f));
+        alpha[q] = r.b.y * G[q];
+        band = band || (fabsf(alpha[q] - 1.0f / 255.0f) < 1e-7f);
+    }
+    if (band) {                       // rare: same skip decision as the forward pass
+#pragma unroll
+        for (int q = 0; q < kPix; q++) { G[q] = expf(power[q]); alpha[q] = r.b.y * G[q]; }
+    }
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < kPix; q++) {
+        BwdPix& p = Q[q];
+        const float al = fminf(0.99f, alpha[q]);
+        const bool ok = (pos < p.last_contributor) && !(power[q] > 0.0f) && !(al < 1.0f / 255.0f);
+        any = any || ok;
+        const float a_ = ok ? al : 0.f;                     // alpha = 0 makes every update below a no-op
+        const float inv = __frcp_rn(1.f - a_);
+        const float T = p.T * inv;
+        const float dchannel_dcolor = a_ * T;
+        float dL_dalpha = 0.0f;
+        const float c0 = r.b.z, c1 = r.b.w, c2 = r.c.x;
+        // backward.cu:520-528 updates accum_rec lazily (last_alpha * last_color + (1 - last_alpha) * accum_rec at
+        // the NEXT contributing splat); the same expression is evaluated here eagerly, right after use.
+        dL_dalpha += (c0 - p.ar0) * p.g0;
+        dL_dalpha += (c1 - p.ar1) * p.g1;
+        dL_dalpha += (c2 - p.ar2) * p.g2;
+        p.ar0 = a_ * c0 + (1.f - a_) * p.ar0;
+        p.ar1 = a_ * c1 + (1.f - a_) * p.ar1;
+        p.ar2 = a_ * c2 + (1.f - a_) * p.ar2;
+        p.T = T;
+        vv[0] += dchannel_dcolor * p.g0; vv[1] += dchannel_dcolor * p.g1; vv[2] += dchannel_dcolor * p.g2;
+        dL_dalpha *= T;
+        dL_dalpha += p.tb * inv;
+        dL_dalpha = ok ? dL_dalpha : 0.f;
+        const float dL_dG = r.b.y * dL_dalpha;
+        const float Gq = ok ? G[q] : 0.f;                   // keeps inf/NaN of skipped splats out of the sums
+        const float gdx = Gq * dx, gdy = Gq * dy[q];
+        const float dG_ddelx = -gdx * r.a.z - gdy * r.a.w;
+        const float dG_ddely = -gdy * r.b.x - gdx * r.a.w;
+        vv[3] += dL_dG * dG_ddelx * ddelx_dx;
+        vv[4] += dL_dG * dG_ddely * ddely_dy;
+        vv[5] += -0.5f * gdx * dx * dL_dG;
+        vv[6] += -0.5f * gdx * dy[q] * dL_dG;
+        vv[7] += -0.5f * gdy * dy[q] * dL_dG;
+        vv[8] += Gq * dL_dalpha;
+    }
+    return any;
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 10)
 k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ list,
             const float4* __restrict__ rec, const float* __restrict__ final_Ts,
             const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix, float4* __restrict__ acc) {
     __shared__ SRec sRec[kBatch];
     __shared__ float sAcc[kBatch * 9];
-    __shared__ uint32_t sMask[4][kWords];
+    __shared__ uint32_t sMask[2][kWords];
     __shared__ int sMax[kThreads / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int tx0 = blockIdx.x * GS_TILE, ty0 = blockIdx.y * GS_TILE;
-    const uint32_t px = tx0 + 8 * (wid & 1) + (lane & 7);
-    const uint32_t py0 = ty0 + 8 * (wid >> 1) + (lane >> 3), py1 = py0 + 4;
-    const bool in0 = px < (uint32_t)v.W && py0 < (uint32_t)v.H;
-    const bool in1 = px < (uint32_t)v.W && py1 < (uint32_t)v.H;
-    const float pixx = (float)px, pixy0 = (float)py0, pixy1 = (float)py1;
+    const uint32_t px = tx0 + (lane & 15);
+    const uint32_t pyb = ty0 + 8 * wid + (lane >> 4);
+    const float pixx = (float)px;
     const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
     if (beg == end) return;
 
     const size_t HW = (size_t)v.H * v.W;
     const float bgc0 = __ldg(v.bg), bgc1 = __ldg(v.bg + 1), bgc2 = __ldg(v.bg + 2);
-    BwdPix Q[2];
+    BwdPix Q[kPix];
+    int wmax = 0;
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const bool in = q ? in1 : in0;
-        const uint32_t pix_id = (uint32_t)v.W * (q ? py1 : py0) + px;
+    for (int q = 0; q < kPix; q++) {
+        const uint32_t py = pyb + 2 * q;
+        const bool in = px < (uint32_t)v.W && py < (uint32_t)v.H;
+        const uint32_t pix_id = (uint32_t)v.W * py + px;
         BwdPix& p = Q[q];
-        p.T_final = in ? final_Ts[pix_id] : 0.f;
-        p.T = p.T_final;
+        const float T_final = in ? final_Ts[pix_id] : 0.f;
+        p.T = T_final;
         p.last_contributor = in ? (int)n_contrib[pix_id] : 0;
         p.g0 = in ? dL_dpix[pix_id] : 0.f; p.g1 = in ? dL_dpix[HW + pix_id] : 0.f; p.g2 = in ? dL_dpix[2 * HW + pix_id] : 0.f;
         float bd = 0.f;
         bd += bgc0 * p.g0; bd += bgc1 * p.g1; bd += bgc2 * p.g2;
-        p.bg_dot = bd;
-        p.last_alpha = 0.f; p.ar0 = p.ar1 = p.ar2 = 0.f; p.lc0 = p.lc1 = p.lc2 = 0.f;
+        p.tb = -T_final * bd;
+        p.ar0 = p.ar1 = p.ar2 = 0.f;
+        wmax = max(wmax, p.last_contributor);
     }
     const float ddelx_dx = 0.5 * v.W, ddely_dy = 0.5 * v.H;
 
     // max of n_contrib over the warp's block / over the tile: nothing behind it contributes
-    int wmax = max(Q[0].last_contributor, Q[1].last_contributor);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     if (lane == 0) sMax[wid] = wmax;
@@ -287,56 +355,51 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
 
     for (int hi = maxc; hi > 0; hi -= kBatch) {
         __syncthreads();
-        const int pos = hi - 1 - tid;            // position in the tile list this thread stages (j = tid)
-        uint32_t m = 0;
-        if (pos >= 0) {
-            const uint32_t id = list[beg + pos];
-            const float4* r = rec + (size_t)GS_REC_V4 * id;
-            const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-            SRec s; s.a = a; s.b = b; s.c = make_float2(c.x, c.y); s.id = id; s.pad = 0;
-            sRec[tid] = s;
-            m = block_mask(a, b, c.w, tx0, ty0);
-        }
-#pragma unroll
-        for (int k = 0; k < 9; k++) sAcc[tid * 9 + k] = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            const uint32_t bits = __ballot_sync(0xffffffffu, (m >> w) & 1u);
-            if (lane == 0) sMask[w][wid] = bits;
-        }
-        __syncthreads();
         const int cnt = min(kBatch, hi);
+        // slot j holds list position hi-1-j: reverse traversal = increasing j
+        stage_batch(sRec, sMask, list, rec, beg, cnt, tx0, ty0, [&](int j) { return hi - 1 - j; });
+#pragma unroll
+        for (int h = 0; h < kBatch / kThreads; h++)
+#pragma unroll
+            for (int k = 0; k < 9; k++) sAcc[(tid + h * kThreads) * 9 + k] = 0.f;
+        __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < kWords; k++) {
             uint32_t bits = sMask[wid][k];
             while (bits) {
                 const int j = 32 * k + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const int p = hi - 1 - j;        // 0-based list position; reverse traversal = increasing j
+                const int p = hi - 1 - j;        // 0-based list position
                 if (p >= wmax) continue;         // behind every pixel of this block
                 const SRec& r = sRec[j];
                 const float dx = r.a.x - pixx;
                 float vv[9];
 #pragma unroll
                 for (int q = 0; q < 9; q++) vv[q] = 0.f;
-                const bool c0 = bwd_eval(Q[0], r, dx, r.a.y - pixy0, p, ddelx_dx, ddely_dy, vv);
-                const bool c1 = bwd_eval(Q[1], r, dx, r.a.y - pixy1, p, ddelx_dx, ddely_dy, vv);
-                if (!__any_sync(0xffffffffu, c0 || c1)) continue;
+                float dy[kPix];
+#pragma unroll
+                for (int q = 0; q < kPix; q++) dy[q] = r.a.y - (float)(pyb + 2 * q);
+                const bool any = bwd_eval4(Q, r, dx, dy, p, ddelx_dx, ddely_dy, vv);
+                if (!__any_sync(0xffffffffu, any)) continue;
                 warp_reduce9(vv, lane);
                 if (owner) atomicAdd(&sAcc[j * 9 + slot], vv[0]);
             }
         }
         __syncthreads();
-        if (tid < cnt) {
-            float r[9];
-            bool any = false;
 #pragma unroll
-            for (int k = 0; k < 9; k++) { r[k] = sAcc[tid * 9 + k]; any = any || (r[k] != 0.f); }
-            if (any) {
-                float4* dst = acc + (size_t)3 * sRec[tid].id;
-                atomicAdd(dst, make_float4(r[3], r[4], r[5], r[6]));
-                atomicAdd(dst + 1, make_float4(r[7], r[8], r[0], r[1]));
-                atomicAdd(reinterpret_cast<float*>(dst + 2), r[2]);
+        for (int h = 0; h < kBatch / kThreads; h++) {
+            const int j = tid + h * kThreads;
+            if (j < cnt) {
+                float r[9];
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < 9; k++) { r[k] = sAcc[j * 9 + k]; any = any || (r[k] != 0.f); }
+                if (any) {
+                    float4* dst = acc + (size_t)3 * sRec[j].id;
+                    atomicAdd(dst, make_float4(r[3], r[4], r[5], r[6]));
+                    atomicAdd(dst + 1, make_float4(r[7], r[8], r[0], r[1]));
+                    atomicAdd(reinterpret_cast<float*>(dst + 2), r[2]);
+                }
             }
         }
     }

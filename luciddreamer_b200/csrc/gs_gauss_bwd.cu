@@ -275,7 +275,8 @@ k_grad_write(const int P, const int M, const int* __restrict__ radii, const floa
         if (g.drots) {
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             if (cl >= 0) { const float* q = s_row + cl * kRow + 9; r = make_float4(q[0], q[1], q[2], q[3]); }
-            reinterpret_cast<float4*>(g.drots)[i] = r;
+            if ((reinterpret_cast<uintptr_t>(g.drots) & 15) == 0) reinterpret_cast<float4*>(g.drots)[i] = r;
+            else { float* d = g.drots + 4 * i; d[0] = r.x; d[1] = r.y; d[2] = r.z; d[3] = r.w; }
         }
     }
     if (g.dsh && M > 0) {
@@ -283,7 +284,7 @@ k_grad_write(const int P, const int M, const int* __restrict__ radii, const floa
         const long long rows = min((long long)kT, (long long)P - row0);
         float* dst = g.dsh + row0 * M3;
         const int total = (int)rows * M3;
-        if (M3 == 48) {                                  // M = 16: 12 float4 per row, compile-time index maths
+        if (M3 == 48 && (reinterpret_cast<uintptr_t>(g.dsh) & 15) == 0) {   // M = 16: 12 float4 per row
             const int total4 = total >> 2;
             for (int f = tid; f < total4; f += kT) {
                 const int row = f / 12, j = f - row * 12;

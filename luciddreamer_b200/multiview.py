@@ -34,13 +34,16 @@ class GradBucket:
     def __init__(self, P: int, M: int, device, dtype=torch.float32):
         self.P, self.M = int(P), int(M)
         self.width = 3 + 3 * self.M + 1 + 3 + 4
-        self.flat = torch.zeros(self.P * self.width, dtype=dtype, device=device)
+        widths = (3, 3 * self.M, 1, 3, 4)
+        seg = [(self.P * w + 63) // 64 * 64 for w in widths]      # segment starts stay 256-byte aligned
+        self.flat = torch.zeros(sum(seg), dtype=dtype, device=device)
         o = 0
+        it = iter(seg)
 
         def take(w, shape):
             nonlocal o
             v = self.flat[o:o + self.P * w].view(*shape)
-            o += self.P * w
+            o += next(it)
             return v
 
         self.means3D = take(3, (self.P, 3))

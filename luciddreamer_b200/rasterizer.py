@@ -101,8 +101,9 @@ def _forward_impl(prep: _Prepared):
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom = torch.empty((L.gs_geom_bytes(P),), **u8)
-        img = torch.empty((L.gs_image_bytes(W, H),), **u8)
+        ng, ni = L.gs_geom_bytes(P), L.gs_image_bytes(W, H)
+        scratch = torch.empty((ng + ni,), **u8)          # one allocation; both sizes are multiples of 256 B
+        geom, img = scratch[:ng], scratch[ng:]
         ticket = C.c_int32(-1)
         N.check(L.gs_forward_preprocess(ctx, C.byref(f), geom.data_ptr(), img.data_ptr(), radii.data_ptr(), stream,
                                         C.byref(ticket)))
@@ -145,13 +146,24 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
         stream = torch.cuda.current_stream(idx).cuda_stream
         f32 = dict(dtype=torch.float32, device=dev)
         g = N.GsGrads()
+        # every gradient without a caller-provided sink is a view of ONE flat allocation, in bucket order
+        # [means3D | sh | opacity | scales | rotations | means2D]
+        need = {"dm3": 3, "dsh": 3 * M, "dop": 1, "dsc": 3, "drot": 4, "dm2": 3}
+        missing = [k for k in need if out.get(k) is None]
+        offs, o = {}, 0
+        for k in missing:                      # segment starts stay 256-byte aligned (128-bit stores in the kernels)
+            offs[k] = o
+            o += (P * need[k] + 63) // 64 * 64
+        flat = torch.empty((o,), **f32) if missing else None
+
         def dst(key, shape, zero=False):
             t = out.get(key)
             if t is not None:
                 if tuple(t.shape) != tuple(shape) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
                     raise RuntimeError(f"gradient sink '{key}' must be a contiguous f32 {tuple(shape)} tensor on {dev}")
-                return t.zero_() if zero else t
-            return torch.zeros(shape, **f32) if zero else torch.empty(shape, **f32)
+            else:
+                t = flat[offs[key]:offs[key] + P * need[key]].view(shape)
+            return t.zero_() if zero else t
 
         dm3 = dst("dm3", (P, 3)); dm2 = dst("dm2", (P, 3))
         dop = dst("dop", (P, 1))

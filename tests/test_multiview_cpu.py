@@ -23,14 +23,17 @@ def test_shard_views_partitions():
 
 
 def test_bucket_layout_is_one_flat_buffer():
-    b = MV.GradBucket(10, 16, "cpu")
-    assert b.width == 59 and b.flat.numel() == 590 and b.nbytes() == 590 * 4
+    b = MV.GradBucket(64, 16, "cpu")
+    assert b.width == 59 and b.flat.numel() == 64 * 59 and b.nbytes() == 64 * 59 * 4
     b.means3D.fill_(1); b.shs.fill_(2); b.opacities.fill_(3); b.scales.fill_(4); b.rotations.fill_(5)
     f = b.flat.numpy()
-    assert (f[:30] == 1).all() and (f[30:510] == 2).all() and (f[510:520] == 3).all()
-    assert (f[520:550] == 4).all() and (f[550:] == 5).all()
-    for v in (b.means3D, b.shs, b.opacities, b.scales, b.rotations):
-        assert v.is_contiguous() and v.data_ptr() >= b.flat.data_ptr()
+    assert (f[:192] == 1).all() and (f[192:192 + 3072] == 2).all() and (f[3264:3328] == 3).all()
+    assert (f[3328:3520] == 4).all() and (f[3520:] == 5).all()
+    odd = MV.GradBucket(10, 16, "cpu")             # ragged P: segments are padded to 256-byte boundaries
+    for bb in (b, odd):
+        for v in (bb.means3D, bb.shs, bb.opacities, bb.scales, bb.rotations):
+            assert v.is_contiguous() and (v.data_ptr() - bb.flat.data_ptr()) % 256 == 0
+    assert odd.means3D.shape == (10, 3) and odd.shs.shape == (10, 16, 3) and odd.rotations.shape == (10, 4)
 
 
 def test_camera_conventions():
