@@ -342,8 +342,12 @@ def cpu_baseline(scene, cam, cot, D, budget_s=12.0, max_steps=3):
 
 
 def shared_model_leg(scene, cam, cot, dev, D, steps, warmup, world):
-    """Config-5 style step: every rank renders its view straight into a flat gradient bucket, then ONE NCCL
-    all-reduce(sum) of the bucket (59 floats/Gaussian)."""
+    """Config-5 style step on every rank: forward+backward of its view, then the ONE exchange of the path -- the sum
+    of the per-Gaussian gradients over all views.  Two implementations are timed:
+      fused  the final backward kernel adds the rows of the VISIBLE Gaussians straight into every rank's symmetric
+             bucket (multimem.red through the NVSwitch multicast address, or peer stores), bracketed by two
+             device-side barriers -- traffic ~ 59 floats x P_vis per rank
+      nccl   dense local bucket + NCCL all-reduce(sum) of 59 floats x P (the baseline this replaces)"""
     from luciddreamer_b200 import multiview as MV
     from luciddreamer_b200 import rasterizer as R
     params = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
@@ -351,26 +355,49 @@ def shared_model_leg(scene, cam, cot, dev, D, steps, warmup, world):
     rs = R.GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, bg, 1.0,
                                          cam.viewmatrix.to(dev), cam.projmatrix.to(dev), D, cam.campos.to(dev), False, False)
     P, M = params["means3D"].shape[0], params["shs"].shape[1]
-    bucket = MV.GradBucket(P, M, dev)
     dm2 = torch.empty(P, 3, device=dev)
+    rays = cam.image_height * cam.image_width
 
-    def step():
-        MV.view_step(params, rs, cot, bucket=bucket, means2D_grad=dm2)
-        MV.allreduce_bucket(bucket)
+    def timed(step):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record(); torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
 
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record(); torch.cuda.synchronize(); dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
-    return {"ms_per_step": ms, "value": world * cam.image_height * cam.image_width / ms / 1e3, "unit": "Mrays/s",
-            "allreduce_bytes": bucket.nbytes(), "collective": "nccl all_reduce(sum) of the flat gradient bucket"}
+    dense = MV.GradBucket(P, M, dev)
+
+    def step_nccl():
+        MV.view_step(params, rs, cot, bucket=dense, means2D_grad=dm2)
+        MV.allreduce_bucket(dense)
+
+    ms_nccl = timed(step_nccl)
+    out = {"nccl_allreduce": {"ms_per_step": ms_nccl, "value": world * rays / ms_nccl / 1e3, "unit": "Mrays/s",
+                              "bytes_reduced_per_rank": dense.nbytes()}}
+    try:
+        symm = MV.SymmGradBucket(P, M, dev)
+
+        def step_fused():
+            symm.begin_step()
+            MV.view_step(params, rs, cot, bucket=symm, means2D_grad=dm2)
+            symm.end_step()
+
+        ms_f = timed(step_fused)
+        torch.cuda.synchronize()
+        err = float(((symm.flat - dense.flat).norm() / dense.flat.norm().clamp_min(1e-30)).item())
+        out["fused_peer_reduce"] = {"ms_per_step": ms_f, "value": world * rays / ms_f / 1e3, "unit": "Mrays/s",
+                                    "multicast": bool(symm.peers["mc"]), "rel_err_vs_nccl": err}
+        out["ms_per_step"], out["value"], out["unit"] = ms_f, world * rays / ms_f / 1e3, "Mrays/s"
+    except Exception as ex:                     # symmetric memory unavailable: the NCCL leg is the result
+        out["fused_peer_reduce"] = {"unavailable": str(ex)[:200]}
+        out["ms_per_step"], out["value"], out["unit"] = ms_nccl, world * rays / ms_nccl / 1e3, "Mrays/s"
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------- main

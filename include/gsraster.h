@@ -89,6 +89,18 @@ typedef struct GsGrads {
     float* dL_dscales;    /* [P,3] */
     float* dL_drotations; /* [P,4] */
     float* dL_dcov3D;     /* [P,6] */
+    /* Data-parallel shared-model step (no reference counterpart).  peer_world > 0: instead of
+     * writing dL_dmeans3D / dL_dsh / dL_dopacity / dL_dscales / dL_drotations locally, the final kernel ADDS the rows
+     * of this view's visible Gaussians into every rank's gradient bucket: peer_buckets[r] is the (peer-mapped) base
+     * of rank r's bucket for r < peer_world (<= 16), peer_multicast optionally the NVSwitch multicast address of the
+     * same buckets (then one multimem.red per element replaces peer_world stores), peer_seg_off[5] the float
+     * offsets of the five segments inside a bucket.  Buckets must be zeroed and all ranks synchronised before,
+     * and synchronised again after, by the caller.  dL_dmeans2D is still written locally. */
+    int32_t peer_world;
+    int32_t peer_pad;
+    void* const* peer_buckets;   /* HOST array of peer_world device pointers */
+    void* peer_multicast;
+    const int64_t* peer_seg_off; /* HOST array [5] */
 } GsGrads;
 
 /* Host-visible result of the per-Gaussian pass. */

@@ -28,7 +28,9 @@ class GsFrame(C.Structure):
 class GsGrads(C.Structure):
     _fields_ = [("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dsh", C.c_void_p),
                 ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dscales", C.c_void_p),
-                ("dL_drotations", C.c_void_p), ("dL_dcov3D", C.c_void_p)]
+                ("dL_drotations", C.c_void_p), ("dL_dcov3D", C.c_void_p),
+                ("peer_world", C.c_int32), ("peer_pad", C.c_int32), ("peer_buckets", C.POINTER(C.c_void_p)),
+                ("peer_multicast", C.c_void_p), ("peer_seg_off", C.POINTER(C.c_int64))]
 
 
 class GsCounts(C.Structure):

@@ -78,7 +78,8 @@ int debug_sync(const GsFrame* f, cudaStream_t s, const char* what) {
 constexpr int kNumKernels = GS_NUM_KERNELS;
 static const char* const kKernelNames[kNumKernels] = {"k_project", "k_tile_scan", "k_emit", "k_tile_sort",
                                                       "k_tile_sort_big", "k_blend_fwd", "k_blend_bwd", "k_grad_vis",
-                                                      "k_shade_count", "k_grad_write"};
+                                                      "k_shade_count", "k_grad_write"};   // slot 9 also times
+                                                                                          // k_grad_reduce_peers
 
 struct GsContext {
     int device;
@@ -276,6 +277,16 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
                                            f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec, gl.acc,
                                            gl.vis_list, il.status, gout, s));
     if ((rc = debug_sync(f, s, "grad_vis"))) return rc;
+    if (grads->peer_world > 0) {
+        // data-parallel shared-model step: the five parameter gradients are reduced straight into every rank's
+        // bucket (peer stores / NVSwitch multicast); only dL_dmeans2D is written locally
+        if (grads->peer_world > GS_MAX_PEERS || !grads->peer_buckets) return fail(GS_EINVAL, "bad peer arguments");
+        GS_TIMED(ctx, 9, s, gs_launch_grad_reduce_peers(f->P, v.M, radii, gl.acc, gout, grads->dL_dmeans2D,
+                                                        (float* const*)grads->peer_buckets, grads->peer_world,
+                                                        (float*)grads->peer_multicast, (const long long*)grads->peer_seg_off, s));
+        if ((rc = debug_sync(f, s, "grad_reduce_peers"))) return rc;
+        return GS_OK;
+    }
     GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, s));
     if ((rc = debug_sync(f, s, "grad_write"))) return rc;
     // outputs the fused kernel does not produce in this input mode are defined as zeros (reference: torch::zeros)

@@ -26,6 +26,8 @@ struct GsDevStatus {         // lives at the end of the image buffer
     unsigned long long num_visible;
     unsigned int overflow;             // set by k_emit when num_pairs > capacity at render time
     unsigned int n_big;                // tiles queued for k_tile_sort_big
+    unsigned int n_mid;                // tiles queued for k_tile_sort_mid
+    unsigned int pad;
 };
 
 struct GsImageLayout {
@@ -73,6 +75,7 @@ __host__ inline GsGeomLayout gs_geom_layout(void* base, int P) {
     return L;
 }
 
+#define GS_MAX_PEERS 16
 #define GS_GOUT_FLOATS 44    // compact per-visible-Gaussian gradient row (gs_gauss_bwd.cu)
 
 struct GsBinLayout {
@@ -306,4 +309,7 @@ void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, cons
 void gs_grad_write_init();
 void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
                           cudaStream_t s);
+void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* acc, const float* gout, float* dmeans2D,
+                                 float* const* peers, int world, float* mc, const long long* seg_off,
+                                 cudaStream_t s);
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);

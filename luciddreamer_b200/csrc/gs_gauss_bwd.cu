@@ -315,7 +315,106 @@ k_grad_write(const int P, const int M, const int* __restrict__ radii, const floa
     }
 }
 
+// Fused "final gradient -> peer reduce" for the shared-model data-parallel step: instead of writing
+// a dense local gradient and all-reducing 59 floats x P over NCCL, every rank adds the rows of its VISIBLE
+// Gaussians straight into every rank's (pre-zeroed, symmetric) gradient bucket with red.global.add.f32 over
+// NVLink peer mappings -- or with ONE multimem.red per element through the NVSwitch multicast address when the
+// buckets are bound to a multicast object.  Traffic is 59 floats x P_vis per rank and peer instead of a dense
+// 2 x 59 x P all-reduce; rows of invisible Gaussians are never touched.  dL_dmeans2D stays local (it feeds the
+// per-view densification statistic, scene/gaussian_model.py:405-407).
+struct GsPeerArgs {
+    float* peers[GS_MAX_PEERS];       // bucket base of every rank (peer-mapped), [0, world)
+    float* mc;                        // multicast address of the bucket, or nullptr
+    int world;
+    long long off_m3, off_sh, off_op, off_sc, off_rot;   // segment offsets inside the bucket, in floats
+};
+
+__device__ __forceinline__ void peer_add(const GsPeerArgs& pa, long long off, float v) {
+    if (v == 0.f) return;
+    if (pa.mc) {
+        asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(pa.mc + off), "f"(v) : "memory");
+    } else {
+        for (int r = 0; r < pa.world; r++) atomicAdd(pa.peers[r] + off, v);
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+k_grad_reduce_peers(const int P, const int M, const int* __restrict__ radii, const float4* __restrict__ acc,
+                    const float* __restrict__ gout, float* __restrict__ dmeans2D, const GsPeerArgs pa) {
+    extern __shared__ __align__(16) float s_row[];
+    __shared__ int s_rowidx[kT];
+    __shared__ int s_slot[kT];
+    __shared__ int s_count;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * kT;
+    const long long i = row0 + tid;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const bool vis = i < P && radii[i] > 0;
+    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    int cl = -1;
+    if (m) {
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&s_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (vis) cl = base + __popc(m & ((1u << lane) - 1u));
+    }
+    s_slot[tid] = cl;
+    if (vis) {
+        s_rowidx[cl] = tid;
+        const uint32_t slot = __float_as_uint(__ldg(reinterpret_cast<const float*>(acc + (size_t)3 * i + 2) + 3));
+        const float4* src = reinterpret_cast<const float4*>(gout + (size_t)slot * kRow);
+        float4* dstr = reinterpret_cast<float4*>(s_row + cl * kRow);
+#pragma unroll
+        for (int k = 0; k < kRow / 4; k++) dstr[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    if (dmeans2D) {                                      // local, dense (zeros for invisible rows)
+        const long long base = row0 * 3, lim = (long long)P * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int e = tid + kT * k;
+            const int row = e / 3, comp = e - row * 3;
+            const int c2 = s_slot[row];
+            if (base + e < lim) dmeans2D[base + e] = (c2 < 0 || comp == 2) ? 0.f : s_row[c2 * kRow + 3 + comp];
+        }
+    }
+    const int nv = s_count;
+    const int M3 = M * 3;
+    const int per = 3 + M3 + 1 + 3 + 4;                  // floats per Gaussian in the bucket
+    for (int e = tid; e < nv * per; e += kT) {
+        const int c2 = e / per;
+        int k = e - c2 * per;
+        const long long gi = row0 + s_rowidx[c2];
+        const float* r = s_row + c2 * kRow;
+        if (k < 3) { peer_add(pa, pa.off_m3 + gi * 3 + k, r[k]); continue; }
+        k -= 3;
+        if (k < M3) {
+            const int kk = k / 3, ch = k - 3 * kk;
+            peer_add(pa, pa.off_sh + gi * M3 + k, kk < 16 ? r[16 + kk] * r[13 + ch] : 0.f);
+            continue;
+        }
+        k -= M3;
+        if (k < 1) { peer_add(pa, pa.off_op + gi, r[5]); continue; }
+        k -= 1;
+        if (k < 3) { peer_add(pa, pa.off_sc + gi * 3 + k, r[6 + k]); continue; }
+        k -= 3;
+        peer_add(pa, pa.off_rot + gi * 4 + k, r[9 + k]);
+    }
+}
+
 }  // namespace
+
+void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* acc, const float* gout, float* dmeans2D,
+                                 float* const* peers, int world, float* mc, const long long* seg_off,
+                                 cudaStream_t s) {
+    GsPeerArgs pa;
+    for (int r = 0; r < GS_MAX_PEERS; r++) pa.peers[r] = r < world ? peers[r] : nullptr;
+    pa.mc = mc; pa.world = world;
+    pa.off_m3 = seg_off[0]; pa.off_sh = seg_off[1]; pa.off_op = seg_off[2]; pa.off_sc = seg_off[3]; pa.off_rot = seg_off[4];
+    const int grid = (P + kT - 1) / kT;
+    k_grad_reduce_peers<<<grid, kT, kT * kRow * sizeof(float), s>>>(P, M, radii, acc, gout, dmeans2D, pa);
+}
 
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
@@ -326,6 +425,7 @@ void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, cons
 }
 void gs_grad_write_init() {
     cudaFuncSetAttribute(k_grad_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kRow * (int)sizeof(float));
+    cudaFuncSetAttribute(k_grad_reduce_peers, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kRow * (int)sizeof(float));
 }
 void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
                           cudaStream_t s) {

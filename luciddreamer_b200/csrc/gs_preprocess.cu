@@ -60,13 +60,16 @@ __device__ __forceinline__ uint32_t cta_scan_areas(CandShared& s, uint32_t area)
 // Visits every (Gaussian, tile) candidate of the chunk that passes the culling test: f(tile, p0, p1).
 template <typename F>
 __device__ __forceinline__ void cta_for_each_hit(const CandShared& s, uint32_t total, int gx, F f) {
-    for (uint32_t q = threadIdx.x; q < total; q += kThreads) {
-        int lo = 0, hi = kThreads;                       // largest c with cum[c] <= q
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s.cum[mid] <= q) lo = mid; else hi = mid;
-        }
-        const int c = lo;
+    uint32_t q = threadIdx.x;
+    if (q >= total) return;
+    int lo = 0, hi = kThreads;                           // largest c with cum[c] <= q (binary search once ...)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s.cum[mid] <= q) lo = mid; else hi = mid;
+    }
+    int c = lo;
+    for (; q < total; q += kThreads) {
+        while (s.cum[c + 1] <= q) c++;                   // ... then the slot only ever advances
         const int r = (int)(q - s.cum[c]);
         const int w = s.rw[c];
         const int yy = r / w, xx = r - yy * w;
@@ -296,7 +299,7 @@ k_emit(const GsView v, const int* __restrict__ radii, const float4* __restrict__
         if (blockIdx.x == 0 && threadIdx.x == 0) status->overflow = 1u;
         return;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) status->n_big = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { status->n_big = 0u; status->n_mid = 0u; }
     __shared__ CandShared S;
     const uint32_t nvis = (uint32_t)status->num_visible;
     for (uint32_t chunk = blockIdx.x * kThreads; chunk < nvis; chunk += gridDim.x * kThreads) {

@@ -6,9 +6,10 @@
 // so each tile only has to order its own bucket by key = (depth_bits << 32 | gaussian_idx): identical order
 // to the reference's stable sort, whose ties (same tile, bit-identical depth) resolve by ascending Gaussian
 // index (emission order).
-//   k_tile_sort      one WARP per tile for buckets up to 1024 keys (shared memory, __syncwarp only);
-//                    larger buckets are queued for
-//   k_tile_sort_big  one CTA per queued tile, up to 16384 keys in shared memory; beyond that the same network
+//   k_tile_sort      one WARP per tile for buckets up to 256 keys (shared memory, __syncwarp only); larger
+//                    buckets are queued (mid from the front of the queue, big from the back) for
+//   k_tile_sort_mid  one 128-thread CTA per queued tile, up to 4096 keys (32 KB shared memory), persistent grid
+//   k_tile_sort_big  one 512-thread CTA per queued tile, up to 16384 keys (128 KB); beyond that the same network
 //                    runs in place in global memory (slow path, correctness only).
 // Sorting network: bitonic for arbitrary n (flip / half-cleaner form, every comparison ascending, so the virtual
 // +inf padding never moves and comparisons against it are simply skipped).
@@ -17,7 +18,9 @@
 namespace {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kWarpKeys = 1024;      // 8 KB of u64 keys per warp
+constexpr int kWarpKeys = 256;       // 2 KB of u64 keys per warp
+constexpr int kMidThreads = 128;
+constexpr int kMidKeys = 4096;       // 32 KB static shared memory
 constexpr int kBigThreads = 512;
 constexpr int kBigKeys = 16384;      // 128 KB dynamic shared memory
 
@@ -63,8 +66,11 @@ k_tile_sort(int G, const uint32_t* __restrict__ tile_off, uint32_t* __restrict__
     const int n = (int)(end - beg);
     if (lane == 0) tile_cur[tile] = 0u;                  // cursors back to zero for a possible re-render
     if (n == 0) return;
-    if (n > kWarpKeys) {
-        if (lane == 0) big_list[atomicAdd(&status->n_big, 1u)] = (uint32_t)tile;
+    if (n > kWarpKeys) {                                 // queue: mid tiles from the front, big tiles from the back
+        if (lane == 0) {
+            if (n <= kMidKeys) big_list[atomicAdd(&status->n_mid, 1u)] = (uint32_t)tile;
+            else big_list[G - 1 - atomicAdd(&status->n_big, 1u)] = (uint32_t)tile;
+        }
         return;
     }
     unsigned long long* a = s_keys[wid];
@@ -75,15 +81,36 @@ k_tile_sort(int G, const uint32_t* __restrict__ tile_off, uint32_t* __restrict__
     for (int t = lane; t < n; t += 32) list[beg + t] = (uint32_t)a[t];
 }
 
+// buckets of 257..4096 keys: one 128-thread CTA per tile, persistent over the queue
+__global__ void __launch_bounds__(kMidThreads)
+k_tile_sort_mid(const uint32_t* __restrict__ tile_off, const GsDevStatus* __restrict__ status,
+                const uint32_t* __restrict__ big_list, const unsigned long long* __restrict__ keys,
+                uint32_t* __restrict__ list, long long capacity) {
+    if ((long long)status->num_pairs > capacity) return;
+    __shared__ unsigned long long s_mid[kMidKeys];
+    const unsigned nmid = status->n_mid;
+    for (unsigned b = blockIdx.x; b < nmid; b += gridDim.x) {
+        const uint32_t tile = big_list[b];
+        const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
+        const int n = (int)(end - beg);
+        const unsigned long long* g = keys + beg;
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += kMidThreads) s_mid[t] = g[t];
+        __syncthreads();
+        bitonic_sort_any_n(s_mid, n, threadIdx.x, kMidThreads, [] { __syncthreads(); });
+        for (int t = threadIdx.x; t < n; t += kMidThreads) list[beg + t] = (uint32_t)s_mid[t];
+    }
+}
+
 __global__ void __launch_bounds__(kBigThreads)
-k_tile_sort_big(const uint32_t* __restrict__ tile_off, const GsDevStatus* __restrict__ status,
+k_tile_sort_big(int G, const uint32_t* __restrict__ tile_off, const GsDevStatus* __restrict__ status,
                 const uint32_t* __restrict__ big_list, unsigned long long* __restrict__ keys,
                 uint32_t* __restrict__ list, long long capacity) {
     if ((long long)status->num_pairs > capacity) return;
     extern __shared__ unsigned long long s_big[];
     const unsigned nbig = status->n_big;
     for (unsigned b = blockIdx.x; b < nbig; b += gridDim.x) {
-        const uint32_t tile = big_list[b];
+        const uint32_t tile = big_list[G - 1 - b];
         const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
         const int n = (int)(end - beg);
         unsigned long long* g = keys + beg;
@@ -113,8 +140,10 @@ void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t*
     if (prof) cudaEventRecord(prof[0], s);
     k_tile_sort<<<(G + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, s>>>(G, tile_off, tile_cur, status,
                                                                                  big_list, keys, list, capacity);
+    const int gmid = G < num_sms * 6 ? G : num_sms * 6;
+    k_tile_sort_mid<<<gmid, kMidThreads, 0, s>>>(tile_off, status, big_list, keys, list, capacity);
     if (prof) { cudaEventRecord(prof[1], s); cudaEventRecord(prof[2], s); }
     const int grid = G < num_sms ? G : num_sms;
-    k_tile_sort_big<<<grid, kBigThreads, kBigKeys * 8, s>>>(tile_off, status, big_list, keys, list, capacity);
+    k_tile_sort_big<<<grid, kBigThreads, kBigKeys * 8, s>>>(G, tile_off, status, big_list, keys, list, capacity);
     if (prof) cudaEventRecord(prof[3], s);
 }

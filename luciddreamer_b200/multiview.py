@@ -56,6 +56,49 @@ class GradBucket:
         return self.flat.numel() * self.flat.element_size()
 
 
+class SymmGradBucket(GradBucket):
+    """GradBucket whose storage is symmetric memory (one peer-mapped allocation per rank, same layout everywhere), so
+    the final backward kernel of every rank can add its visible rows straight into EVERY rank's bucket over NVLink
+    (`red.global.add` on peer pointers, or one `multimem.red` per element through the NVSwitch multicast address).
+    This replaces the dense 59-floats-per-Gaussian all-reduce of the shared-model step by traffic proportional to
+    the number of VISIBLE Gaussians.  Usage per optimisation step, on every rank:
+
+        bucket.begin_step()                 # zero the local bucket, then a cross-rank barrier
+        view_step(params, settings, cot, bucket=bucket)     # forward + backward, gradients land in all buckets
+        bucket.end_step()                   # cross-rank barrier: bucket.flat now holds the sum over all views
+    """
+
+    def __init__(self, P: int, M: int, device, group=None, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.P, self.M = int(P), int(M)
+        self.width = 3 + 3 * self.M + 1 + 3 + 4
+        widths = (3, 3 * self.M, 1, 3, 4)
+        seg = [(self.P * w + 63) // 64 * 64 for w in widths]
+        self.group = group if group is not None else dist.group.WORLD
+        self.flat = symm_mem.empty(sum(seg), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.flat, self.group)
+        self.flat.zero_()
+        offs = [0]
+        for x in seg[:-1]:
+            offs.append(offs[-1] + x)
+        self.seg_off = offs
+        shapes = ((self.P, 3), (self.P, self.M, 3), (self.P, 1), (self.P, 3), (self.P, 4))
+        views = [self.flat[o:o + self.P * w].view(*sh) for o, w, sh in zip(offs, widths, shapes)]
+        self.means3D, self.shs, self.opacities, self.scales, self.rotations = views
+        mc = 0
+        if use_multicast and getattr(self.handle, "has_multicast_support", False):
+            mc = int(self.handle.multicast_ptr or 0)
+        self.peers = dict(world=self.handle.world_size, ptrs=[int(p) for p in self.handle.buffer_ptrs], mc=mc,
+                          seg_off=offs)
+
+    def begin_step(self):
+        self.flat.zero_()
+        self.handle.barrier(channel=0)
+
+    def end_step(self):
+        self.handle.barrier(channel=1)
+
+
 class DensifyStats:
     """xyz_gradient_accum / denom / max_radii2D of scene/gaussian_model.py:151-155,405-407 and
     luciddreamer.py:306-312, kept so that they can be reduced across ranks."""
@@ -107,9 +150,13 @@ def view_step(params: dict, settings, cotangent: torch.Tensor, bucket: Optional[
     if bucket is None:
         bucket = GradBucket(prep.P, prep.M, prep.device)
     dm2 = means2D_grad if means2D_grad is not None else torch.empty((prep.P, 3), device=prep.device)
-    R._backward_impl(prep, radii, geom, binning, img, cap, cotangent, False, False,
-                     out=dict(dm3=bucket.means3D, dm2=dm2, dop=bucket.opacities, dsh=bucket.shs, dsc=bucket.scales,
-                              drot=bucket.rotations))
+    if isinstance(bucket, SymmGradBucket):
+        R._backward_impl(prep, radii, geom, binning, img, cap, cotangent, False, False, out=dict(dm2=dm2),
+                         peers=bucket.peers)
+    else:
+        R._backward_impl(prep, radii, geom, binning, img, cap, cotangent, False, False,
+                         out=dict(dm3=bucket.means3D, dm2=dm2, dop=bucket.opacities, dsh=bucket.shs, dsc=bucket.scales,
+                                  drot=bucket.rotations))
     return color, depth, radii, bucket, dm2
 
 

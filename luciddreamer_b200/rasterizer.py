@@ -134,12 +134,14 @@ def _forward_impl(prep: _Prepared):
 
 
 def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, want_colors: bool, want_cov: bool,
-                   out: Optional[dict] = None):
+                   out: Optional[dict] = None, peers: Optional[dict] = None):
     """`out` (optional): pre-allocated contiguous f32 destinations keyed dm3/dm2/dop/dsh/dsc/drot -- e.g. views of
     a flat multiview.GradBucket -- that the kernels write instead of fresh tensors (every row is overwritten)."""
     L = N.lib()
     out = out or {}
     f, dev, P, M = prep.frame, prep.device, prep.P, prep.M
+    if peers is not None:
+        return _backward_peers(prep, radii, geom, binning, img, cap, grad_color, out, peers)
     cap, nvis = cap if isinstance(cap, tuple) else (cap, P)   # `_C` path: num_visible unknown -> bound by P
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     with torch.cuda.device(idx):
@@ -184,6 +186,35 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
         N.check(L.gs_backward(_ctx(idx), C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
                               img.data_ptr(), scratch.data_ptr(), nscr, _p(gc), None, C.byref(g), stream))
     return dm2, dcol, dop, dm3, dcov, dsh, dsc, drot
+
+
+def _backward_peers(prep: _Prepared, radii, geom, binning, img, cap, grad_color, out, peers):
+    """Shared-model data-parallel backward: the parameter gradients of this view are ADDED into every rank's
+    symmetric gradient bucket by the final kernel (multiview.SymmGradBucket); only dL_dmeans2D is returned."""
+    L = N.lib()
+    f, dev, P = prep.frame, prep.device, prep.P
+    cap, nvis = cap if isinstance(cap, tuple) else (cap, P)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with torch.cuda.device(idx):
+        stream = torch.cuda.current_stream(idx).cuda_stream
+        dm2 = out.get("dm2")
+        if dm2 is None:
+            dm2 = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        g = N.GsGrads()
+        g.dL_dmeans2D = dm2.data_ptr()
+        world = int(peers["world"])
+        ptrs = (C.c_void_p * world)(*[int(p) for p in peers["ptrs"]])
+        seg = (C.c_int64 * 5)(*[int(o) for o in peers["seg_off"]])
+        g.peer_world = world
+        g.peer_buckets = C.cast(ptrs, C.POINTER(C.c_void_p))
+        g.peer_multicast = int(peers.get("mc") or 0) or None
+        g.peer_seg_off = C.cast(seg, C.POINTER(C.c_int64))
+        gc = _dev_f32(grad_color, dev)
+        nscr = L.gs_backward_scratch_bytes(nvis)
+        scratch = torch.empty((nscr,), dtype=torch.uint8, device=dev)
+        N.check(L.gs_backward(_ctx(idx), C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
+                              img.data_ptr(), scratch.data_ptr(), nscr, _p(gc), None, C.byref(g), stream))
+    return dm2
 
 
 # ------------------------------------------------------------------------- `_C`-compatible module surface
