@@ -161,15 +161,22 @@ class Ours:
         self.kernels_per_step = 10
         self.last = None
 
-    def step(self, cot):
+    def forward(self):
         L = self.leaves
         for t in L.values():
             t.grad = None
         self.m2.grad = None
         color, radii, depth = self.rast(L["means3D"], self.m2, L["opacities"], shs=L["shs"], scales=L["scales"],
                                         rotations=L["rotations"])
-        torch.autograd.backward(color, grad_tensors=cot)
         self.last = (color, radii)
+        return color
+
+    def backward(self, color, cot):
+        torch.autograd.backward(color, grad_tensors=cot)
+
+    def step(self, cot):
+        color = self.forward()
+        self.backward(color, cot)
         return color
 
     def set_camera(self, vm, pm, cp):      # e2e: camera arrives from the host every step
@@ -213,13 +220,20 @@ class RefCuda:
         self.cam = cam
         self.kernels_per_step = 0
 
-    def step(self, cot):
+    def forward(self):
         t, cam = self.t, self.cam
         R, color, depth, radii = self.rc.rasterize_gaussians(
             self.ctx, self.bg, t["means3D"], None, t["opacities"], t["scales"], t["rotations"], 1.0, None, self.vm,
             self.pm, cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, t["shs"], self.D, self.cp)
-        self.rc.rasterize_gaussians_backward(self.ctx, radii, cot)
         self.last = (color, radii, R)
+        return color
+
+    def backward(self, color, cot):
+        self.rc.rasterize_gaussians_backward(self.ctx, self.last[1], cot)
+
+    def step(self, cot):
+        color = self.forward()
+        self.backward(color, cot)
         return color
 
     def set_camera(self, vm, pm, cp):
@@ -252,32 +266,34 @@ def time_steps(impl, cot, steps, warmup, world):
     return ms
 
 
-def time_e2e(impl, cam, cot_cpu, steps, warmup, world):
-    """Same metric end to end: every step uploads that step's inputs (camera matrices + the [3,H,W] image-space
-    cotangent, standing in for the ground-truth image of the photometric loss) from pinned host memory and reads
-    the step's scalar result (<color, cotangent>) back.  Uploads of step k+1 overlap the compute of step k on a
-    copy stream; everything is inside the timed region."""
+def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
+    """Same metric end to end, shaped like one training iteration of the reference (luciddreamer.py:291-304): every
+    step uploads that step's inputs from pinned host memory -- the camera (viewmatrix, projmatrix, campos: 35 floats)
+    and the uint8 target image [H,W,3] -- computes the L1 photometric loss and its gradient on the device, runs
+    forward+backward through the operator API, and reads the scalar loss back.  Target uploads of step k+1 overlap the
+    compute of step k on a copy stream (double buffered); everything is inside the timed region.
+    fused_loss: our fused L1 kernel (luciddreamer_b200.losses); the reference arm uses plain torch ops."""
     dev = impl.dev
-    pin = lambda t: t.contiguous().pin_memory()
-    h_cot, h_vm, h_pm, h_cp = pin(cot_cpu), pin(cam.viewmatrix), pin(cam.projmatrix), pin(cam.campos)
-    d_cot = [torch.empty_like(cot_cpu, device=dev) for _ in range(2)]
-    d_vm = [torch.empty(4, 4, device=dev) for _ in range(2)]
-    d_pm = [torch.empty(4, 4, device=dev) for _ in range(2)]
-    d_cp = [torch.empty(3, device=dev) for _ in range(2)]
+    H, W = cam.image_height, cam.image_width
+    h_tgt = target_u8_cpu.contiguous().pin_memory()
+    h_cam = torch.cat([cam.viewmatrix.reshape(-1), cam.projmatrix.reshape(-1), cam.campos.reshape(-1)]).contiguous().pin_memory()
+    d_tgt = [torch.empty_like(target_u8_cpu, device=dev) for _ in range(2)]
+    d_cam = torch.empty(35, device=dev)
     h_loss = torch.zeros(steps + warmup, dtype=torch.float32).pin_memory()
     copy_s = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     ev_up = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
-    h2d = (h_cot.numel() + 16 + 16 + 3) * 4
+    h2d = h_tgt.numel() + 35 * 4
     d2h = 4
+    if fused_loss:
+        from luciddreamer_b200 import losses
 
     def upload(k):
         b = k & 1
         with torch.cuda.stream(copy_s):
             copy_s.wait_event(ev_free[b])
-            d_cot[b].copy_(h_cot, non_blocking=True); d_vm[b].copy_(h_vm, non_blocking=True)
-            d_pm[b].copy_(h_pm, non_blocking=True); d_cp[b].copy_(h_cp, non_blocking=True)
+            d_tgt[b].copy_(h_tgt, non_blocking=True)
             ev_up[b].record(copy_s)
 
     def run(n, base):
@@ -286,11 +302,18 @@ def time_e2e(impl, cam, cot_cpu, steps, warmup, world):
             b = k & 1
             if k + 1 < base + n:
                 upload(k + 1)
+            d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream
+            impl.set_camera(d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35])
             main.wait_event(ev_up[b])
-            impl.set_camera(d_vm[b], d_pm[b], d_cp[b])
-            color = impl.step(d_cot[b])
-            loss = (color.detach() * d_cot[b]).sum()
-            h_loss[k].copy_(loss, non_blocking=True)
+            color = impl.forward()
+            if fused_loss:
+                loss, cot = losses.l1_loss_with_grad(color, d_tgt[b])
+            else:
+                diff = color.detach() - d_tgt[b].permute(2, 0, 1).float().div_(255.0)
+                loss = diff.abs().mean()
+                cot = torch.sign(diff).div_(diff.numel())
+            impl.backward(color, cot)
+            h_loss[k].copy_(loss.reshape(()), non_blocking=True)
             ev_free[b].record(main)
 
     for b in range(2):
@@ -461,7 +484,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     st = impl.stats()
     value = world * rays * args.steps / ms / 1e3           # Mrays/s, whole job
-    e2e_ms, h2d, d2h, loss = time_e2e(impl, cam, cot_cpu, args.steps, args.warmup, world)
+    g = torch.Generator().manual_seed(4242)
+    target_u8 = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8)
+    e2e_ms, h2d, d2h, loss = time_e2e(impl, cam, target_u8, args.steps, args.warmup, world, fused_loss=(args.impl == "ours"))
     e2e_val = world * rays * args.steps / e2e_ms / 1e3
 
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -469,8 +494,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(wl, args, world),
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
-                    "protocol": "per step: H2D camera (35 floats) + [3,H,W] cotangent from pinned memory (copy stream, "
-                                "double buffered), forward+backward via the autograd API, D2H scalar <color,cotangent>"},
+                    "protocol": "per step: H2D camera (35 floats) + uint8 target image [H,W,3] from pinned memory (copy "
+                                "stream, double buffered), forward, on-device L1 loss + gradient, backward, D2H scalar loss"},
             "clocks": clocks, "scene_stats": {"P_vis": st["P_vis"], "pairs": st["pairs"]}}
     if args.impl == "reference":
         line["impl"] = "reference"

@@ -148,9 +148,25 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
                 size_t grad_scratch_bytes, const float* dL_dout_color, const float* dL_dout_depth,
                 const GsGrads* grads, gs_stream_t stream);
 
+/* The two halves of gs_backward as separate calls: the tile pass needs no gradient outputs, so a host can enqueue
+ * it before allocating them (keeps the GPU fed while Python allocates). */
+int gs_backward_blend(GsContext* ctx, const GsFrame* f, const void* geom_buffer, const void* binning_buffer,
+                      int64_t pair_capacity, const void* image_buffer, const float* dL_dout_color,
+                      gs_stream_t stream);
+int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
+                          const void* image_buffer, void* grad_scratch, size_t grad_scratch_bytes,
+                          const GsGrads* grads, gs_stream_t stream);
+
 /* replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153): present[i] = (z_view > 0.2) */
 int gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     uint8_t* present, gs_stream_t stream);
+
+/* "Next" row, first slice: fused L1 photometric loss + gradient.  Replaces utils/loss.py:18
+ * `l1_loss` and its autograd backward in the training step (luciddreamer.py:301-304): loss[0] = weight *
+ * mean|color - target/255|, dL_dcolor = weight * sign(color - target/255) / (3HW).  color, dL_dcolor: [3,H,W] f32;
+ * target_u8: [H,W,3] uint8 (the layout images arrive in from the host). */
+int gs_l1_loss_backward(GsContext* ctx, const float* color, const uint8_t* target_u8, int32_t H, int32_t W, float weight,
+                        float* dL_dcolor, float* loss, gs_stream_t stream);
 
 /* Introspection for tests: copies the per-tile exclusive offsets (uint32 [G+1]; tile t owns
  * [off[t], off[t+1]) -- the reference's `ranges`, rasterizer_impl.cu:116-138) and the depth-sorted Gaussian

@@ -247,26 +247,40 @@ size_t gs_backward_scratch_bytes(int64_t num_visible) {
     return gs_align_up((size_t)(num_visible > 0 ? num_visible : 1) * GS_GOUT_FLOATS * sizeof(float), 256);
 }
 
-int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
-                const void* binning_buffer, int64_t pair_capacity, const void* image_buffer, void* grad_scratch,
-                size_t grad_scratch_bytes, const float* dL_dout_color, const float* dL_dout_depth,
-                const GsGrads* grads, gs_stream_t stream) {
-    (void)dL_dout_depth;                                 // depth gradient disabled in the reference
+// Backward, first half: reverse tile traversal into the per-Gaussian accumulators.  Needs no gradient outputs,
+// so a host can enqueue it before it has allocated them.
+int gs_backward_blend(GsContext* ctx, const GsFrame* f, const void* geom_buffer, const void* binning_buffer,
+                      int64_t pair_capacity, const void* image_buffer, const float* dL_dout_color,
+                      gs_stream_t stream) {
     int rc = check_frame(f);
     if (rc) return rc;
-    if (!grads) return fail(GS_EINVAL, "grads is NULL");
     if (f->P == 0) return GS_OK;
-    if (!radii || !geom_buffer || !binning_buffer || !image_buffer || !dL_dout_color || !grad_scratch)
-        return fail(GS_EINVAL, "radii / scratch / dL_dout_color is NULL");
-    (void)grad_scratch_bytes;   // sized by the caller with gs_backward_scratch_bytes(num_visible)
+    if (!geom_buffer || !binning_buffer || !image_buffer || !dL_dout_color)
+        return fail(GS_EINVAL, "scratch / dL_dout_color is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     const GsView v = make_view(f);
     GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
     GsGeomLayout gl = gs_geom_layout(const_cast<void*>(geom_buffer), f->P);
     GsBinLayout bl = gs_bin_layout(const_cast<void*>(binning_buffer), pair_capacity > 0 ? pair_capacity : 1);
     GS_TIMED(ctx, 6, s, gs_launch_blend_bwd(v, il.tile_off, bl.list, gl.rec, il.final_T, il.n_contrib, dL_dout_color,
-                                                gl.acc, s));
-    if ((rc = debug_sync(f, s, "blend_bwd"))) return rc;
+                                            gl.acc, s));
+    return debug_sync(f, s, "blend_bwd");
+}
+
+// Backward, second half: per-Gaussian gradients from the accumulators into the caller's tensors (or peers' buckets).
+int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
+                          const void* image_buffer, void* grad_scratch, size_t grad_scratch_bytes,
+                          const GsGrads* grads, gs_stream_t stream) {
+    int rc = check_frame(f);
+    if (rc) return rc;
+    if (!grads) return fail(GS_EINVAL, "grads is NULL");
+    if (f->P == 0) return GS_OK;
+    if (!radii || !geom_buffer || !image_buffer || !grad_scratch) return fail(GS_EINVAL, "radii / scratch is NULL");
+    (void)grad_scratch_bytes;   // sized by the caller with gs_backward_scratch_bytes(num_visible)
+    cudaStream_t s = (cudaStream_t)stream;
+    const GsView v = make_view(f);
+    GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
+    GsGeomLayout gl = gs_geom_layout(const_cast<void*>(geom_buffer), f->P);
     GsGradPtrs g;
     g.dmeans3D = grads->dL_dmeans3D; g.dmeans2D = grads->dL_dmeans2D; g.dsh = f->shs ? grads->dL_dsh : nullptr;
     g.dcolors = grads->dL_dcolors; g.dopacity = grads->dL_dopacity;
@@ -284,8 +298,7 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
         GS_TIMED(ctx, 9, s, gs_launch_grad_reduce_peers(f->P, v.M, radii, gl.acc, gout, grads->dL_dmeans2D,
                                                         (float* const*)grads->peer_buckets, grads->peer_world,
                                                         (float*)grads->peer_multicast, (const long long*)grads->peer_seg_off, s));
-        if ((rc = debug_sync(f, s, "grad_reduce_peers"))) return rc;
-        return GS_OK;
+        return debug_sync(f, s, "grad_reduce_peers");
     }
     GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, s));
     if ((rc = debug_sync(f, s, "grad_write"))) return rc;
@@ -293,6 +306,17 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
     const size_t Ps = (size_t)f->P;
     if (!f->shs && grads->dL_dsh && f->M > 0) GS_CUDA(cudaMemsetAsync(grads->dL_dsh, 0, Ps * f->M * 3 * sizeof(float), s));
     return GS_OK;
+}
+
+int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
+                const void* binning_buffer, int64_t pair_capacity, const void* image_buffer, void* grad_scratch,
+                size_t grad_scratch_bytes, const float* dL_dout_color, const float* dL_dout_depth,
+                const GsGrads* grads, gs_stream_t stream) {
+    (void)dL_dout_depth;                                 // depth gradient disabled in the reference
+    if (!grads) return fail(GS_EINVAL, "grads is NULL");
+    int rc = gs_backward_blend(ctx, f, geom_buffer, binning_buffer, pair_capacity, image_buffer, dL_dout_color, stream);
+    if (rc) return rc;
+    return gs_backward_gradients(ctx, f, radii, geom_buffer, image_buffer, grad_scratch, grad_scratch_bytes, grads, stream);
 }
 
 int gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
@@ -304,6 +328,15 @@ int gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, co
     gs_launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return fail(GS_ECUDA, "mark_visible launch: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
+int gs_l1_loss_backward(GsContext* ctx, const float* color, const uint8_t* target_u8, int32_t H, int32_t W, float weight,
+                        float* dL_dcolor, float* loss, gs_stream_t stream) {
+    if (!color || !target_u8 || !dL_dcolor || !loss || H <= 0 || W <= 0) return fail(GS_EINVAL, "bad argument");
+    gs_launch_l1_loss_grad(color, target_u8, H, W, weight, dL_dcolor, loss, ctx ? ctx->num_sms : 148, (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GS_ECUDA, "l1_loss launch: %s", cudaGetErrorString(e));
     return GS_OK;
 }
 

@@ -312,4 +312,6 @@ void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, con
 void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* acc, const float* gout, float* dmeans2D,
                                  float* const* peers, int world, float* mc, const long long* seg_off,
                                  cudaStream_t s);
+void gs_launch_l1_loss_grad(const float* color, const uint8_t* target, int H, int W, float weight, float* dL_dcolor,
+                            float* loss, int num_sms, cudaStream_t s);
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);

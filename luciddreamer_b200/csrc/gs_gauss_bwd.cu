@@ -20,7 +20,9 @@ constexpr int kT = 256;
 // masked), 16-31 SH basis, 32-34 dcolor (raw), 35-40 dcov3D, 41-43 pad
 constexpr int kRow = GS_GOUT_FLOATS;
 
-__global__ void __launch_bounds__(kT)
+constexpr int kVisT = 64;              // small CTAs: P_vis is often only a few 10^4, spread it over all SMs
+
+__global__ void __launch_bounds__(kVisT)
 k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
            const float* __restrict__ scales, const float* __restrict__ rotations,
            const float* __restrict__ cov3D_precomp, const float4* __restrict__ rec, float4* __restrict__ acc,
@@ -28,7 +30,7 @@ k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __res
     __shared__ GsCam cam;
     gs_load_cam(v, &cam);
     const uint32_t nvis = (uint32_t)status->num_visible;
-    for (uint32_t c = blockIdx.x * kT + threadIdx.x; c < nvis; c += gridDim.x * kT) {
+    for (uint32_t c = blockIdx.x * kVisT + threadIdx.x; c < nvis; c += gridDim.x * kVisT) {
         const uint32_t i = vis_list[c];
         float4* aa = acc + (size_t)3 * i;
         const float4 a0 = aa[0], a1 = aa[1], a2 = aa[2];
@@ -419,9 +421,9 @@ void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* a
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
                         const uint32_t* vis_list, const GsDevStatus* status, float* gout, cudaStream_t s) {
-    const int need = (v.P + kT - 1) / kT;
-    const int grid = need < num_sms * 2 ? need : num_sms * 2;
-    k_grad_vis<<<grid, kT, 0, s>>>(v, means3D, shs, scales, rotations, cov3D_precomp, rec, acc, vis_list, status, gout);
+    const int need = (v.P + kVisT - 1) / kVisT;
+    const int grid = need < num_sms * 8 ? need : num_sms * 8;
+    k_grad_vis<<<grid, kVisT, 0, s>>>(v, means3D, shs, scales, rotations, cov3D_precomp, rec, acc, vis_list, status, gout);
 }
 void gs_grad_write_init() {
     cudaFuncSetAttribute(k_grad_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kRow * (int)sizeof(float));

@@ -21,6 +21,8 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kChunk = 64;            // Gaussians per CTA round in the vis-list kernels: small chunks keep all SMs busy
+                                      // when only a few 10^4 Gaussians are visible (the candidate walk uses all threads)
 
 // Exact tile culling (parity-safe): a (tile, splat) pair is binned only if the splat can
 // reach alpha >= 1/255 somewhere in the tile (gs_box_hit).  Pairs that are dropped are skipped by every pixel of
@@ -33,26 +35,27 @@ __device__ __noinline__ bool gs_tile_hit(float mx, float my, float A, float B, f
 }
 
 struct CandShared {                   // per-CTA candidate table (one entry per Gaussian of the chunk)
-    float mx[kThreads], my[kThreads], A[kThreads], B[kThreads], C[kThreads], thr[kThreads];
-    int rx[kThreads], ry[kThreads], rw[kThreads];
-    uint32_t p0[kThreads], p1[kThreads];
-    uint32_t cum[kThreads + 1];
-    uint32_t warp_tot[kThreads / 32];
+    float mx[kChunk], my[kChunk], A[kChunk], B[kChunk], C[kChunk], thr[kChunk];
+    int rx[kChunk], ry[kChunk], rw[kChunk];
+    uint32_t p0[kChunk], p1[kChunk];
+    uint32_t cum[kChunk + 1];
+    uint32_t warp_tot[kChunk / 32];
 };
 
-// Block-wide exclusive scan of `area` into s.cum[0..256]; returns the total.  All 256 threads must call.
+// Exclusive scan of the chunk's `area`s (threads 0..kChunk-1 hold one each) into s.cum[0..kChunk]; returns the total.
+// All threads of the CTA must call.
 __device__ __forceinline__ uint32_t cta_scan_areas(CandShared& s, uint32_t area) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t x = area;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s.warp_tot[wid] = x;
+    if (lane == 31 && wid < kChunk / 32) s.warp_tot[wid] = x;
     __syncthreads();
     uint32_t wbase = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; w++) { const uint32_t t = s.warp_tot[w]; if (w < wid) wbase += t; total += t; }
-    s.cum[tid] = wbase + x - area;
-    if (tid == kThreads - 1) s.cum[kThreads] = total;
+    for (int w = 0; w < kChunk / 32; w++) { const uint32_t t = s.warp_tot[w]; if (w < wid) wbase += t; total += t; }
+    if (tid < kChunk) s.cum[tid] = wbase + x - area;
+    if (tid == 0) s.cum[kChunk] = total;
     __syncthreads();
     return total;
 }
@@ -62,7 +65,7 @@ template <typename F>
 __device__ __forceinline__ void cta_for_each_hit(const CandShared& s, uint32_t total, int gx, F f) {
     uint32_t q = threadIdx.x;
     if (q >= total) return;
-    int lo = 0, hi = kThreads;                           // largest c with cum[c] <= q (binary search once ...)
+    int lo = 0, hi = kChunk;                             // largest c with cum[c] <= q (binary search once ...)
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (s.cum[mid] <= q) lo = mid; else hi = mid;
@@ -179,10 +182,10 @@ k_shade_count(const GsView v, const float* __restrict__ means3D, const float* __
     __syncthreads();
     const uint32_t nvis = (uint32_t)status->num_visible;
     const bool aligned = ((v.M * 3) & 3) == 0;
-    for (uint32_t chunk = blockIdx.x * kThreads; chunk < nvis; chunk += gridDim.x * kThreads) {
+    for (uint32_t chunk = blockIdx.x * kChunk; chunk < nvis; chunk += gridDim.x * kChunk) {
         const uint32_t c = chunk + threadIdx.x;
         uint32_t area = 0;
-        if (c < nvis) {
+        if (threadIdx.x < kChunk && c < nvis) {
             const uint32_t i = vis_list[c];
             float4* rr = rec + (size_t)GS_REC_V4 * i;
             const float4 q0 = rr[0], q1 = rr[1];         // written by k_project: (x,y,A,B), (C, opacity, depth, thr)
@@ -233,8 +236,9 @@ k_shade_count(const GsView v, const float* __restrict__ means3D, const float* __
     }
 }
 
-// Exclusive scan of the G tile counts (single CTA: G is ~8k at 1080p).  Resets the counts to zero so the same
-// array serves as the emission cursors, and mirrors the totals to a pinned host slot.
+// Exclusive scan of the G tile counts (single CTA: G is ~8k at 1080p, one round).  Every thread owns 8 consecutive
+// tiles (two 128-bit loads), scans them in registers, and the block scans the per-thread totals.  Resets the counts
+// to zero so the same array serves as the emission cursors, and mirrors the totals to a pinned host slot.
 constexpr int kScanT = 1024, kScanK = 8;
 __global__ void __launch_bounds__(kScanT)
 k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_off, GsDevStatus* __restrict__ status,
@@ -245,37 +249,46 @@ k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (int base = 0; base < G; base += kScanT * kScanK) {
+        const int t0 = base + tid * kScanK;              // tile_cnt / tile_off are 256-byte aligned, t0 % 8 == 0
         uint32_t cv[kScanK];
+        if (t0 + kScanK <= G) {
+            const uint4 a = *reinterpret_cast<const uint4*>(tile_cnt + t0);
+            const uint4 b = *reinterpret_cast<const uint4*>(tile_cnt + t0 + 4);
+            cv[0] = a.x; cv[1] = a.y; cv[2] = a.z; cv[3] = a.w; cv[4] = b.x; cv[5] = b.y; cv[6] = b.z; cv[7] = b.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < kScanK; k++) {               // all loads in flight before the first scan step
-            const int t = base + k * kScanT + tid;
-            cv[k] = t < G ? tile_cnt[t] : 0u;
+            for (int k = 0; k < kScanK; k++) cv[k] = (t0 + k < G) ? tile_cnt[t0 + k] : 0u;
         }
+        uint32_t tot = 0;
 #pragma unroll
-        for (int k = 0; k < kScanK; k++) {
-            const int t = base + k * kScanT + tid;
-            if (base + k * kScanT < G) {
-                const uint32_t c = cv[k];
-                uint32_t x = c;
+        for (int k = 0; k < kScanK; k++) { const uint32_t c = cv[k]; cv[k] = tot; tot += c; }   // exclusive, local
+        uint32_t x = tot;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-                if (lane == 31) s_warp[wid] = x;
-                __syncthreads();
-                if (wid == 0) {
-                    uint32_t w = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_warp[lane];
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-                    s_warp[lane] = w;                    // inclusive over warps
-                }
-                __syncthreads();
-                const uint32_t carry = s_carry;
-                const uint32_t incl = x + (wid ? s_warp[wid - 1] : 0u);
-                if (t < G) { tile_off[t] = carry + incl - c; tile_cnt[t] = 0u; }
-                __syncthreads();
-                if (tid == kScanT - 1) s_carry = carry + incl;
-                __syncthreads();
-            }
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;                            // inclusive over warps
         }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + (x - tot) + (wid ? s_warp[wid - 1] : 0u);
+        if (t0 + kScanK <= G) {
+            *reinterpret_cast<uint4*>(tile_off + t0) = make_uint4(excl + cv[0], excl + cv[1], excl + cv[2], excl + cv[3]);
+            *reinterpret_cast<uint4*>(tile_off + t0 + 4) = make_uint4(excl + cv[4], excl + cv[5], excl + cv[6], excl + cv[7]);
+            *reinterpret_cast<uint4*>(tile_cnt + t0) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(tile_cnt + t0 + 4) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanK; k++)
+                if (t0 + k < G) { tile_off[t0 + k] = excl + cv[k]; tile_cnt[t0 + k] = 0u; }
+        }
+        __syncthreads();
+        if (tid == kScanT - 1) s_carry = excl + tot;
+        __syncthreads();
     }
     if (tid == 0) {
         const uint32_t total = s_carry;
@@ -302,10 +315,10 @@ k_emit(const GsView v, const int* __restrict__ radii, const float4* __restrict__
     if (blockIdx.x == 0 && threadIdx.x == 0) { status->n_big = 0u; status->n_mid = 0u; }
     __shared__ CandShared S;
     const uint32_t nvis = (uint32_t)status->num_visible;
-    for (uint32_t chunk = blockIdx.x * kThreads; chunk < nvis; chunk += gridDim.x * kThreads) {
+    for (uint32_t chunk = blockIdx.x * kChunk; chunk < nvis; chunk += gridDim.x * kChunk) {
         const uint32_t c = chunk + threadIdx.x;
         uint32_t area = 0;
-        if (c < nvis) {
+        if (threadIdx.x < kChunk && c < nvis) {
             const uint32_t i = vis_list[c];
             const float4* rr = rec + (size_t)GS_REC_V4 * i;
             const float4 q0 = __ldg(rr), q1 = __ldg(rr + 1), q2 = __ldg(rr + 2);
@@ -346,8 +359,8 @@ void gs_launch_project(const GsView& v, const float* means3D, const float* opaci
 void gs_launch_shade_count(const GsView& v, int num_sms, const float* means3D, const float* shs,
                            const float* colors_precomp, const int* radii, float4* rec, float4* acc,
                            const uint32_t* vis_list, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s) {
-    const int need = (v.P + kThreads - 1) / kThreads;
-    const int grid = need < num_sms * 4 ? need : num_sms * 4;
+    const int need = (v.P + kChunk - 1) / kChunk;
+    const int grid = need < num_sms * 8 ? need : num_sms * 8;
     k_shade_count<<<grid, kThreads, 0, s>>>(v, means3D, shs, colors_precomp, radii, rec, acc, vis_list, tile_cnt, status);
 }
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status, GsDevStatus* host_slot,
@@ -357,8 +370,8 @@ void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevSta
 void gs_launch_emit(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
                     const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status, unsigned long long* keys,
                     long long capacity, cudaStream_t s) {
-    const int need = (v.P + kThreads - 1) / kThreads;
-    const int grid = need < num_sms * 4 ? need : num_sms * 4;
+    const int need = (v.P + kChunk - 1) / kChunk;
+    const int grid = need < num_sms * 8 ? need : num_sms * 8;
     k_emit<<<grid, kThreads, 0, s>>>(v, radii, rec, vis_list, tile_off, tile_cur, status, keys, capacity);
 }
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s) {

@@ -26,23 +26,25 @@ constexpr int kBigKeys = 16384;      // 128 KB dynamic shared memory
 
 template <typename Ptr, typename Sync>
 __device__ __forceinline__ void bitonic_sort_any_n(Ptr a, const int n, const int tid, const int nthreads, Sync sync) {
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    const int half = np2 >> 1;
-    for (int k = 2; k <= np2; k <<= 1) {
-        const int hk = k >> 1;
+    int lg = 0;
+    while ((1 << lg) < n) lg++;                           // np2 = 1 << lg
+    const int half = (1 << lg) >> 1;
+    for (int lk = 1; lk <= lg; lk++) {                    // k = 1 << lk; all index maths in shifts and masks
+        const int k = 1 << lk, hk = k >> 1;
         for (int t = tid; t < half; t += nthreads) {      // flip: i pairs with its mirror inside the k-block
-            const int blk = t / hk, r = t - blk * hk;
-            const int i = blk * k + r, j = blk * k + (k - 1 - r);
+            const int r = t & (hk - 1);
+            const int b0 = (t >> (lk - 1)) << lk;
+            const int i = b0 + r, j = b0 + (k - 1 - r);
             if (j < n) {
                 const unsigned long long x = a[i], y = a[j];
                 if (x > y) { a[i] = y; a[j] = x; }
             }
         }
         sync();
-        for (int d = k >> 2; d >= 1; d >>= 1) {
+        for (int ld = lk - 2; ld >= 0; ld--) {            // d = 1 << ld
+            const int d = 1 << ld;
             for (int t = tid; t < half; t += nthreads) {
-                const int i = ((t / d) * (d << 1)) + (t % d), j = i + d;
+                const int i = ((t >> ld) << (ld + 1)) + (t & (d - 1)), j = i + d;
                 if (j < n) {
                     const unsigned long long x = a[i], y = a[j];
                     if (x > y) { a[i] = y; a[j] = x; }

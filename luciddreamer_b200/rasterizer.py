@@ -147,6 +147,10 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
     with torch.cuda.device(idx):
         stream = torch.cuda.current_stream(idx).cuda_stream
         f32 = dict(dtype=torch.float32, device=dev)
+        # the tile pass goes to the GPU first; allocations below overlap with it
+        gc = _dev_f32(grad_color, dev)
+        N.check(L.gs_backward_blend(_ctx(idx), C.byref(f), geom.data_ptr(), binning.data_ptr(), cap, img.data_ptr(),
+                                    _p(gc), stream))
         g = N.GsGrads()
         # every gradient without a caller-provided sink is a view of ONE flat allocation, in bucket order
         # [means3D | sh | opacity | scales | rotations | means2D]
@@ -180,11 +184,10 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
         g.dL_drotations = drot.data_ptr() if f.rotations else None
         g.dL_dcolors = _p(dcol)
         g.dL_dcov3D = _p(dcov)
-        gc = _dev_f32(grad_color, dev)
         nscr = L.gs_backward_scratch_bytes(nvis)
         scratch = torch.empty((nscr,), dtype=torch.uint8, device=dev)
-        N.check(L.gs_backward(_ctx(idx), C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
-                              img.data_ptr(), scratch.data_ptr(), nscr, _p(gc), None, C.byref(g), stream))
+        N.check(L.gs_backward_gradients(_ctx(idx), C.byref(f), radii.data_ptr(), geom.data_ptr(), img.data_ptr(),
+                                        scratch.data_ptr(), nscr, C.byref(g), stream))
     return dm2, dcol, dop, dm3, dcov, dsh, dsc, drot
 
 

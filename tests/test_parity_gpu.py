@@ -253,3 +253,18 @@ def test_full_size_against_live_reference(scale_mult):
     inv = gold["radii"] == 0
     for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity"):
         assert not np.any(mine[k].reshape(P, -1)[inv])
+
+
+def test_fused_l1_loss_matches_torch():
+    """gs_l1_loss_backward == utils/loss.py:18 l1_loss (|out - gt|.mean()) and its autograd gradient."""
+    from luciddreamer_b200 import losses
+    d = dev()
+    g = torch.Generator().manual_seed(5)
+    H, W = 70, 100
+    color = torch.rand(3, H, W, generator=g).to(d).requires_grad_(True)
+    tgt = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8).to(d)
+    ref = 0.8 * (color - tgt.permute(2, 0, 1).float() / 255.0).abs().mean()
+    ref.backward()
+    loss, grad = losses.l1_loss_with_grad(color, tgt, weight=0.8)
+    assert abs(float(loss) - float(ref)) < 1e-6
+    assert torch.allclose(grad, color.grad, atol=1e-9)

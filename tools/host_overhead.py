@@ -30,3 +30,9 @@ for _ in range(n):
 torch.cuda.synchronize()
 tot = (time.perf_counter() - t0) / n
 print(f"host: {tot*1e6:.1f} us per fwd+bwd step (forward call {tf/n*1e6:.1f} us, backward call {(tot - tf/n)*1e6:.1f} us) at P={P}, {W}x{H}")
+
+import cProfile, pstats, io
+pr = cProfile.Profile(); pr.enable()
+for _ in range(200): step()
+torch.cuda.synchronize(); pr.disable()
+st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("tottime").print_stats(22); print(st.getvalue()[:4500])
