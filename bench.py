@@ -114,9 +114,9 @@ def alg_bytes(P, Pv, pairs, N, G, M):
     """Algorithmic (compulsory) HBM bytes per launch of each kernel -- DESIGN.md section 4 states the model."""
     return {
         "k_project": 12 * P + 4 * P + Pv * (12 + 16 + 4 + 32 + 4),
-        "k_shade_count": Pv * (4 + 32 + 12 + 12 * M + 4 + 32 + 48) + 4 * pairs,
+        "k_count_tiles": Pv * (4 + 32 + 4) + 4 * pairs,
         "k_tile_scan": 12 * G,
-        "k_emit": Pv * (4 + 48 + 4) + 8 * pairs + 4 * pairs,
+        "k_shade_emit": Pv * (4 + 32 + 12 + 12 * M + 4 + 32 + 48) + 12 * pairs,
         "k_tile_sort": 8 * pairs + 4 * pairs,
         "k_tile_sort_big": 0,
         "k_blend_fwd": 4 * pairs + 48 * Pv + 24 * N,
@@ -300,12 +300,12 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
         upload(base)
         for k in range(base, base + n):
             b = k & 1
+            d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream, before the next big
+            impl.set_camera(d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35])   # upload occupies the
+            main.wait_event(ev_up[b])                             # H2D copy engine
+            color = impl.forward()
             if k + 1 < base + n:
                 upload(k + 1)
-            d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream
-            impl.set_camera(d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35])
-            main.wait_event(ev_up[b])
-            color = impl.forward()
             if fused_loss:
                 loss, cot = losses.l1_loss_with_grad(color, d_tgt[b])
             else:

@@ -134,10 +134,11 @@ int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out);
 
 /* replaces the second half of Rasterizer::forward (rasterizer_impl.cu:284-338).
  * out_color [3,H,W], out_depth [1,H,W] are fully written.  Returns GS_OK even if the capacity turns out
- * too small on the device (nothing is rendered then) -- check with gs_forward_counts. */
+ * too small on the device (nothing is rendered then) -- check with gs_forward_counts.  rerender = 0 for the first
+ * render of a frame (it also shades the visible Gaussians), 1 when repeating it with a larger binning buffer. */
 int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, void* geom_buffer, void* binning_buffer,
                       int64_t pair_capacity, void* image_buffer, float* out_color, float* out_depth,
-                      gs_stream_t stream);
+                      int32_t rerender, gs_stream_t stream);
 
 /* replaces Rasterizer::backward (rasterizer_impl.cu:343-444) + the nine torch::zeros of its binding.
  * dL_dout_depth is accepted and ignored: the reference's depth gradient is commented out

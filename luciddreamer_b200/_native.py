@@ -50,7 +50,7 @@ SYMBOLS = [
                                         C.c_void_p, C.POINTER(C.c_int32)]),
     ("gs_forward_counts", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GsCounts)]),
     ("gs_forward_render", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     ("gs_backward_scratch_bytes", C.c_size_t, [C.c_int64]),
     ("gs_backward", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(GsGrads),

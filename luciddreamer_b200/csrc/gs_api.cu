@@ -76,9 +76,9 @@ int debug_sync(const GsFrame* f, cudaStream_t s, const char* what) {
 }  // namespace
 
 constexpr int kNumKernels = GS_NUM_KERNELS;
-static const char* const kKernelNames[kNumKernels] = {"k_project", "k_tile_scan", "k_emit", "k_tile_sort",
+static const char* const kKernelNames[kNumKernels] = {"k_project", "k_tile_scan", "k_shade_emit", "k_tile_sort",
                                                       "k_tile_sort_big", "k_blend_fwd", "k_blend_bwd", "k_grad_vis",
-                                                      "k_shade_count", "k_grad_write"};   // slot 9 also times
+                                                      "k_count_tiles", "k_grad_write"};   // slot 9 also times
                                                                                           // k_grad_reduce_peers
 
 struct GsContext {
@@ -183,9 +183,8 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
         GS_TIMED(ctx, 0, s, gs_launch_project(v, f->means3D, f->opacities, f->scales, f->rotations, f->cov3D_precomp,
                                               radii, gl.rec, gl.vis_list, il.status, s));
         if ((rc = debug_sync(f, s, "project"))) return rc;
-        GS_TIMED(ctx, 8, s, gs_launch_shade_count(v, ctx->num_sms, f->means3D, f->shs, f->colors_precomp, radii, gl.rec,
-                                                  gl.acc, gl.vis_list, il.tile_cnt, il.status, s));
-        if ((rc = debug_sync(f, s, "shade_count"))) return rc;
+        GS_TIMED(ctx, 8, s, gs_launch_count_tiles(v, ctx->num_sms, radii, gl.rec, gl.vis_list, il.tile_cnt, il.status, s));
+        if ((rc = debug_sync(f, s, "count_tiles"))) return rc;
     }
     GsDevStatus* dev_slot = nullptr;
     GS_CUDA(cudaHostGetDevicePointer((void**)&dev_slot, host_slot, 0));
@@ -209,7 +208,7 @@ int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out) {
 
 int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, void* geom_buffer, void* binning_buffer,
                       int64_t pair_capacity, void* image_buffer, float* out_color, float* out_depth,
-                      gs_stream_t stream) {
+                      int32_t rerender, gs_stream_t stream) {
     int rc = check_frame(f);
     if (rc) return rc;
     if (!image_buffer || !out_color || !out_depth) return fail(GS_EINVAL, "image buffer / outputs are NULL");
@@ -226,8 +225,9 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
     GsImageLayout il = gs_image_layout(image_buffer, f->W, f->H);
     GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
     GsBinLayout bl = gs_bin_layout(binning_buffer, pair_capacity > 0 ? pair_capacity : 1);
-    GS_TIMED(ctx, 2, s, gs_launch_emit(v, ctx ? ctx->num_sms : 148, radii, gl.rec, gl.vis_list, il.tile_off, il.tile_cnt,
-                                       il.status, bl.keys, pair_capacity, s));
+    GS_TIMED(ctx, 2, s, gs_launch_shade_emit(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs, f->colors_precomp, radii,
+                                             gl.rec, gl.acc, gl.vis_list, il.tile_off, il.tile_cnt, il.status, bl.keys,
+                                             pair_capacity, rerender != 0, s));
     if ((rc = debug_sync(f, s, "emit"))) return rc;
     {
         const bool prof = ctx && ctx->profile;

@@ -9,7 +9,7 @@
 //                          forward; consumed and re-zeroed by the backward)
 //                          a0 = (dmean2D.x, dmean2D.y, dconic.a, dconic.b)
 //                          a1 = (dconic.c, dopacity, dcolor.r, dcolor.g)
-//                          a2 = (dcolor.b, 0, 0, 0)
+//                          a2 = (dcolor.b, 0, 0, compact slot)
 //  image buffer  final_T[N] f32 | n_contrib[N] u32 | tile_off[G+1] u32 | tile_cnt[G] u32 | status
 //  binning       keys[C] u64 = (depth_bits << 32 | gaussian_idx)  |  list[C] u32 (per tile, depth sorted)
 #pragma once
@@ -285,14 +285,14 @@ struct GsGradPtrs {
 void gs_launch_project(const GsView& v, const float* means3D, const float* opacities, const float* scales,
                        const float* rotations, const float* cov3D_precomp, int* radii, float4* rec,
                        uint32_t* vis_list, GsDevStatus* status, cudaStream_t s);
-void gs_launch_shade_count(const GsView& v, int num_sms, const float* means3D, const float* shs,
-                           const float* colors_precomp, const int* radii, float4* rec, float4* acc,
-                           const uint32_t* vis_list, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s);
+void gs_launch_count_tiles(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
+                           uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s);
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status,
                          GsDevStatus* host_slot, cudaStream_t s);
-void gs_launch_emit(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
-                    const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status, unsigned long long* keys,
-                    long long capacity, cudaStream_t s);
+void gs_launch_shade_emit(const GsView& v, int num_sms, const float* means3D, const float* shs,
+                          const float* colors_precomp, const int* radii, float4* rec, float4* acc,
+                          const uint32_t* vis_list, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
+                          unsigned long long* keys, long long capacity, bool shaded, cudaStream_t s);
 void gs_tile_sort_init();
 void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
                          uint32_t* big_list, unsigned long long* keys, uint32_t* list, long long capacity,

@@ -5,13 +5,14 @@
 //                  in_frustum (auxiliary.h:139-164): streaming pass over all P Gaussians, one thread each; visible
 //                  ones are appended to a compact list (warp-aggregated atomic) so that every later per-Gaussian
 //                  kernel runs densely over P_vis instead of divergently over P
-//   k_shade_count  the colour half (computeColorFromSH, forward.cu:20-71,236-246) on the compact list, 128-bit
-//                  SH loads all in flight at once, + the tile histogram that replaces tiles_touched / InclusiveSum
+//   k_count_tiles  the tile histogram over the compact list that replaces tiles_touched / InclusiveSum
 //   k_tile_scan    cub::DeviceScan::InclusiveSum over P Gaussians + blocking D2H of num_rendered
 //                  (rasterizer_impl.cu:278-282): here a scan over the G tiles only, totals mirrored to pinned
 //                  host memory so the host never blocks the stream
-//   k_emit         duplicateWithKeys (rasterizer_impl.cu:70-111): pairs go straight into their tile's bucket
-//                  (per-tile cursors), keyed by (depth bits, Gaussian index) for the per-tile sort
+//   k_shade_emit   the colour half (computeColorFromSH, forward.cu:20-71,236-246) on the compact list, 128-bit
+//                  SH loads all in flight at once, + duplicateWithKeys (rasterizer_impl.cu:70-111): pairs go
+//                  straight into their tile's bucket (per-tile cursors), keyed by (depth bits, Gaussian index).
+//                  Runs AFTER the scan, i.e. after the point the host waits for, so shading overlaps the host
 //   k_mark_visible checkFrustum (rasterizer_impl.cu:54-66)
 // Histogram and emission spread the (Gaussian, tile) candidates of a CTA's 256 Gaussians evenly over its threads
 // (block scan of the rect areas + binary search), so a splat covering thousands of tiles costs the same per thread
@@ -27,7 +28,7 @@ constexpr int kChunk = 64;            // Gaussians per CTA round in the vis-list
 // Exact tile culling (parity-safe): a (tile, splat) pair is binned only if the splat can
 // reach alpha >= 1/255 somewhere in the tile (gs_box_hit).  Pairs that are dropped are skipped by every pixel of
 // the tile in the reference too (forward.cu:336-346), so no output changes.
-// __noinline__: the histogram pass (k_shade_count) and the emission pass (k_emit) must take bit-identical
+// __noinline__: the histogram pass (k_count_tiles) and the emission pass (k_shade_emit) must take bit-identical
 // decisions, so both call the same machine code on the same stored floats.
 __device__ __noinline__ bool gs_tile_hit(float mx, float my, float A, float B, float C, float thr, int tx, int ty) {
     const float x0 = (float)(tx * GS_TILE), y0 = (float)(ty * GS_TILE);
@@ -172,57 +173,18 @@ __device__ __forceinline__ void sh_to_rgb(const float* __restrict__ sh, float x,
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_shade_count(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
-              const float* __restrict__ colors_precomp, const int* __restrict__ radii, float4* __restrict__ rec,
-              float4* __restrict__ acc, const uint32_t* __restrict__ vis_list, uint32_t* __restrict__ tile_cnt,
+k_count_tiles(const GsView v, const int* __restrict__ radii, const float4* __restrict__ rec,
+              const uint32_t* __restrict__ vis_list, uint32_t* __restrict__ tile_cnt,
               GsDevStatus* __restrict__ status) {
     __shared__ CandShared S;
-    __shared__ float s_campos[3];
-    if (threadIdx.x < 3) s_campos[threadIdx.x] = __ldg(v.campos + threadIdx.x);
-    __syncthreads();
     const uint32_t nvis = (uint32_t)status->num_visible;
-    const bool aligned = ((v.M * 3) & 3) == 0;
     for (uint32_t chunk = blockIdx.x * kChunk; chunk < nvis; chunk += gridDim.x * kChunk) {
         const uint32_t c = chunk + threadIdx.x;
         uint32_t area = 0;
         if (threadIdx.x < kChunk && c < nvis) {
             const uint32_t i = vis_list[c];
-            float4* rr = rec + (size_t)GS_REC_V4 * i;
-            const float4 q0 = rr[0], q1 = rr[1];         // written by k_project: (x,y,A,B), (C, opacity, depth, thr)
-            float r_, g_, b_;
-            uint32_t clamped = 0;
-            if (colors_precomp) {
-                r_ = colors_precomp[3 * i]; g_ = colors_precomp[3 * i + 1]; b_ = colors_precomp[3 * i + 2];
-            } else {                                     // forward.cu:20-71
-                const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
-                float3 d = make_float3(p.x - s_campos[0], p.y - s_campos[1], p.z - s_campos[2]);
-                const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-                d.x = d.x / len; d.y = d.y / len; d.z = d.z / len;
-                const float* sh = shs + (size_t)i * v.M * 3;
-                float cr, cg, cb;
-                if (aligned) {
-                    switch (v.D) {
-                        case 0: sh_to_rgb<0>(sh, d.x, d.y, d.z, cr, cg, cb); break;
-                        case 1: sh_to_rgb<1>(sh, d.x, d.y, d.z, cr, cg, cb); break;
-                        case 2: sh_to_rgb<2>(sh, d.x, d.y, d.z, cr, cg, cb); break;
-                        default: sh_to_rgb<3>(sh, d.x, d.y, d.z, cr, cg, cb); break;
-                    }
-                } else {
-                    float bs[16];
-                    gs_sh_basis(v.D, d.x, d.y, d.z, bs);
-                    cr = bs[0] * sh[0]; cg = bs[0] * sh[1]; cb = bs[0] * sh[2];
-                    const int na = (v.D + 1) * (v.D + 1);
-                    for (int k = 1; k < na; k++) { cr = cr + bs[k] * sh[3 * k]; cg = cg + bs[k] * sh[3 * k + 1]; cb = cb + bs[k] * sh[3 * k + 2]; }
-                }
-                cr += 0.5f; cg += 0.5f; cb += 0.5f;
-                clamped = (cr < 0.f ? 1u : 0u) | (cg < 0.f ? 2u : 0u) | (cb < 0.f ? 4u : 0u);
-                r_ = fmaxf(cr, 0.f); g_ = fmaxf(cg, 0.f); b_ = fmaxf(cb, 0.f);
-            }
-            rr[1] = make_float4(q1.x, q1.y, r_, g_);
-            rr[2] = make_float4(b_, q1.z, __uint_as_float(clamped), q1.w);
-            float4* aa = acc + (size_t)3 * i;
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));   // a2.w = compact slot
+            const float4* rr = rec + (size_t)GS_REC_V4 * i;
+            const float4 q0 = __ldg(rr), q1 = __ldg(rr + 1);   // k_project: (x,y,A,B), (C, opacity, depth, thr)
             const int4 rect = gs_rect(q0.x, q0.y, radii[i], v.gx, v.gy);
             area = (uint32_t)((rect.z - rect.x) * (rect.w - rect.y));
             const int t = threadIdx.x;
@@ -304,30 +266,84 @@ k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_
     }
 }
 
+// After the scan (off the host's critical path): SH -> RGB for the visible Gaussians, final record + zeroed
+// accumulator, and emission of the (tile, Gaussian) pairs into the tile buckets.
 __global__ void __launch_bounds__(kThreads)
-k_emit(const GsView v, const int* __restrict__ radii, const float4* __restrict__ rec,
-       const uint32_t* __restrict__ vis_list, const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ tile_cur,
-       GsDevStatus* __restrict__ status, unsigned long long* __restrict__ keys, long long capacity) {
-    if ((long long)status->num_pairs > capacity) {      // device-side guard: nothing is binned, host re-renders
-        if (blockIdx.x == 0 && threadIdx.x == 0) status->overflow = 1u;
-        return;
+k_shade_emit(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
+             const float* __restrict__ colors_precomp, const int* __restrict__ radii, float4* __restrict__ rec,
+             float4* __restrict__ acc, const uint32_t* __restrict__ vis_list, const uint32_t* __restrict__ tile_off,
+             uint32_t* __restrict__ tile_cur, GsDevStatus* __restrict__ status, unsigned long long* __restrict__ keys,
+             long long capacity, const bool shaded) {
+    const bool overflow = (long long)status->num_pairs > capacity;   // device-side guard: nothing is binned then,
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                       // the host re-renders with a larger buffer
+        if (overflow) status->overflow = 1u;
+        else { status->n_big = 0u; status->n_mid = 0u; }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { status->n_big = 0u; status->n_mid = 0u; }
     __shared__ CandShared S;
+    __shared__ float s_campos[3];
+    if (threadIdx.x < 3) s_campos[threadIdx.x] = __ldg(v.campos + threadIdx.x);
+    __syncthreads();
     const uint32_t nvis = (uint32_t)status->num_visible;
+    const bool aligned = ((v.M * 3) & 3) == 0;
     for (uint32_t chunk = blockIdx.x * kChunk; chunk < nvis; chunk += gridDim.x * kChunk) {
         const uint32_t c = chunk + threadIdx.x;
         uint32_t area = 0;
         if (threadIdx.x < kChunk && c < nvis) {
             const uint32_t i = vis_list[c];
-            const float4* rr = rec + (size_t)GS_REC_V4 * i;
-            const float4 q0 = __ldg(rr), q1 = __ldg(rr + 1), q2 = __ldg(rr + 2);
+            float4* rr = rec + (size_t)GS_REC_V4 * i;
+            const float4 q0 = rr[0];
+            float4 q1 = rr[1];
+            float depth, thr;
+            const float4 q2old = rr[2];
+            // first render of this frame: q1 = (C, opacity, depth, thr) from k_project.  A re-render after a capacity
+            // overflow (`shaded`, set by the host) finds the final record layout already in place.
+            if (!shaded) {
+                depth = q1.z; thr = q1.w;
+                float r_, g_, b_;
+                uint32_t clamped = 0;
+                if (colors_precomp) {
+                    r_ = colors_precomp[3 * i]; g_ = colors_precomp[3 * i + 1]; b_ = colors_precomp[3 * i + 2];
+                } else {                                 // forward.cu:20-71
+                    const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+                    float3 d = make_float3(p.x - s_campos[0], p.y - s_campos[1], p.z - s_campos[2]);
+                    const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+                    d.x = d.x / len; d.y = d.y / len; d.z = d.z / len;
+                    const float* sh = shs + (size_t)i * v.M * 3;
+                    float cr, cg, cb;
+                    if (aligned) {
+                        switch (v.D) {
+                            case 0: sh_to_rgb<0>(sh, d.x, d.y, d.z, cr, cg, cb); break;
+                            case 1: sh_to_rgb<1>(sh, d.x, d.y, d.z, cr, cg, cb); break;
+                            case 2: sh_to_rgb<2>(sh, d.x, d.y, d.z, cr, cg, cb); break;
+                            default: sh_to_rgb<3>(sh, d.x, d.y, d.z, cr, cg, cb); break;
+                        }
+                    } else {
+                        float bs[16];
+                        gs_sh_basis(v.D, d.x, d.y, d.z, bs);
+                        cr = bs[0] * sh[0]; cg = bs[0] * sh[1]; cb = bs[0] * sh[2];
+                        const int na = (v.D + 1) * (v.D + 1);
+                        for (int k = 1; k < na; k++) { cr = cr + bs[k] * sh[3 * k]; cg = cg + bs[k] * sh[3 * k + 1]; cb = cb + bs[k] * sh[3 * k + 2]; }
+                    }
+                    cr += 0.5f; cg += 0.5f; cb += 0.5f;
+                    clamped = (cr < 0.f ? 1u : 0u) | (cg < 0.f ? 2u : 0u) | (cb < 0.f ? 4u : 0u);
+                    r_ = fmaxf(cr, 0.f); g_ = fmaxf(cg, 0.f); b_ = fmaxf(cb, 0.f);
+                }
+                q1 = make_float4(q1.x, q1.y, r_, g_);
+                rr[1] = q1;
+                rr[2] = make_float4(b_, depth, __uint_as_float(clamped), thr);
+                float4* aa = acc + (size_t)3 * i;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                aa[0] = z4; aa[1] = z4;
+                aa[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));   // a2.w = compact slot
+            } else {
+                depth = q2old.y; thr = q2old.w;
+            }
             const int4 rect = gs_rect(q0.x, q0.y, radii[i], v.gx, v.gy);   // same recomputation as rasterizer_impl.cu:91
-            area = (uint32_t)((rect.z - rect.x) * (rect.w - rect.y));
+            area = overflow ? 0u : (uint32_t)((rect.z - rect.x) * (rect.w - rect.y));
             const int t = threadIdx.x;
-            S.mx[t] = q0.x; S.my[t] = q0.y; S.A[t] = q0.z; S.B[t] = q0.w; S.C[t] = q1.x; S.thr[t] = q2.w;
+            S.mx[t] = q0.x; S.my[t] = q0.y; S.A[t] = q0.z; S.B[t] = q0.w; S.C[t] = q1.x; S.thr[t] = thr;
             S.rx[t] = rect.x; S.ry[t] = rect.y; S.rw[t] = rect.z - rect.x;
-            S.p0[t] = __float_as_uint(q2.y); S.p1[t] = i;
+            S.p0[t] = __float_as_uint(depth); S.p1[t] = i;
         }
         const uint32_t total = cta_scan_areas(S, area);
         cta_for_each_hit(S, total, v.gx, [&](uint32_t tile, uint32_t d, uint32_t idx) {
@@ -356,23 +372,24 @@ void gs_launch_project(const GsView& v, const float* means3D, const float* opaci
     k_project<<<grid, kThreads, 0, s>>>(v, means3D, opacities, scales, rotations, cov3D_precomp, radii, rec, vis_list,
                                        status);
 }
-void gs_launch_shade_count(const GsView& v, int num_sms, const float* means3D, const float* shs,
-                           const float* colors_precomp, const int* radii, float4* rec, float4* acc,
-                           const uint32_t* vis_list, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s) {
+void gs_launch_count_tiles(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
+                           uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s) {
     const int need = (v.P + kChunk - 1) / kChunk;
     const int grid = need < num_sms * 8 ? need : num_sms * 8;
-    k_shade_count<<<grid, kThreads, 0, s>>>(v, means3D, shs, colors_precomp, radii, rec, acc, vis_list, tile_cnt, status);
+    k_count_tiles<<<grid, kThreads, 0, s>>>(v, radii, rec, vis_list, tile_cnt, status);
 }
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status, GsDevStatus* host_slot,
                          cudaStream_t s) {
     k_tile_scan<<<1, kScanT, 0, s>>>(G, tile_cnt, tile_off, status, host_slot);
 }
-void gs_launch_emit(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
-                    const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status, unsigned long long* keys,
-                    long long capacity, cudaStream_t s) {
+void gs_launch_shade_emit(const GsView& v, int num_sms, const float* means3D, const float* shs,
+                          const float* colors_precomp, const int* radii, float4* rec, float4* acc,
+                          const uint32_t* vis_list, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
+                          unsigned long long* keys, long long capacity, bool shaded, cudaStream_t s) {
     const int need = (v.P + kChunk - 1) / kChunk;
     const int grid = need < num_sms * 8 ? need : num_sms * 8;
-    k_emit<<<grid, kThreads, 0, s>>>(v, radii, rec, vis_list, tile_off, tile_cur, status, keys, capacity);
+    k_shade_emit<<<grid, kThreads, 0, s>>>(v, means3D, shs, colors_precomp, radii, rec, acc, vis_list, tile_off,
+                                           tile_cur, status, keys, capacity, shaded);
 }
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s) {
     k_mark_visible<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, vm, present);

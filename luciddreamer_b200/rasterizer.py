@@ -115,20 +115,20 @@ def _forward_impl(prep: _Prepared):
             cap = _round_cap(counts.num_pairs * 1.25 + 4096)
             binning = torch.empty((L.gs_binning_bytes(cap),), **u8)
             N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
-                                        img.data_ptr(), color.data_ptr(), depth.data_ptr(), stream))
+                                        img.data_ptr(), color.data_ptr(), depth.data_ptr(), 0, stream))
         else:
             # speculative: enqueue the render with the previous capacity, *then* wait for the count; the GPU
             # never idles on the host (reference: blocking cudaMemcpy, rasterizer_impl.cu:282)
             cap = _round_cap(hint * 1.25 + 4096)
             binning = torch.empty((L.gs_binning_bytes(cap),), **u8)
             N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
-                                        img.data_ptr(), color.data_ptr(), depth.data_ptr(), stream))
+                                        img.data_ptr(), color.data_ptr(), depth.data_ptr(), 0, stream))
             N.check(L.gs_forward_counts(ctx, ticket, C.byref(counts)))
             if counts.num_pairs > cap:       # device-side guard skipped the render: grow and redo it
                 cap = _round_cap(counts.num_pairs * 1.25 + 4096)
                 binning = torch.empty((L.gs_binning_bytes(cap),), **u8)
                 N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
-                                            cap, img.data_ptr(), color.data_ptr(), depth.data_ptr(), stream))
+                                            cap, img.data_ptr(), color.data_ptr(), depth.data_ptr(), 1, stream))
         _cap_hint[idx] = int(counts.num_pairs)
     return int(counts.num_rendered), color, depth, radii, geom, binning, img, (cap, int(counts.num_visible))
 

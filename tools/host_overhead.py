@@ -36,3 +36,18 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(200): step()
 torch.cuda.synchronize(); pr.disable()
 st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("tottime").print_stats(22); print(st.getvalue()[:4500])
+
+# ---- the e2e loop of bench.py on the same tiny scene: host cost of the extra per-step operations
+import bench as B
+class _I:  # minimal impl wrapper like bench.Ours
+    pass
+cam_small = cam
+impl = B.Ours({k: sc[k].cpu() for k in sc}, cam_small, dev, 3)
+tgt = torch.randint(0, 256, (H, W, 3), dtype=torch.uint8)
+for _ in range(2):
+    ms, h2d, d2h, loss = B.time_e2e(impl, cam_small, tgt, 200, 20, 1, fused_loss=True)
+print(f"host: e2e loop {ms/200*1e3:.1f} us per step at P={P}, {W}x{H}")
+pr = cProfile.Profile(); pr.enable()
+B.time_e2e(impl, cam_small, tgt, 200, 5, 1, fused_loss=True)
+pr.disable()
+st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("tottime").print_stats(16); print(st.getvalue()[:3800])
