@@ -121,11 +121,12 @@ __device__ __forceinline__ void fwd_eval4(FwdPix* P, const SRec& r, const float 
         const bool term = ok && (test_T < 0.0001f);       // forward.cu:348-352 (also true for T <= 0)
         const bool upd = ok && !term;
         if (upd) {
-            p.C0 += r.b.z * al * p.T;
-            p.C1 += r.b.w * al * p.T;
-            p.C2 += r.c.x * al * p.T;
-            p.D += r.c.y * al * p.T;
-            p.acc += al * p.T;
+            const float w = al * p.T;                     // one weight for colour, depth and coverage
+            p.C0 += r.b.z * w;
+            p.C1 += r.b.w * w;
+            p.C2 += r.c.x * w;
+            p.D += r.c.y * w;
+            p.acc += w;
             p.last = pos1;
         }
         p.T = upd ? test_T : (term ? -fabsf(p.T) : p.T);
@@ -247,6 +248,7 @@ __device__ __forceinline__ bool bwd_eval4(BwdPix* Q, const SRec& r, const float 
                                           const float ddelx_dx, const float ddely_dy, float* vv) {
     float power[kPix], G[kPix], alpha[kPix];
     bool band = false;
+    const float Adx = r.a.z * dx, Bdx = r.a.w * dx, dx2 = dx * dx;
 #pragma unroll
     for (int q = 0; q < kPix; q++) {
         power[q] = -0.5f * (r.a.z * dx * dx + r.b.x * dy[q] * dy[q]) - r.a.w * dx * dy[q];
@@ -284,17 +286,21 @@ __device__ __forceinline__ bool bwd_eval4(BwdPix* Q, const SRec& r, const float 
         dL_dalpha *= T;
         dL_dalpha += p.tb * inv;
         dL_dalpha = ok ? dL_dalpha : 0.f;
-        const float dL_dG = r.b.y * dL_dalpha;
         const float Gq = ok ? G[q] : 0.f;                   // keeps inf/NaN of skipped splats out of the sums
-        const float gdx = Gq * dx, gdy = Gq * dy[q];
-        const float dG_ddelx = -gdx * r.a.z - gdy * r.a.w;
-        const float dG_ddely = -gdy * r.b.x - gdx * r.a.w;
-        vv[3] += dL_dG * dG_ddelx * ddelx_dx;
-        vv[4] += dL_dG * dG_ddely * ddely_dy;
-        vv[5] += -0.5f * gdx * dx * dL_dG;
-        vv[6] += -0.5f * gdx * dy[q] * dL_dG;
-        vv[7] += -0.5f * gdy * dy[q] * dL_dG;
-        vv[8] += Gq * dL_dalpha;
+        // backward.cu:563-583 with the constant factors (-0.5*W, -0.5*H for the mean, -0.5 for the conic) applied
+        // once per (tile, splat) when the CTA flushes, and the dx terms shared by the four pixels:
+        //   dL_dmean2D.x = -0.5 W * sum k (A dx + B dy)      dL_dconic.a = -0.5 * sum k dx dx
+        //   dL_dmean2D.y = -0.5 H * sum k (C dy + B dx)      dL_dconic.b = -0.5 * sum k dx dy      k = o G dL_dalpha
+        //   dL_dopacity  = sum G dL_dalpha                   dL_dconic.c = -0.5 * sum k dy dy
+        const float gda = Gq * dL_dalpha;
+        const float k = r.b.y * gda;
+        const float kdy = k * dy[q];
+        vv[3] += k * (Adx + r.a.w * dy[q]);
+        vv[4] += k * (r.b.x * dy[q] + Bdx);
+        vv[5] += k * dx2;
+        vv[6] += kdy * dx;
+        vv[7] += kdy * dy[q];
+        vv[8] += gda;
     }
     return any;
 }
@@ -396,8 +402,8 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
                 for (int k = 0; k < 9; k++) { r[k] = sAcc[j * 9 + k]; any = any || (r[k] != 0.f); }
                 if (any) {
                     float4* dst = acc + (size_t)3 * sRec[j].id;
-                    atomicAdd(dst, make_float4(r[3], r[4], r[5], r[6]));
-                    atomicAdd(dst + 1, make_float4(r[7], r[8], r[0], r[1]));
+                    atomicAdd(dst, make_float4(-r[3] * ddelx_dx, -r[4] * ddely_dy, -0.5f * r[5], -0.5f * r[6]));
+                    atomicAdd(dst + 1, make_float4(-0.5f * r[7], r[8], r[0], r[1]));
                     atomicAdd(reinterpret_cast<float*>(dst + 2), r[2]);
                 }
             }
