@@ -160,6 +160,34 @@ def view_step(params: dict, settings, cotangent: torch.Tensor, bucket: Optional[
     return color, depth, radii, bucket, dm2
 
 
+def multi_view_step(params: dict, settings_list: Sequence, cotangents: Sequence, bucket: GradBucket, rank: int = 0,
+                    world: int = 1, stats: Optional[DensifyStats] = None):
+    """This rank's share of a shared-model optimisation step over `settings_list` (config 5): forward+backward of
+    every local view, parameter gradients SUMMED over the views into `bucket`.  With a SymmGradBucket the sum also
+    runs over all ranks (call bucket.begin_step() before and bucket.end_step() after); with a plain GradBucket call
+    allreduce_bucket(bucket) afterwards.  Returns {view: (color, depth, radii)}."""
+    out = {}
+    views = shard_views(len(settings_list), rank, world)
+    symm = isinstance(bucket, SymmGradBucket)
+    tmp = None
+    for n, v in enumerate(views):
+        if symm or n == 0:
+            target = bucket
+        else:
+            if tmp is None:
+                tmp = GradBucket(bucket.P, bucket.M, bucket.flat.device)
+            target = tmp
+        color, depth, radii, _b, dm2 = view_step(params, settings_list[v], cotangents[v], bucket=target)
+        if target is tmp:
+            bucket.flat.add_(tmp.flat)
+        if stats is not None:
+            stats.add_view(dm2, radii)
+        out[v] = (color, depth, radii)
+    if not views and not symm:
+        bucket.flat.zero_()
+    return out
+
+
 def render_views(params: dict, settings_list: Sequence, rank: int = 0, world: int = 1):
     """Forward-only batch render of this rank's share of `settings_list` (config 4).  Returns {view: (color, depth)}."""
     from . import rasterizer as R

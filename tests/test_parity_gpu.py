@@ -268,3 +268,82 @@ def test_fused_l1_loss_matches_torch():
     loss, grad = losses.l1_loss_with_grad(color, tgt, weight=0.8)
     assert abs(float(loss) - float(ref)) < 1e-6
     assert torch.allclose(grad, color.grad, atol=1e-9)
+
+
+def _rot_views(n, W, H, d, D=3):
+    from luciddreamer_b200 import GaussianRasterizationSettings
+    from luciddreamer_b200 import synthetic as syn
+    poses = syn.rotate360_poses(64)
+    out = []
+    for k in range(n):
+        cam = syn.make_camera(W, H, c2w=poses[(k * 7) % 64], swap_fov_like_load_json=True)
+        out.append((cam, GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=d), 1.0,
+                                                       cam.viewmatrix.to(d), cam.projmatrix.to(d), D, cam.campos.to(d),
+                                                       False, False)))
+    return out
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_cuda", fromlist=["x"]).available(), reason="oracle/_ref not built")
+def test_view_batch_matches_reference_per_view():
+    """BASELINE config 4 in miniature: a rotate360 view batch rendered forward-only through multiview.render_views
+    (sharded 1- and 2-way) equals the reference rasterizer view by view."""
+    from luciddreamer_b200 import multiview as MV
+    from luciddreamer_b200 import synthetic as syn
+    from oracle import ref_cuda
+    d = dev()
+    P, W, H = 60_000, 320, 180
+    sc = {k: v.to(d) for k, v in syn.make_scene(P, 31, scale_mult=2.0).items()}
+    views = _rot_views(6, W, H, d)
+    settings = [s for _, s in views]
+    full = MV.render_views(sc, settings)
+    parts = {}
+    for r in range(2):
+        parts.update(MV.render_views(sc, settings, rank=r, world=2))
+    assert sorted(parts) == sorted(full) == list(range(6))
+    rc = ref_cuda.RefContext()
+    for v, (cam, rs) in enumerate(views):
+        R, rcol, rdep, rrad = ref_cuda.rasterize_gaussians(rc, rs.bg, sc["means3D"], None, sc["opacities"], sc["scales"],
+                                                           sc["rotations"], 1.0, None, rs.viewmatrix, rs.projmatrix,
+                                                           cam.tanfovx, cam.tanfovy, H, W, sc["shs"], 3, rs.campos)
+        torch.cuda.synchronize()
+        assert torch.equal(full[v][0], parts[v][0])                 # sharding does not change a view's pixels
+        gold = dict(color=rcol.cpu().numpy(), depth=rdep.cpu().numpy(), radii=np.zeros(0))
+        dc = np.abs(full[v][0].cpu().numpy() - gold["color"]).max()
+        dd = np.abs(full[v][1].cpu().numpy() - gold["depth"]).max()
+        assert dc <= util.FWD_ABS_TOL and dd <= util.FWD_ABS_TOL, (v, dc, dd)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_cuda", fromlist=["x"]).available(), reason="oracle/_ref not built")
+def test_shared_model_step_sums_reference_gradients():
+    """BASELINE config 5 in miniature (single process): multiview.multi_view_step sums the per-view parameter
+    gradients into one flat bucket; compare with the sum of the reference's per-view gradients; the densification
+    statistics are sums of per-view norms."""
+    from luciddreamer_b200 import multiview as MV
+    from luciddreamer_b200 import synthetic as syn
+    from oracle import ref_cuda
+    d = dev()
+    P, W, H = 40_000, 256, 144
+    sc = {k: v.to(d) for k, v in syn.make_scene(P, 32, scale_mult=2.0).items()}
+    views = _rot_views(3, W, H, d)
+    cots = [syn.make_cotangent(H, W, 100 + k).to(d) for k in range(3)]
+    bucket = MV.GradBucket(P, 16, d)
+    stats = MV.DensifyStats(P, d)
+    MV.multi_view_step(sc, [s for _, s in views], cots, bucket, stats=stats)
+    rc = ref_cuda.RefContext()
+    acc = {k: 0 for k in ("m3", "sh", "op", "sc", "rot")}
+    norm_acc = torch.zeros(P, 1, device=d); denom = torch.zeros(P, 1, device=d)
+    for (cam, rs), cot in zip(views, cots):
+        R, rcol, rdep, rrad = ref_cuda.rasterize_gaussians(rc, rs.bg, sc["means3D"], None, sc["opacities"], sc["scales"],
+                                                           sc["rotations"], 1.0, None, rs.viewmatrix, rs.projmatrix,
+                                                           cam.tanfovx, cam.tanfovy, H, W, sc["shs"], 3, rs.campos)
+        g = ref_cuda.rasterize_gaussians_backward(rc, rrad, cot)
+        acc["m3"] = acc["m3"] + g[3]; acc["sh"] = acc["sh"] + g[5]; acc["op"] = acc["op"] + g[2]
+        acc["sc"] = acc["sc"] + g[6]; acc["rot"] = acc["rot"] + g[7]
+        vis = rrad > 0
+        norm_acc[vis] += torch.norm(g[0][vis, :2], dim=-1, keepdim=True); denom[vis] += 1
+    torch.cuda.synchronize()
+    for name, mine in (("m3", bucket.means3D), ("sh", bucket.shs), ("op", bucket.opacities), ("sc", bucket.scales),
+                       ("rot", bucket.rotations)):
+        assert util.rel_err(mine.cpu().numpy(), acc[name].cpu().numpy()) < util.GRAD_REL_TOL, name
+    assert torch.equal(stats.denom, denom)
+    assert util.rel_err(stats.xyz_gradient_accum.cpu().numpy(), norm_acc.cpu().numpy()) < util.GRAD_REL_TOL
