@@ -339,6 +339,17 @@ __device__ __forceinline__ void peer_add(const GsPeerArgs& pa, long long off, fl
         for (int r = 0; r < pa.world; r++) atomicAdd(pa.peers[r] + off, v);
     }
 }
+// 128-bit variant (off must be a multiple of 4 floats and the buckets 16-byte aligned)
+__device__ __forceinline__ void peer_add4(const GsPeerArgs& pa, long long off, float4 v) {
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
+    if (pa.mc) {
+        asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pa.mc + off), "f"(v.x),
+                     "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    } else {
+        for (int r = 0; r < pa.world; r++) atomicAdd(reinterpret_cast<float4*>(pa.peers[r] + off), v);
+    }
+}
 
 __global__ void __launch_bounds__(kT)
 k_grad_reduce_peers(const int P, const int M, const int* __restrict__ radii, const float4* __restrict__ acc,
@@ -383,6 +394,30 @@ k_grad_reduce_peers(const int P, const int M, const int* __restrict__ radii, con
     }
     const int nv = s_count;
     const int M3 = M * 3;
+    if (M3 == 48 && ((pa.off_sh | pa.off_rot) & 3) == 0) {
+        // M = 16: 20 reductions per visible Gaussian -- 3 (mean) + 12 x 128-bit (SH) + 1 (opacity) + 3 (scale)
+        // + 1 x 128-bit (rotation)
+        for (int e = tid; e < nv * 20; e += kT) {
+            const int c2 = e / 20, k = e - c2 * 20;
+            const long long gi = row0 + s_rowidx[c2];
+            const float* r = s_row + c2 * kRow;
+            if (k < 3) peer_add(pa, pa.off_m3 + gi * 3 + k, r[k]);
+            else if (k < 15) {
+                const int j = k - 3;                     // float4 j of the row's 48 SH gradients
+                float o[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int q = 4 * j + u;
+                    const int kk = q / 3, ch = q - 3 * kk;
+                    o[u] = r[16 + kk] * r[13 + ch];
+                }
+                peer_add4(pa, pa.off_sh + gi * 48 + 4 * j, make_float4(o[0], o[1], o[2], o[3]));
+            } else if (k == 15) peer_add(pa, pa.off_op + gi, r[5]);
+            else if (k < 19) peer_add(pa, pa.off_sc + gi * 3 + (k - 16), r[6 + (k - 16)]);
+            else peer_add4(pa, pa.off_rot + gi * 4, make_float4(r[9], r[10], r[11], r[12]));
+        }
+        return;
+    }
     const int per = 3 + M3 + 1 + 3 + 4;                  // floats per Gaussian in the bucket
     for (int e = tid; e < nv * per; e += kT) {
         const int c2 = e / per;
