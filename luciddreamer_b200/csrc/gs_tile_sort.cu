@@ -8,21 +8,83 @@
 // index (emission order).
 //   k_tile_sort      one WARP per tile for buckets up to 256 keys (shared memory, __syncwarp only); larger
 //                    buckets are queued (mid from the front of the queue, big from the back) for
-//   k_tile_sort_mid  one 128-thread CTA per queued tile, up to 4096 keys (32 KB shared memory), persistent grid
-//   k_tile_sort_big  one 512-thread CTA per queued tile, up to 16384 keys (128 KB); beyond that the same network
+//   k_tile_sort_mid  one 128-thread CTA per queued tile, up to 2048 keys (2 x 16 KB shared memory), persistent grid
+//   k_tile_sort_big  one 512-thread CTA per queued tile, up to 8192 keys (2 x 64 KB); beyond that a bitonic network
 //                    runs in place in global memory (slow path, correctness only).
-// Sorting network: bitonic for arbitrary n (flip / half-cleaner form, every comparison ascending, so the virtual
-// +inf padding never moves and comparisons against it are simply skipped).
+// Algorithm in shared memory: runs of 32 keys are sorted in registers with a warp-shuffle bitonic network, then
+// runs are merged pairwise by rank: every key binary-searches its position in the sibling run (keys are unique, so
+// "number of sibling keys smaller than mine" is its exact offset) and is written to own-offset + rank in a second
+// buffer.  ~log2(n/32) passes of log2(L)+1 shared-memory probes per key instead of the ~log2(n)^2/2 compare-exchange
+// stages of a full bitonic network.
 #include "gs_common.cuh"
 
 namespace {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kWarpKeys = 256;       // 2 KB of u64 keys per warp
+constexpr int kWarpKeys = 256;       // 2 x 2 KB of u64 keys per warp
 constexpr int kMidThreads = 128;
-constexpr int kMidKeys = 4096;       // 32 KB static shared memory
+constexpr int kMidKeys = 2048;       // 2 x 16 KB static shared memory
 constexpr int kBigThreads = 512;
-constexpr int kBigKeys = 16384;      // 128 KB dynamic shared memory
+constexpr int kBigKeys = 8192;       // 2 x 64 KB dynamic shared memory
+
+// sorts the 32 keys held one per lane (ascending across lanes); keys are unique
+__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long key, const int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool up = ((lane & k) == 0);            // ascending block?
+            const bool lower = ((lane & j) == 0);         // I hold the lower position of the pair
+            const bool take_min = (up == lower);
+            const bool other_smaller = other < key;
+            key = (take_min == other_smaller) ? other : key;
+        }
+    }
+    return key;
+}
+
+// number of elements of a[0..len) that are < key; len <= L, L a power of two
+__device__ __forceinline__ int rank_in_run(const unsigned long long* a, const int len, const int L,
+                                           const unsigned long long key) {
+    int pos = 0;
+    for (int step = L; step >= 1; step >>= 1) {
+        const int probe = pos + step;
+        if (probe <= len && a[probe - 1] < key) pos = probe;
+    }
+    return pos;
+}
+
+// Sorts n unique keys that sit in A[0..n); B is scratch of the same capacity.  Returns the buffer holding the result.
+// All `nthreads` threads of the group call; sync() synchronises the group.
+template <typename Sync>
+__device__ __forceinline__ unsigned long long* merge_rank_sort(unsigned long long* A, unsigned long long* B, const int n,
+                                                               const int tid, const int nthreads, Sync sync) {
+    const int lane = tid & 31;
+    // phase 1: each warp sorts runs of 32 in registers
+    for (int c = (tid >> 5) * 32; c < n; c += nthreads) {
+        const int i = c + lane;
+        unsigned long long key = i < n ? A[i] : ~0ull;    // +inf padding sorts to the end of the run
+        key = warp_sort32(key, lane);
+        if (i < n) A[i] = key;
+    }
+    sync();
+    // phase 2: pairwise merges by rank
+    for (int L = 32; L < n; L <<= 1) {
+        for (int i = tid; i < n; i += nthreads) {
+            const int own = i & ~(L - 1);
+            const int sib = own ^ L;
+            const int sl = min(L, n - sib);               // <= 0 when the sibling run does not exist
+            const unsigned long long key = A[i];
+            // ties cannot occur (unique keys), so "< key" ranks are exact for both sides of the pair
+            const int rank = sl > 0 ? rank_in_run(A + sib, sl, L, key) : 0;
+            B[min(own, sib) + (i - own) + rank] = key;
+        }
+        sync();
+        unsigned long long* t = A; A = B; B = t;
+    }
+    return A;
+}
 
 template <typename Ptr, typename Sync>
 __device__ __forceinline__ void bitonic_sort_any_n(Ptr a, const int n, const int tid, const int nthreads, Sync sync) {
@@ -60,7 +122,7 @@ k_tile_sort(int G, const uint32_t* __restrict__ tile_off, uint32_t* __restrict__
             GsDevStatus* __restrict__ status, uint32_t* __restrict__ big_list,
             const unsigned long long* __restrict__ keys, uint32_t* __restrict__ list, long long capacity) {
     if ((long long)status->num_pairs > capacity) return;
-    __shared__ unsigned long long s_keys[kWarpsPerCta][kWarpKeys];
+    __shared__ unsigned long long s_keys[kWarpsPerCta][2][kWarpKeys];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int tile = blockIdx.x * kWarpsPerCta + wid;
     if (tile >= G) return;
@@ -75,11 +137,11 @@ k_tile_sort(int G, const uint32_t* __restrict__ tile_off, uint32_t* __restrict__
         }
         return;
     }
-    unsigned long long* a = s_keys[wid];
+    unsigned long long* a = s_keys[wid][0];
     const unsigned long long* g = keys + beg;
     for (int t = lane; t < n; t += 32) a[t] = g[t];
     __syncwarp();
-    if (n > 1) bitonic_sort_any_n(a, n, lane, 32, [] { __syncwarp(); });
+    if (n > 1) a = merge_rank_sort(a, s_keys[wid][1], n, lane, 32, [] { __syncwarp(); });
     for (int t = lane; t < n; t += 32) list[beg + t] = (uint32_t)a[t];
 }
 
@@ -89,7 +151,7 @@ k_tile_sort_mid(const uint32_t* __restrict__ tile_off, const GsDevStatus* __rest
                 const uint32_t* __restrict__ big_list, const unsigned long long* __restrict__ keys,
                 uint32_t* __restrict__ list, long long capacity) {
     if ((long long)status->num_pairs > capacity) return;
-    __shared__ unsigned long long s_mid[kMidKeys];
+    __shared__ unsigned long long s_mid[2][kMidKeys];
     const unsigned nmid = status->n_mid;
     for (unsigned b = blockIdx.x; b < nmid; b += gridDim.x) {
         const uint32_t tile = big_list[b];
@@ -97,10 +159,10 @@ k_tile_sort_mid(const uint32_t* __restrict__ tile_off, const GsDevStatus* __rest
         const int n = (int)(end - beg);
         const unsigned long long* g = keys + beg;
         __syncthreads();
-        for (int t = threadIdx.x; t < n; t += kMidThreads) s_mid[t] = g[t];
+        for (int t = threadIdx.x; t < n; t += kMidThreads) s_mid[0][t] = g[t];
         __syncthreads();
-        bitonic_sort_any_n(s_mid, n, threadIdx.x, kMidThreads, [] { __syncthreads(); });
-        for (int t = threadIdx.x; t < n; t += kMidThreads) list[beg + t] = (uint32_t)s_mid[t];
+        const unsigned long long* r = merge_rank_sort(s_mid[0], s_mid[1], n, threadIdx.x, kMidThreads, [] { __syncthreads(); });
+        for (int t = threadIdx.x; t < n; t += kMidThreads) list[beg + t] = (uint32_t)r[t];
     }
 }
 
@@ -120,8 +182,8 @@ k_tile_sort_big(int G, const uint32_t* __restrict__ tile_off, const GsDevStatus*
         if (n <= kBigKeys) {
             for (int t = threadIdx.x; t < n; t += kBigThreads) s_big[t] = g[t];
             __syncthreads();
-            bitonic_sort_any_n(s_big, n, threadIdx.x, kBigThreads, [] { __syncthreads(); });
-            for (int t = threadIdx.x; t < n; t += kBigThreads) list[beg + t] = (uint32_t)s_big[t];
+            const unsigned long long* r = merge_rank_sort(s_big, s_big + kBigKeys, n, threadIdx.x, kBigThreads, [] { __syncthreads(); });
+            for (int t = threadIdx.x; t < n; t += kBigThreads) list[beg + t] = (uint32_t)r[t];
         } else {
             bitonic_sort_any_n(g, n, threadIdx.x, kBigThreads, [] { __syncthreads(); });
             for (int t = threadIdx.x; t < n; t += kBigThreads) list[beg + t] = (uint32_t)g[t];
@@ -133,7 +195,7 @@ k_tile_sort_big(int G, const uint32_t* __restrict__ tile_off, const GsDevStatus*
 
 // per device, once (called from gs_context_create with the device current)
 void gs_tile_sort_init() {
-    cudaFuncSetAttribute(k_tile_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigKeys * 8);
+    cudaFuncSetAttribute(k_tile_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBigKeys * 8);
 }
 
 void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
@@ -146,6 +208,6 @@ void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t*
     k_tile_sort_mid<<<gmid, kMidThreads, 0, s>>>(tile_off, status, big_list, keys, list, capacity);
     if (prof) { cudaEventRecord(prof[1], s); cudaEventRecord(prof[2], s); }
     const int grid = G < num_sms ? G : num_sms;
-    k_tile_sort_big<<<grid, kBigThreads, kBigKeys * 8, s>>>(G, tile_off, status, big_list, keys, list, capacity);
+    k_tile_sort_big<<<grid, kBigThreads, 2 * kBigKeys * 8, s>>>(G, tile_off, status, big_list, keys, list, capacity);
     if (prof) cudaEventRecord(prof[3], s);
 }

@@ -347,3 +347,41 @@ def test_shared_model_step_sums_reference_gradients():
         assert util.rel_err(mine.cpu().numpy(), acc[name].cpu().numpy()) < util.GRAD_REL_TOL, name
     assert torch.equal(stats.denom, denom)
     assert util.rel_err(stats.xyz_gradient_accum.cpu().numpy(), norm_acc.cpu().numpy()) < util.GRAD_REL_TOL
+
+
+@pytest.mark.parametrize("P", [600, 1500, 5000, 12000])
+def test_long_tile_lists_all_sort_paths(P):
+    """Every Gaussian covers the whole 32x32 image, so each of the 4 tiles holds P pairs: exercises the warp
+    (<=256), mid (<=2048), big (<=8192) and in-place global (>8192) per-tile sort paths, incl. bit-identical depths."""
+    from luciddreamer_b200 import synthetic as syn
+    from luciddreamer_b200.rasterizer import _C
+    from oracle import oracle
+    d = dev()
+    g = torch.Generator().manual_seed(P)
+    means = torch.stack([torch.rand(P, generator=g) * 0.6 - 0.3, torch.rand(P, generator=g) * 0.6 - 0.3,
+                         torch.rand(P, generator=g) * 2 + 1], 1)
+    means[1::7, 2] = means[0::7, 2][: means[1::7].shape[0]]          # depth ties
+    scales = (torch.rand(P, 3, generator=g) * 0.4 + 0.4).contiguous()
+    rots = torch.randn(P, 4, generator=g)
+    rots = (rots / rots.norm(dim=1, keepdim=True)).contiguous()
+    opac = torch.rand(P, 1, generator=g) * 0.03 + 0.005
+    cols = torch.rand(P, 3, generator=g)
+    cam = syn.make_camera(32, 32)
+    e = torch.empty(0)
+    args = (torch.zeros(3), means, cols, opac, scales, rots, 1.0, e, cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy,
+            32, 32, e, 0, cam.campos, False, False)
+    f = oracle.rasterize_gaussians(*args[:17])
+    cot = syn.make_cotangent(32, 32, P)
+    og = oracle.rasterize_gaussians_backward(f, cot.numpy())
+    dargs = tuple(a.to(d) if isinstance(a, torch.Tensor) and a.numel() else a for a in args)
+    nr, color, depth, radii, geom, binning, img = _C.rasterize_gaussians(*dargs)
+    (bg, m3, colors, op, sc, rt, mod, cov, vm, pm, tfx, tfy, H, W, sh, D, cp, _p, dbg) = dargs
+    gr = _C.rasterize_gaussians_backward(bg, m3, radii, colors, sc, rt, mod, cov, vm, pm, tfx, tfy, cot.to(d),
+                                         torch.zeros(1, 32, 32, device=d), sh, D, cp, geom, nr, binning, img, dbg)
+    torch.cuda.synchronize()
+    assert nr == f.num_rendered
+    assert int(f.ranges[:, 1].max() - f.ranges[:, 0].min()) >= P            # really P pairs per tile
+    assert np.abs(color.cpu().numpy() - f.color).max() <= util.FWD_ABS_TOL
+    assert np.abs(depth.cpu().numpy() - f.depth).max() <= util.FWD_ABS_TOL
+    for k in (0, 1, 2, 3, 6, 7):
+        assert util.rel_err(gr[k].cpu().numpy(), og[k]) < util.GRAD_REL_TOL, cases.GRAD_NAMES[k]
