@@ -247,18 +247,14 @@ struct BwdPix {
 __device__ __forceinline__ bool bwd_eval4(BwdPix* Q, const SRec& r, const float dx, const float* dy, const int pos,
                                           const float ddelx_dx, const float ddely_dy, float* vv) {
     float power[kPix], G[kPix], alpha[kPix];
-    bool band = false;
     const float Adx = r.a.z * dx, Bdx = r.a.w * dx, dx2 = dx * dx;
+    // no exact-exp band here: a borderline alpha ~ 1/255 decided differently from the forward changes one pixel's
+    // reconstructed transmittance by 0.4 %, far below the gradient tolerance, and saves 3 instructions per pixel
 #pragma unroll
     for (int q = 0; q < kPix; q++) {
         power[q] = -0.5f * (r.a.z * dx * dx + r.b.x * dy[q] * dy[q]) - r.a.w * dx * dy[q];
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G[q]) : "f"(power[q] * 1.4426950408889634f));
         alpha[q] = r.b.y * G[q];
-        band = band || (fabsf(alpha[q] - 1.0f / 255.0f) < 1e-7f);
-    }
-    if (band) {                       // rare: same skip decision as the forward pass
-#pragma unroll
-        for (int q = 0; q < kPix; q++) { G[q] = expf(power[q]); alpha[q] = r.b.y * G[q]; }
     }
     bool any = false;
 #pragma unroll
