@@ -364,6 +364,41 @@ def cpu_baseline(scene, cam, cot, D, budget_s=12.0, max_steps=3):
                       f"{threads} threads, fp32), best {best * 1e3:.0f} ms/step"}
 
 
+def loss_leg(H, W, dev, iters=20):
+    """SURVEY 8f-1 ("next" row): the reference's training loss 0.8*L1 + 0.2*(1-SSIM) forward+backward at the bench
+    resolution -- our fused kernels vs the same formula in torch ops (what utils/loss.py runs), same inputs."""
+    from luciddreamer_b200 import losses
+    from oracle import loss_oracle
+    g = torch.Generator().manual_seed(7)
+    gt = torch.rand(3, H, W, generator=g).to(dev)
+    img = (gt + 0.1 * torch.randn(3, H, W, generator=g).to(dev)).clamp(0, 1)
+
+    def ours():
+        return losses.photometric_loss_with_grad(img, gt, 0.2)
+
+    def torch_ref():
+        x = img.clone().requires_grad_(True)
+        l = 0.8 * loss_oracle.l1_loss(x, gt) + 0.2 * (1.0 - loss_oracle.ssim(x, gt))
+        l.backward()
+        return l, x.grad
+
+    out = {}
+    for name, fn in (("fused_ms", ours), ("torch_ops_ms", torch_ref)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            r = fn()
+        e1.record(); torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / iters
+    a, b = ours(), torch_ref()
+    out["rel_err_grad_vs_torch"] = float(((a[1] - b[1]).norm() / b[1].norm()).item())
+    out["what"] = "0.8*L1 + 0.2*(1-SSIM) loss + gradient at the bench resolution (luciddreamer.py:301-304)"
+    return out
+
+
 def shared_model_leg(scene, cam, cot, dev, D, steps, warmup, world):
     """Config-5 style step on every rank: forward+backward of its view, then the ONE exchange of the path -- the sum
     of the per-Gaussian gradients over all views.  Two implementations are timed:
@@ -527,6 +562,11 @@ def main():
         if world > 1 and not args.no_shared_model:
             line["shared_model_step"] = shared_model_leg(scene, cam, cot, dev, D, args.steps, args.warmup, world)
 
+    if rank == 0 and world == 1 and args.impl == "ours":
+        try:
+            line["next_rows"] = {"photometric_loss": loss_leg(H, W, dev)}
+        except Exception as ex:
+            line["next_rows"] = {"photometric_loss": {"error": str(ex)[:200]}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(scene, cam, cot_cpu, D)
     if rank == 0:

@@ -169,6 +169,16 @@ int gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, co
 int gs_l1_loss_backward(GsContext* ctx, const float* color, const uint8_t* target_u8, int32_t H, int32_t W, float weight,
                         float* dL_dcolor, float* loss, gs_stream_t stream);
 
+/* "Next" row: the reference's full photometric training loss and its gradient, fused:
+ *   loss3[0] = (1 - lambda) * l1_loss(image, gt) + lambda * (1 - ssim(image, gt))     (luciddreamer.py:301-303)
+ *   loss3[1] = l1_loss (utils/loss.py:18),  loss3[2] = ssim (utils/loss.py:38-69: 11x11 Gaussian window, sigma 1.5,
+ *   zero padding, C1 = 0.01^2, C2 = 0.03^2, mean over all elements)
+ *   dL_dimage = d loss3[0] / d image   (NULL: forward only)
+ * image, gt, dL_dimage: [3,H,W] f32 device; loss3: [3] f32 device; scratch: gs_photometric_scratch_bytes(H, W). */
+size_t gs_photometric_scratch_bytes(int32_t H, int32_t W);
+int gs_photometric_loss_backward(GsContext* ctx, const float* image, const float* gt, int32_t H, int32_t W,
+                                 float lambda_dssim, void* scratch, float* dL_dimage, float* loss3, gs_stream_t stream);
+
 /* Introspection for tests: copies the per-tile exclusive offsets (uint32 [G+1]; tile t owns
  * [off[t], off[t+1]) -- the reference's `ranges`, rasterizer_impl.cu:116-138) and the depth-sorted Gaussian
  * index list (uint32 [max_pairs]; the reference's `point_list`) out of the opaque buffers (device -> device). */

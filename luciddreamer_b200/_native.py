@@ -62,6 +62,9 @@ SYMBOLS = [
     ("gs_mark_visible", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gs_l1_loss_backward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    ("gs_photometric_scratch_bytes", C.c_size_t, [C.c_int32, C.c_int32]),
+    ("gs_photometric_loss_backward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gs_debug_export_binning", C.c_int, [C.POINTER(GsFrame), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p]),
     ("gs_profile_enable", C.c_int, [C.c_void_p, C.c_int]),

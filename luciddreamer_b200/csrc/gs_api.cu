@@ -340,6 +340,18 @@ int gs_l1_loss_backward(GsContext* ctx, const float* color, const uint8_t* targe
     return GS_OK;
 }
 
+size_t gs_photometric_scratch_bytes(int32_t H, int32_t W) { return 256 + (size_t)9 * H * W * sizeof(float); }
+
+int gs_photometric_loss_backward(GsContext* ctx, const float* image, const float* gt, int32_t H, int32_t W,
+                                 float lambda_dssim, void* scratch, float* dL_dimage, float* loss3, gs_stream_t stream) {
+    (void)ctx;
+    if (!image || !gt || !scratch || !loss3 || H <= 0 || W <= 0) return fail(GS_EINVAL, "bad argument");
+    gs_launch_photometric(image, gt, H, W, lambda_dssim, scratch, dL_dimage, loss3, (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GS_ECUDA, "photometric loss launch: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
 int gs_debug_export_binning(const GsFrame* f, const void* binning_buffer, int64_t pair_capacity,
                             const void* image_buffer, uint32_t* ranges, uint32_t* point_list, int64_t max_pairs,
                             gs_stream_t stream) {

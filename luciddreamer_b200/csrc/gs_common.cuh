@@ -314,4 +314,6 @@ void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* a
                                  cudaStream_t s);
 void gs_launch_l1_loss_grad(const float* color, const uint8_t* target, int H, int W, float weight, float* dL_dcolor,
                             float* loss, int num_sms, cudaStream_t s);
+void gs_launch_photometric(const float* img, const float* gt, int H, int W, float lambda_dssim, void* scratch,
+                           float* dL_dimg, float* loss3, cudaStream_t s);
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);

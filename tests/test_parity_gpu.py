@@ -385,3 +385,26 @@ def test_long_tile_lists_all_sort_paths(P):
     assert np.abs(depth.cpu().numpy() - f.depth).max() <= util.FWD_ABS_TOL
     for k in (0, 1, 2, 3, 6, 7):
         assert util.rel_err(gr[k].cpu().numpy(), og[k]) < util.GRAD_REL_TOL, cases.GRAD_NAMES[k]
+
+
+def test_fused_photometric_loss_matches_reference_golden_and_oracle():
+    """gs_photometric_loss_backward (L1 + SSIM, fused forward+backward) vs the reference's own utils/loss.py outputs
+    (golden) and vs the float64 oracle; also through the autograd wrapper."""
+    import os
+    from luciddreamer_b200 import losses
+    from oracle import loss_oracle
+    d = dev()
+    Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_golden.npz"))
+    for name in sorted({k.rsplit("_", 1)[0] for k in Z.files if k.endswith("_loss")}):
+        img, gt = torch.from_numpy(Z[name + "_img"]).to(d), torch.from_numpy(Z[name + "_gt"]).to(d)
+        loss3, grad = losses.photometric_loss_with_grad(img, gt, 0.2)
+        torch.cuda.synchronize()
+        assert abs(float(loss3[0]) - float(Z[name + "_loss"])) < 2e-6, name
+        assert abs(float(loss3[1]) - float(Z[name + "_l1"])) < 2e-6 and abs(float(loss3[2]) - float(Z[name + "_ssim"])) < 2e-6
+        t64 = loss_oracle.photometric_loss_with_grad(img, gt, 0.2, dtype=torch.float64)[3].numpy()
+        assert util.rel_err(grad.cpu().numpy(), Z[name + "_grad"]) < 1e-4, name
+        assert util.rel_err(grad.cpu().numpy(), t64) < 1e-4, name
+    x = torch.from_numpy(Z["a_37x53_img"]).to(d).requires_grad_(True)
+    loss = losses.photometric_loss(x, torch.from_numpy(Z["a_37x53_gt"]).to(d), 0.2)
+    (2.0 * loss).backward()
+    assert util.rel_err(x.grad.cpu().numpy(), 2.0 * Z["a_37x53_grad"]) < 1e-4
