@@ -367,8 +367,20 @@ def cpu_baseline(scene, cam, cot, D, budget_s=12.0, max_steps=3):
 def loss_leg(H, W, dev, iters=20):
     """SURVEY 8f-1 ("next" row): the reference's training loss 0.8*L1 + 0.2*(1-SSIM) forward+backward at the bench
     resolution -- our fused kernels vs the same formula in torch ops (what utils/loss.py runs), same inputs."""
+    import torch.nn.functional as F
     from luciddreamer_b200 import losses
-    from oracle import loss_oracle
+    g1 = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)])
+    g1 = (g1 / g1.sum()).unsqueeze(1)
+    win = (g1 @ g1.t()).expand(3, 1, 11, 11).contiguous().to(dev)
+
+    def torch_ssim(x, y):                      # the formula of utils/loss.py:38-69 in torch ops (baseline only)
+        x4, y4 = x.unsqueeze(0), y.unsqueeze(0)
+        conv = lambda t: F.conv2d(t, win, padding=5, groups=3)
+        mu1, mu2 = conv(x4), conv(y4)
+        s1, s2, s12 = conv(x4 * x4) - mu1 * mu1, conv(y4 * y4) - mu2 * mu2, conv(x4 * y4) - mu1 * mu2
+        C1, C2 = 0.01 ** 2, 0.03 ** 2
+        return (((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2))).mean()
+
     g = torch.Generator().manual_seed(7)
     gt = torch.rand(3, H, W, generator=g).to(dev)
     img = (gt + 0.1 * torch.randn(3, H, W, generator=g).to(dev)).clamp(0, 1)
@@ -378,7 +390,7 @@ def loss_leg(H, W, dev, iters=20):
 
     def torch_ref():
         x = img.clone().requires_grad_(True)
-        l = 0.8 * loss_oracle.l1_loss(x, gt) + 0.2 * (1.0 - loss_oracle.ssim(x, gt))
+        l = 0.8 * (x - gt).abs().mean() + 0.2 * (1.0 - torch_ssim(x, gt))
         l.backward()
         return l, x.grad
 
@@ -396,6 +408,47 @@ def loss_leg(H, W, dev, iters=20):
     a, b = ours(), torch_ref()
     out["rel_err_grad_vs_torch"] = float(((a[1] - b[1]).norm() / b[1].norm()).item())
     out["what"] = "0.8*L1 + 0.2*(1-SSIM) loss + gradient at the bench resolution (luciddreamer.py:301-304)"
+    return out
+
+
+def adam_leg(scene, dev, iters=10):
+    """SURVEY 8f-2 ("next" row): one optimiser step over all parameters of the bench model -- our fused
+    activation-backward + Adam launch vs autograd through the activations + torch.optim.Adam (what the reference runs)."""
+    from luciddreamer_b200 import multiview as MV
+    from luciddreamer_b200 import optim
+    P = scene["means3D"].shape[0]
+    g = torch.Generator().manual_seed(11)
+    raw = dict(xyz=scene["means3D"].clone(), f_dc=scene["shs"][:, :1].contiguous(), f_rest=scene["shs"][:, 1:].contiguous(),
+               opacity=torch.logit(scene["opacities"].clamp(1e-4, 1 - 1e-4)), scaling=torch.log(scene["scales"]),
+               rotation=scene["rotations"].clone())
+    dv = {k: v.to(dev).contiguous() for k, v in raw.items()}
+    bucket = MV.GradBucket(P, 16, dev)
+    bucket.flat.copy_(torch.randn(bucket.flat.numel(), generator=g) * 1e-3)
+    mine = optim.FusedGaussianAdam(dv["xyz"], dv["f_dc"], dv["f_rest"], dv["opacity"], dv["scaling"], dv["rotation"])
+    tp = {k: torch.nn.Parameter(v.clone()) for k, v in dv.items()}
+    opt = torch.optim.Adam([{"params": [tp[k]], "lr": optim.DEFAULT_LRS[k]} for k in tp], lr=0.0, eps=1e-15)
+
+    def torch_step():
+        acts = (tp["xyz"], torch.cat((tp["f_dc"], tp["f_rest"]), dim=1), torch.sigmoid(tp["opacity"]),
+                torch.exp(tp["scaling"]), torch.nn.functional.normalize(tp["rotation"]))
+        opt.zero_grad(set_to_none=True)
+        torch.autograd.backward(acts, [bucket.means3D, bucket.shs, bucket.opacities, bucket.scales, bucket.rotations])
+        opt.step()
+
+    out = {}
+    for name, fn in (("fused_ms", lambda: mine.step(bucket)), ("torch_adam_ms", torch_step)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / iters
+    nbytes = 59 * P * 4 * 7
+    out["fused_GBps"] = nbytes / (out["fused_ms"] * 1e-3) / 1e9
+    out["what"] = "activation chain rule + Adam over all 59 parameters/Gaussian (28 B/parameter of compulsory traffic)"
     return out
 
 
@@ -564,7 +617,7 @@ def main():
 
     if rank == 0 and world == 1 and args.impl == "ours":
         try:
-            line["next_rows"] = {"photometric_loss": loss_leg(H, W, dev)}
+            line["next_rows"] = {"photometric_loss": loss_leg(H, W, dev), "optimizer_step": adam_leg(scene, dev)}
         except Exception as ex:
             line["next_rows"] = {"photometric_loss": {"error": str(ex)[:200]}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -169,6 +169,27 @@ int gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, co
 int gs_l1_loss_backward(GsContext* ctx, const float* color, const uint8_t* target_u8, int32_t H, int32_t W, float weight,
                         float* dL_dcolor, float* loss, gs_stream_t stream);
 
+/* "Next" row: fused optimiser step.  One launch replaces the autograd backward through the parameter
+ * activations of scene/gaussian_model.py:97-117 and torch.optim.Adam(eps=1e-15) over the parameter groups of
+ * gaussian_model.py:156-165.  `grad` is the gradient w.r.t. the ACTIVATED value as written by gs_backward (e.g. a
+ * segment of the flat gradient bucket): the parameter at (row, c) reads grad[row * grad_row_width + grad_offset + c].
+ * activation: 0 none (xyz, SH features), 1 sigmoid (opacity logit), 2 exp (log scale), 3 F.normalize (quaternion rows
+ * of 4; row_width ignored).  param / exp_avg / exp_avg_sq (16-byte aligned) are updated in place; `step` is the 1-based Adam step. */
+typedef struct GsAdamGroup {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t rows;
+    int32_t row_width;
+    int32_t grad_row_width;
+    int32_t grad_offset;
+    int32_t activation;
+    double lr;
+} GsAdamGroup;
+int gs_gaussian_adam_step(GsContext* ctx, const GsAdamGroup* groups, int32_t ngroups, double beta1, double beta2,
+                          double eps, int32_t step, gs_stream_t stream);
+
 /* "Next" row: the reference's full photometric training loss and its gradient, fused:
  *   loss3[0] = (1 - lambda) * l1_loss(image, gt) + lambda * (1 - ssim(image, gt))     (luciddreamer.py:301-303)
  *   loss3[1] = l1_loss (utils/loss.py:18),  loss3[2] = ssim (utils/loss.py:38-69: 11x11 Gaussian window, sigma 1.5,

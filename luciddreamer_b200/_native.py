@@ -33,6 +33,12 @@ class GsGrads(C.Structure):
                 ("peer_multicast", C.c_void_p), ("peer_seg_off", C.POINTER(C.c_int64))]
 
 
+class GsAdamGroup(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("rows", C.c_int64), ("row_width", C.c_int32), ("grad_row_width", C.c_int32),
+                ("grad_offset", C.c_int32), ("activation", C.c_int32), ("lr", C.c_double)]
+
+
 class GsCounts(C.Structure):
     _fields_ = [("num_rendered", C.c_int64), ("num_pairs", C.c_int64), ("num_visible", C.c_int64)]
 
@@ -62,6 +68,8 @@ SYMBOLS = [
     ("gs_mark_visible", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gs_l1_loss_backward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    ("gs_gaussian_adam_step", C.c_int, [C.c_void_p, C.POINTER(GsAdamGroup), C.c_int32, C.c_double, C.c_double, C.c_double,
+                                        C.c_int32, C.c_void_p]),
     ("gs_photometric_scratch_bytes", C.c_size_t, [C.c_int32, C.c_int32]),
     ("gs_photometric_loss_backward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

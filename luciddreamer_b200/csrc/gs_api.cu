@@ -340,6 +340,34 @@ int gs_l1_loss_backward(GsContext* ctx, const float* color, const uint8_t* targe
     return GS_OK;
 }
 
+int gs_gaussian_adam_step(GsContext* ctx, const GsAdamGroup* groups, int32_t ngroups, double beta1, double beta2,
+                          double eps, int32_t step, gs_stream_t stream) {
+    (void)ctx;
+    if (!groups || ngroups <= 0 || ngroups > 8 || step < 1) return fail(GS_EINVAL, "bad optimiser arguments");
+    GsAdamArgs a;
+    a.nseg = ngroups; a.om_beta1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.om_beta2 = (float)(1.0 - beta2);
+    a.eps = (float)eps;
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    for (int k = 0; k < ngroups; k++) {
+        const GsAdamGroup& g = groups[k];
+        if (!g.param || !g.grad || !g.exp_avg || !g.exp_avg_sq || g.rows < 0 || g.activation < 0 || g.activation > 3)
+            return fail(GS_EINVAL, "optimiser group %d is malformed", k);
+        if ((reinterpret_cast<uintptr_t>(g.param) | reinterpret_cast<uintptr_t>(g.exp_avg) |
+             reinterpret_cast<uintptr_t>(g.exp_avg_sq)) & 15)
+            return fail(GS_EINVAL, "optimiser group %d: param / moments must be 16-byte aligned", k);
+        GsAdamSeg& s = a.seg[k];
+        s.type = g.activation; s.row_w = g.activation == 3 ? 4 : g.row_width; s.g_row_w = g.grad_row_width;
+        s.g_off = g.grad_offset; s.rows = g.rows; s.p = g.param; s.g = g.grad; s.m = g.exp_avg; s.v = g.exp_avg_sq;
+        s.step_size = (float)(g.lr / bc1); s.blocks = 0;
+        if (s.row_w <= 0 || s.g_row_w < s.row_w + s.g_off) return fail(GS_EINVAL, "optimiser group %d: bad row widths", k);
+    }
+    if (gs_launch_gaussian_adam(a, (cudaStream_t)stream) != 0) return fail(GS_EINVAL, "optimiser problem too large");
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GS_ECUDA, "adam launch: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
 size_t gs_photometric_scratch_bytes(int32_t H, int32_t W) { return 256 + (size_t)9 * H * W * sizeof(float); }
 
 int gs_photometric_loss_backward(GsContext* ctx, const float* image, const float* gt, int32_t H, int32_t W,

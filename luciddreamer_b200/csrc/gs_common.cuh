@@ -316,4 +316,19 @@ void gs_launch_l1_loss_grad(const float* color, const uint8_t* target, int H, in
                             float* loss, int num_sms, cudaStream_t s);
 void gs_launch_photometric(const float* img, const float* gt, int H, int W, float lambda_dssim, void* scratch,
                            float* dL_dimg, float* loss3, cudaStream_t s);
+struct GsAdamSeg {
+    int type;            // 0 identity, 1 sigmoid (opacity logit), 2 exp (log scale), 3 normalised quaternion rows
+    int row_w;           // parameter row width (ignored for type 3: 4)
+    int g_row_w, g_off;  // the gradient of parameter (row, c) sits at g[row * g_row_w + g_off + c]
+    long long rows;
+    float* p; const float* g; float* m; float* v;
+    float step_size;     // lr / (1 - beta1^step)
+    int blocks;
+};
+struct GsAdamArgs {
+    GsAdamSeg seg[8];
+    int nseg;
+    float om_beta1, beta2, om_beta2, eps, bc2_sqrt;
+};
+int gs_launch_gaussian_adam(GsAdamArgs a, cudaStream_t s);
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);

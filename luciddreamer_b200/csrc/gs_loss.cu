@@ -16,12 +16,12 @@ namespace {
 
 constexpr int kWin = 11, kHalo = 5, kTile = 16, kIn = kTile + 2 * kHalo;   // 26
 
-__device__ __forceinline__ void gauss_window(float* w) {                    // utils/loss.py:26-28
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < kWin; i++) { w[i] = expf(-(float)((i - kHalo) * (i - kHalo)) / (2.f * 1.5f * 1.5f)); s += w[i]; }
-#pragma unroll
-    for (int i = 0; i < kWin; i++) w[i] /= s;
+// utils/loss.py:26-28: exp(-(i-5)^2 / (2 * 1.5^2)) in double, stored as float32, normalised in float32 -- the
+// eleven resulting float32 values, so that the window is bit-identical to the reference's and costs no expf here
+__device__ __forceinline__ void gauss_window(float* w) {
+    w[0] = 1.028380124e-03f; w[1] = 7.598758209e-03f; w[2] = 3.600077331e-02f; w[3] = 1.093606874e-01f;
+    w[4] = 2.130055279e-01f; w[5] = 2.660117149e-01f; w[6] = 2.130055279e-01f; w[7] = 1.093606874e-01f;
+    w[8] = 3.600077331e-02f; w[9] = 7.598758209e-03f; w[10] = 1.028380124e-03f;
 }
 
 __global__ void __launch_bounds__(kTile * kTile)

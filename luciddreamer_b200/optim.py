@@ -1,0 +1,70 @@
+"""Fused optimiser step for the Gaussian parameters.
+
+`FusedGaussianAdam` holds the six raw parameter tensors of scene/gaussian_model.py (xyz, features_dc, features_rest,
+opacity logit, log scaling, raw rotation) like `GaussianModel.training_setup` registers them with torch.optim.Adam
+(gaussian_model.py:151-169), and consumes the rasterizer's gradients w.r.t. the ACTIVATED values -- a
+`multiview.GradBucket` (or any object with .means3D/.shs/.opacities/.scales/.rotations) -- in ONE kernel launch:
+activation chain rule (sigmoid, exp, F.normalize, cat) + Adam, in place.  No autograd graph, no per-group Python loop."""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import _native as N
+from . import rasterizer as R
+
+# arguments.py:19-27 (GSParams) defaults; xyz is scheduled by the caller via set_lr (gaussian_model.py:171-177)
+DEFAULT_LRS = {"xyz": 0.00016, "f_dc": 0.0025, "f_rest": 0.0025 / 20.0, "opacity": 0.05, "scaling": 0.005,
+               "rotation": 0.001}
+
+
+class FusedGaussianAdam:
+    def __init__(self, xyz, features_dc, features_rest, opacity, scaling, rotation, lrs: Dict[str, float] = None,
+                 betas=(0.9, 0.999), eps: float = 1e-15):
+        self.params = {"xyz": xyz, "f_dc": features_dc, "f_rest": features_rest, "opacity": opacity,
+                       "scaling": scaling, "rotation": rotation}
+        for k, t in self.params.items():
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError(f"{k}: parameters must be contiguous float32 CUDA tensors (no CPU fallback)")
+        self.lrs = dict(DEFAULT_LRS)
+        if lrs:
+            self.lrs.update(lrs)
+        self.betas, self.eps, self.step_count = betas, eps, 0
+        self.exp_avg = {k: torch.zeros_like(t) for k, t in self.params.items()}
+        self.exp_avg_sq = {k: torch.zeros_like(t) for k, t in self.params.items()}
+        self.P = xyz.shape[0]
+        self.M = 1 + features_rest.shape[1]
+
+    def set_lr(self, name: str, lr: float) -> None:
+        self.lrs[name] = float(lr)
+
+    @torch.no_grad()
+    def step(self, grads) -> None:
+        """grads: gradients w.r.t. the activated values (means3D [P,3], shs [P,M,3], opacities [P,1], scales [P,3],
+        rotations [P,4]) -- e.g. the GradBucket the backward wrote."""
+        P, M = self.P, self.M
+        groups = (N.GsAdamGroup * 6)()
+        spec = [  # name, grad tensor, rows, row_width, grad_row_width, grad_offset, activation
+            ("xyz", grads.means3D, P, 3, 3, 0, 0),
+            ("f_dc", grads.shs, P, 3, 3 * M, 0, 0),
+            ("f_rest", grads.shs, P, 3 * (M - 1), 3 * M, 3, 0),
+            ("opacity", grads.opacities, P, 1, 1, 0, 1),
+            ("scaling", grads.scales, P, 3, 3, 0, 2),
+            ("rotation", grads.rotations, P, 4, 4, 0, 3),
+        ]
+        dev = self.params["xyz"].device
+        for k, (name, gt, rows, rw, grw, goff, act) in enumerate(spec):
+            if not (gt.is_cuda and gt.dtype == torch.float32 and gt.is_contiguous() and gt.device == dev):
+                raise RuntimeError(f"gradient for {name} must be a contiguous float32 tensor on {dev}")
+            gr = groups[k]
+            gr.param, gr.grad = self.params[name].data_ptr(), gt.data_ptr()
+            gr.exp_avg, gr.exp_avg_sq = self.exp_avg[name].data_ptr(), self.exp_avg_sq[name].data_ptr()
+            gr.rows, gr.row_width, gr.grad_row_width, gr.grad_offset, gr.activation = rows, rw, grw, goff, act
+            gr.lr = float(self.lrs[name])
+        self.step_count += 1
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(idx):
+            N.check(N.lib().gs_gaussian_adam_step(R._ctx(idx), groups, 6, float(self.betas[0]), float(self.betas[1]),
+                                                  float(self.eps), self.step_count,
+                                                  torch.cuda.current_stream(idx).cuda_stream))

@@ -408,3 +408,41 @@ def test_fused_photometric_loss_matches_reference_golden_and_oracle():
     loss = losses.photometric_loss(x, torch.from_numpy(Z["a_37x53_gt"]).to(d), 0.2)
     (2.0 * loss).backward()
     assert util.rel_err(x.grad.cpu().numpy(), 2.0 * Z["a_37x53_grad"]) < 1e-4
+
+
+def test_fused_gaussian_adam_matches_torch_adam_through_activations():
+    """One launch == autograd through sigmoid/exp/normalize/cat + torch.optim.Adam(eps=1e-15) over the six groups
+    (scene/gaussian_model.py:97-117,156-165), for several steps, reading a flat GradBucket."""
+    from luciddreamer_b200 import multiview as MV
+    from luciddreamer_b200 import optim
+    from oracle import optim_oracle
+    d = dev()
+    P = 3001                                   # not a multiple of 4 / 32
+    g = torch.Generator().manual_seed(9)
+    raw = dict(xyz=torch.randn(P, 3, generator=g), f_dc=torch.randn(P, 1, 3, generator=g),
+               f_rest=torch.randn(P, 15, 3, generator=g) * 0.1, opacity=torch.randn(P, 1, generator=g),
+               scaling=torch.randn(P, 3, generator=g) - 2, rotation=torch.randn(P, 4, generator=g))
+    lrs = dict(optim.DEFAULT_LRS)
+    ref = optim_oracle.ReferenceStepper(raw["xyz"], raw["f_dc"], raw["f_rest"], raw["opacity"], raw["scaling"],
+                                        raw["rotation"], lrs, dtype=torch.float64)
+    dv = {k: v.to(d).contiguous() for k, v in raw.items()}
+    mine = optim.FusedGaussianAdam(dv["xyz"], dv["f_dc"], dv["f_rest"], dv["opacity"], dv["scaling"], dv["rotation"], lrs)
+    bucket = MV.GradBucket(P, 16, d)
+    for step in range(4):
+        grads = [torch.randn(P, 3, generator=g), torch.randn(P, 16, 3, generator=g), torch.randn(P, 1, generator=g),
+                 torch.randn(P, 3, generator=g), torch.randn(P, 4, generator=g)]
+        if step == 2:
+            grads = [t * (torch.rand(P, *([1] * (t.dim() - 1)), generator=g) < 0.05) for t in grads]   # mostly-zero rows
+        for dst, src in zip((bucket.means3D, bucket.shs, bucket.opacities, bucket.scales, bucket.rotations), grads):
+            dst.copy_(src)
+        if step == 1:
+            lrs["xyz"] = 0.5 * lrs["xyz"]
+            mine.set_lr("xyz", lrs["xyz"]); ref.opt.param_groups[0]["lr"] = lrs["xyz"]
+        mine.step(bucket)
+        ref.step(*grads)
+    torch.cuda.synchronize()
+    for name in ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"):
+        p, m, v = ref.state(name)
+        assert util.rel_err(mine.params[name].cpu().numpy(), p.numpy()) < 1e-5, name
+        assert util.rel_err(mine.exp_avg[name].cpu().numpy(), m.numpy()) < 1e-5, name
+        assert util.rel_err(mine.exp_avg_sq[name].cpu().numpy(), v.numpy()) < 1e-5, name
