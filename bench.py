@@ -271,7 +271,7 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
     step uploads that step's inputs from pinned host memory -- the camera (viewmatrix, projmatrix, campos: 35 floats)
     and the uint8 target image [H,W,3] -- computes the L1 photometric loss and its gradient on the device, runs
     forward+backward through the operator API, and reads the scalar loss back.  Target uploads of step k+1 overlap the
-    compute of step k on a copy stream (double buffered); everything is inside the timed region.
+    backward of step k on a copy stream (double buffered); everything is inside the timed region.
     fused_loss: our fused L1 kernel (luciddreamer_b200.losses); the reference arm uses plain torch ops."""
     dev = impl.dev
     H, W = cam.image_height, cam.image_width
@@ -300,12 +300,10 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
         upload(base)
         for k in range(base, base + n):
             b = k & 1
-            d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream, before the next big
-            impl.set_camera(d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35])   # upload occupies the
-            main.wait_event(ev_up[b])                             # H2D copy engine
+            d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream
+            impl.set_camera(d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35])
+            main.wait_event(ev_up[b])
             color = impl.forward()
-            if k + 1 < base + n:
-                upload(k + 1)
             if fused_loss:
                 loss, cot = losses.l1_loss_with_grad(color, d_tgt[b])
             else:
@@ -315,6 +313,8 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
             impl.backward(color, cot)
             h_loss[k].copy_(loss.reshape(()), non_blocking=True)
             ev_free[b].record(main)
+            if k + 1 < base + n:                                  # next target: in flight during this step's backward;
+                upload(k + 1)                                     # issued last so the host reaches backward() early
 
     for b in range(2):
         ev_free[b].record(main)

@@ -190,6 +190,12 @@ typedef struct GsAdamGroup {
 int gs_gaussian_adam_step(GsContext* ctx, const GsAdamGroup* groups, int32_t ngroups, double beta1, double beta2,
                           double eps, int32_t step, gs_stream_t stream);
 
+/* Densification statistics of one view (luciddreamer.py:308-312, scene/gaussian_model.py:405-407), one pass: for every
+ * Gaussian with radii > 0:  max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum += ||dL_dmeans2D[:, :2]||;
+ * denom += 1.  radii: [P] int32; dL_dmeans2D: [P,3]; the three accumulators: [P] f32 (in place). */
+int gs_densify_stats(GsContext* ctx, int32_t P, const int32_t* radii, const float* dL_dmeans2D, float* xyz_gradient_accum,
+                     float* denom, float* max_radii2D, gs_stream_t stream);
+
 /* "Next" row: the reference's full photometric training loss and its gradient, fused:
  *   loss3[0] = (1 - lambda) * l1_loss(image, gt) + lambda * (1 - ssim(image, gt))     (luciddreamer.py:301-303)
  *   loss3[1] = l1_loss (utils/loss.py:18),  loss3[2] = ssim (utils/loss.py:38-69: 11x11 Gaussian window, sigma 1.5,

@@ -368,6 +368,17 @@ int gs_gaussian_adam_step(GsContext* ctx, const GsAdamGroup* groups, int32_t ngr
     return GS_OK;
 }
 
+int gs_densify_stats(GsContext* ctx, int32_t P, const int32_t* radii, const float* dL_dmeans2D, float* xyz_gradient_accum,
+                     float* denom, float* max_radii2D, gs_stream_t stream) {
+    (void)ctx;
+    if (P < 0 || (P > 0 && (!radii || !dL_dmeans2D || !xyz_gradient_accum || !denom || !max_radii2D)))
+        return fail(GS_EINVAL, "bad argument");
+    gs_launch_densify_stats(P, radii, dL_dmeans2D, xyz_gradient_accum, denom, max_radii2D, (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GS_ECUDA, "densify stats launch: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
 size_t gs_photometric_scratch_bytes(int32_t H, int32_t W) { return 256 + (size_t)9 * H * W * sizeof(float); }
 
 int gs_photometric_loss_backward(GsContext* ctx, const float* image, const float* gt, int32_t H, int32_t W,

@@ -102,7 +102,27 @@ k_gaussian_adam(const GsAdamArgs a) {
     }
 }
 
+// luciddreamer.py:308-312 + scene/gaussian_model.py:405-407 in one pass: for every visible Gaussian (radii > 0)
+//   max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum += |dL_dmeans2D.xy|;  denom += 1
+__global__ void __launch_bounds__(kT)
+k_densify_stats(const int P, const int* __restrict__ radii, const float* __restrict__ dm2, float* __restrict__ accum,
+                float* __restrict__ denom, float* __restrict__ max_radii) {
+    const int i = blockIdx.x * kT + threadIdx.x;
+    if (i >= P) return;
+    const int r = radii[i];
+    if (r <= 0) return;
+    const float gx = dm2[3 * (size_t)i], gy = dm2[3 * (size_t)i + 1];
+    max_radii[i] = fmaxf(max_radii[i], (float)r);
+    accum[i] += sqrtf(gx * gx + gy * gy);
+    denom[i] += 1.f;
+}
+
 }  // namespace
+
+void gs_launch_densify_stats(int P, const int* radii, const float* dm2, float* accum, float* denom, float* max_radii,
+                             cudaStream_t s) {
+    if (P > 0) k_densify_stats<<<(P + kT - 1) / kT, kT, 0, s>>>(P, radii, dm2, accum, denom, max_radii);
+}
 
 int gs_launch_gaussian_adam(GsAdamArgs a, cudaStream_t s) {
     long long total = 0;

@@ -109,6 +109,18 @@ class DensifyStats:
         self.max_radii2D = torch.zeros(P, device=device)
 
     def add_view(self, dL_dmeans2D: torch.Tensor, radii: torch.Tensor) -> None:
+        if dL_dmeans2D.is_cuda:               # one fused pass on the GPU (gs_densify_stats); torch ops only for CPU tests
+            from . import _native as N
+            from . import rasterizer as R
+            if not (dL_dmeans2D.is_contiguous() and radii.is_contiguous() and radii.dtype == torch.int32
+                    and dL_dmeans2D.dtype == torch.float32 and dL_dmeans2D.shape[-1] == 3):
+                raise RuntimeError("add_view: expects contiguous dL_dmeans2D [P,3] f32 and radii [P] int32")
+            idx = dL_dmeans2D.device.index
+            with torch.cuda.device(idx):
+                N.check(N.lib().gs_densify_stats(R._ctx(idx), radii.numel(), radii.data_ptr(), dL_dmeans2D.data_ptr(),
+                                                 self.xyz_gradient_accum.data_ptr(), self.denom.data_ptr(),
+                                                 self.max_radii2D.data_ptr(), torch.cuda.current_stream(idx).cuda_stream))
+            return
         vis = radii > 0
         self.max_radii2D[vis] = torch.max(self.max_radii2D[vis], radii[vis].to(self.max_radii2D.dtype))
         self.xyz_gradient_accum[vis] += torch.norm(dL_dmeans2D[vis, :2], dim=-1, keepdim=True)

@@ -7,6 +7,7 @@ opacity logit, log scaling, raw rotation) like `GaussianModel.training_setup` re
 activation chain rule (sigmoid, exp, F.normalize, cat) + Adam, in place.  No autograd graph, no per-group Python loop."""
 from __future__ import annotations
 
+import math
 from typing import Dict
 
 import torch
@@ -17,6 +18,19 @@ from . import rasterizer as R
 # arguments.py:19-27 (GSParams) defaults; xyz is scheduled by the caller via set_lr (gaussian_model.py:171-177)
 DEFAULT_LRS = {"xyz": 0.00016, "f_dc": 0.0025, "f_rest": 0.0025 / 20.0, "opacity": 0.05, "scaling": 0.005,
                "rotation": 0.001}
+
+
+def expon_lr(step: int, lr_init: float, lr_final: float, lr_delay_steps: int = 0, lr_delay_mult: float = 1.0,
+             max_steps: int = 1000000) -> float:
+    """The xyz learning-rate schedule (utils/general.py:31-64): log-linear interpolation lr_init -> lr_final over
+    max_steps, optionally eased in by a sine ramp from lr_delay_mult over lr_delay_steps; 0 disables the group."""
+    if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+        return 0.0
+    delay = 1.0
+    if lr_delay_steps > 0:
+        delay = lr_delay_mult + (1.0 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+    t = min(max(step / max_steps, 0.0), 1.0)
+    return delay * math.exp(math.log(lr_init) * (1.0 - t) + math.log(lr_final) * t)
 
 
 class FusedGaussianAdam:
@@ -31,6 +45,7 @@ class FusedGaussianAdam:
         if lrs:
             self.lrs.update(lrs)
         self.betas, self.eps, self.step_count = betas, eps, 0
+        self._sched = (DEFAULT_LRS["xyz"], 0.0000016, 0, 0.01, 2990)
         self.exp_avg = {k: torch.zeros_like(t) for k, t in self.params.items()}
         self.exp_avg_sq = {k: torch.zeros_like(t) for k, t in self.params.items()}
         self.P = xyz.shape[0]
@@ -38,6 +53,17 @@ class FusedGaussianAdam:
 
     def set_lr(self, name: str, lr: float) -> None:
         self.lrs[name] = float(lr)
+
+    def set_xyz_schedule(self, lr_init: float, lr_final: float, lr_delay_mult: float = 0.01, max_steps: int = 2990,
+                         spatial_lr_scale: float = 1.0) -> None:
+        """GaussianModel.training_setup's xyz scheduler (gaussian_model.py:166-169; defaults arguments.py:20-23)."""
+        self._sched = (lr_init * spatial_lr_scale, lr_final * spatial_lr_scale, 0, lr_delay_mult, max_steps)
+
+    def update_learning_rate(self, iteration: int) -> float:
+        """GaussianModel.update_learning_rate (gaussian_model.py:171-177): host arithmetic, no launch."""
+        lr = expon_lr(iteration, *self._sched)
+        self.lrs["xyz"] = lr
+        return lr
 
     @torch.no_grad()
     def step(self, grads) -> None:

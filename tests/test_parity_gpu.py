@@ -331,7 +331,7 @@ def test_shared_model_step_sums_reference_gradients():
     MV.multi_view_step(sc, [s for _, s in views], cots, bucket, stats=stats)
     rc = ref_cuda.RefContext()
     acc = {k: 0 for k in ("m3", "sh", "op", "sc", "rot")}
-    norm_acc = torch.zeros(P, 1, device=d); denom = torch.zeros(P, 1, device=d)
+    norm_acc = torch.zeros(P, 1, device=d); denom = torch.zeros(P, 1, device=d); max_r = torch.zeros(P, device=d)
     for (cam, rs), cot in zip(views, cots):
         R, rcol, rdep, rrad = ref_cuda.rasterize_gaussians(rc, rs.bg, sc["means3D"], None, sc["opacities"], sc["scales"],
                                                            sc["rotations"], 1.0, None, rs.viewmatrix, rs.projmatrix,
@@ -341,11 +341,13 @@ def test_shared_model_step_sums_reference_gradients():
         acc["sc"] = acc["sc"] + g[6]; acc["rot"] = acc["rot"] + g[7]
         vis = rrad > 0
         norm_acc[vis] += torch.norm(g[0][vis, :2], dim=-1, keepdim=True); denom[vis] += 1
+        max_r[vis] = torch.max(max_r[vis], rrad[vis])          # luciddreamer.py:309-310
     torch.cuda.synchronize()
     for name, mine in (("m3", bucket.means3D), ("sh", bucket.shs), ("op", bucket.opacities), ("sc", bucket.scales),
                        ("rot", bucket.rotations)):
         assert util.rel_err(mine.cpu().numpy(), acc[name].cpu().numpy()) < util.GRAD_REL_TOL, name
     assert torch.equal(stats.denom, denom)
+    assert torch.equal(stats.max_radii2D, max_r)
     assert util.rel_err(stats.xyz_gradient_accum.cpu().numpy(), norm_acc.cpu().numpy()) < util.GRAD_REL_TOL
 
 
