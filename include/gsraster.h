@@ -190,6 +190,13 @@ typedef struct GsAdamGroup {
 int gs_gaussian_adam_step(GsContext* ctx, const GsAdamGroup* groups, int32_t ngroups, double beta1, double beta2,
                           double eps, int32_t step, gs_stream_t stream);
 
+/* "Next" row: simple_knn.distCUDA2 (submodules/simple-knn/spatial.cu:15-26 over SimpleKNN::knn,
+ * simple_knn.cu:185-221): mean_dist2[i] = mean of the squared distances from point i to its 3 nearest other points
+ * (exact search; bit-identical to the reference, incl. duplicates and P < 4).  points: [P,3] f32 device;
+ * scratch: gs_knn_scratch_bytes(P) bytes, 256-byte aligned; mean_dist2: [P] f32 device. */
+size_t gs_knn_scratch_bytes(int32_t P);
+int gs_knn_mean_dist2(GsContext* ctx, int32_t P, const float* points, void* scratch, float* mean_dist2, gs_stream_t stream);
+
 /* Densification statistics of one view (luciddreamer.py:308-312, scene/gaussian_model.py:405-407), one pass: for every
  * Gaussian with radii > 0:  max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum += ||dL_dmeans2D[:, :2]||;
  * denom += 1.  radii: [P] int32; dL_dmeans2D: [P,3]; the three accumulators: [P] f32 (in place). */

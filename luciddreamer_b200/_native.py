@@ -68,6 +68,8 @@ SYMBOLS = [
     ("gs_mark_visible", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gs_l1_loss_backward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    ("gs_knn_scratch_bytes", C.c_size_t, [C.c_int32]),
+    ("gs_knn_mean_dist2", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gs_densify_stats", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     ("gs_gaussian_adam_step", C.c_int, [C.c_void_p, C.POINTER(GsAdamGroup), C.c_int32, C.c_double, C.c_double, C.c_double,

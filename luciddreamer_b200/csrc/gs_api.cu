@@ -368,6 +368,18 @@ int gs_gaussian_adam_step(GsContext* ctx, const GsAdamGroup* groups, int32_t ngr
     return GS_OK;
 }
 
+size_t gs_knn_scratch_bytes(int32_t P) { return P > 0 ? gs_knn_scratch_bytes_impl(P) : 256; }
+
+int gs_knn_mean_dist2(GsContext* ctx, int32_t P, const float* points, void* scratch, float* mean_dist2, gs_stream_t stream) {
+    (void)ctx;
+    if (P < 0 || (P > 0 && (!points || !scratch || !mean_dist2))) return fail(GS_EINVAL, "bad argument");
+    const int rc = gs_launch_knn(P, points, scratch, mean_dist2, (cudaStream_t)stream);
+    if (rc == -1) return fail(GS_EINVAL, "knn: radix-sort temporary storage exceeds the scratch allowance");
+    cudaError_t e = cudaPeekAtLastError();
+    if (rc != 0 || e != cudaSuccess) return fail(GS_ECUDA, "knn launch: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
 int gs_densify_stats(GsContext* ctx, int32_t P, const int32_t* radii, const float* dL_dmeans2D, float* xyz_gradient_accum,
                      float* denom, float* max_radii2D, gs_stream_t stream) {
     (void)ctx;

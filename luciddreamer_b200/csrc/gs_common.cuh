@@ -331,6 +331,8 @@ struct GsAdamArgs {
     float om_beta1, beta2, om_beta2, eps, bc2_sqrt;
 };
 int gs_launch_gaussian_adam(GsAdamArgs a, cudaStream_t s);
+size_t gs_knn_scratch_bytes_impl(int P);
+int gs_launch_knn(int P, const float* points, void* scratch, float* out, cudaStream_t s);
 void gs_launch_densify_stats(int P, const int* radii, const float* dm2, float* accum, float* denom, float* max_radii,
                              cudaStream_t s);
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);

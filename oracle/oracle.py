@@ -23,7 +23,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile oracle/gs_oracle.c -> oracle/liboracle.so (gcc, OpenMP, no FMA contraction)."""
-    src = [os.path.join(_HERE, "gs_oracle.c"), os.path.join(_HERE, "gs_oracle_impl.h")]
+    src = [os.path.join(_HERE, "gs_oracle.c"), os.path.join(_HERE, "gs_oracle_impl.h"), os.path.join(_HERE, "knn_oracle.c")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src if os.path.exists(s))):
         return _LIB_PATH

@@ -100,3 +100,29 @@ def rasterize_gaussians_backward(ctx: RefContext, radii, dL_dout_color, debug=Fa
                        dconic.data_ptr(), dop.data_ptr(), dcol.data_ptr(), dm3.data_ptr(), dcov.data_ptr(),
                        dsh.data_ptr() if M > 0 else None, dsc.data_ptr(), drot.data_ptr(), int(debug))
     return dm2, dcol, dop, dm3, dcov, dsh, dsc, drot, dconic
+
+
+# ---------------------------------------------------------------- simple_knn (the reference's second native extension)
+KNN_LIB_PATH = os.path.join(_HERE, "_ref", "libref_simpleknn.so")
+_knn = None
+
+
+def knn_available() -> bool:
+    return os.path.exists(KNN_LIB_PATH)
+
+
+def distCUDA2(points: torch.Tensor) -> torch.Tensor:
+    """The reference's distCUDA2 (spatial.cu:15-26): torch.full({P}, 0) then SimpleKNN::knn."""
+    global _knn
+    if _knn is None:
+        _knn = C.CDLL(KNN_LIB_PATH)
+        _knn.ref_knn.restype = C.c_int
+        _knn.ref_knn.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    pts = points.contiguous().float()
+    out = torch.zeros(pts.shape[0], device=pts.device)
+    with torch.cuda.device(pts.device):
+        torch.cuda.synchronize()
+        rc = _knn.ref_knn(pts.shape[0], pts.data_ptr(), out.data_ptr())
+    if rc != 0:
+        raise RuntimeError(f"reference simple_knn failed: cuda error {rc}")
+    return out
