@@ -190,6 +190,16 @@ typedef struct GsAdamGroup {
 int gs_gaussian_adam_step(GsContext* ctx, const GsAdamGroup* groups, int32_t ngroups, double beta1, double beta2,
                           double eps, int32_t step, gs_stream_t stream);
 
+/* "Next" row: per-frame host work of render_video (luciddreamer.py:250-262) moved to the device.
+ *   rgb8[y][x][c]  = uint8(round_half_even(clip(color[c][y][x], 0, 1) * 255))           (:254-255)
+ *   neg_depth[y][x] = -(depth[y][x] * (depth[y][x] > 0))                                 (:256)
+ *   minmax_state   = running {min, max} of neg_depth over all frames packed so far       (:257-262); two uint32 the
+ *                    caller initialises to {0xffffffff, 0}; gs_minmax_read decodes them to two floats (device).
+ * color: [3,H,W] f32; depth: [1,H,W] f32 or NULL (colour only); rgb8: [H,W,3] u8; neg_depth: [H,W] f32. */
+int gs_pack_frame(GsContext* ctx, int32_t H, int32_t W, const float* color, const float* depth, uint8_t* rgb8,
+                  float* neg_depth, uint32_t* minmax_state, gs_stream_t stream);
+int gs_minmax_read(GsContext* ctx, uint32_t* minmax_state, float* minmax2, gs_stream_t stream);
+
 /* "Next" row: simple_knn.distCUDA2 (submodules/simple-knn/spatial.cu:15-26 over SimpleKNN::knn,
  * simple_knn.cu:185-221): mean_dist2[i] = mean of the squared distances from point i to its 3 nearest other points
  * (exact search; bit-identical to the reference, incl. duplicates and P < 4).  points: [P,3] f32 device;

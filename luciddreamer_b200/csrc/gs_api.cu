@@ -368,6 +368,27 @@ int gs_gaussian_adam_step(GsContext* ctx, const GsAdamGroup* groups, int32_t ngr
     return GS_OK;
 }
 
+int gs_pack_frame(GsContext* ctx, int32_t H, int32_t W, const float* color, const float* depth, uint8_t* rgb8,
+                  float* neg_depth, uint32_t* minmax_state, gs_stream_t stream) {
+    (void)ctx;
+    if (H < 0 || W < 0 || (H * (int64_t)W > 0 && (!color || !rgb8 || (depth && !neg_depth))))
+        return fail(GS_EINVAL, "bad argument");
+    if ((int64_t)H * W > 0x7fffffffLL / 4) return fail(GS_EINVAL, "image too large");
+    gs_launch_pack_frame(H * W, color, depth, rgb8, neg_depth, minmax_state, (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GS_ECUDA, "pack frame launch: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
+int gs_minmax_read(GsContext* ctx, uint32_t* minmax_state, float* minmax2, gs_stream_t stream) {
+    (void)ctx;
+    if (!minmax_state || !minmax2) return fail(GS_EINVAL, "NULL argument");
+    gs_launch_minmax_decode(minmax_state, minmax2, (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GS_ECUDA, "minmax decode launch: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
 size_t gs_knn_scratch_bytes(int32_t P) { return P > 0 ? gs_knn_scratch_bytes_impl(P) : 256; }
 
 int gs_knn_mean_dist2(GsContext* ctx, int32_t P, const float* points, void* scratch, float* mean_dist2, gs_stream_t stream) {

@@ -3,6 +3,8 @@ operator API / `_C` surface (which sits directly on the C ABI), against
   (1) the golden vectors of the reference CUDA rasterizer,   (2) the CPU oracle on the same seeded inputs,
   (3) the reference CUDA library itself when oracle/_ref travelled with the repo,
 plus size-independent properties at the full BASELINE config-3 size."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -506,3 +508,60 @@ def test_dist_cuda2_full_size_vs_live_reference_and_kdtree():
         assert torch.equal(got, ref_cuda.distCUDA2(t))
     want = knn_oracle.dist2_kdtree(pts)
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-3, atol=1e-12)
+
+
+@pytest.mark.parametrize("H,W", [(72, 128), (70, 101), (1, 3)])
+def test_pack_frame_matches_reference_numpy_expressions(H, W):
+    """gs_pack_frame vs the per-frame host code of render_video (luciddreamer.py:254-262), bit for bit: np.round
+    half-to-even after clip, -(depth * (depth > 0)) incl. the sign of zero, running min/max over frames."""
+    from luciddreamer_b200 import _native as N, rasterizer as R, video
+    d = dev()
+    g = torch.Generator().manual_seed(H * W)
+    F = 3
+    rgb8 = torch.empty(F, H, W, 3, dtype=torch.uint8, device=d)
+    negd = torch.empty(F, H, W, device=d)
+    state = torch.tensor([-1, 0], dtype=torch.int32, device=d)
+    dmin, dmax = 1e8, -1e8
+    for k in range(F):
+        color = torch.rand(3, H, W, generator=g) * 1.4 - 0.2
+        color.view(-1)[:: 7] = (torch.arange(color.numel())[:: 7] % 256 + 0.5) / 255.0          # exact .5 ties
+        depth = torch.randn(1, H, W, generator=g) * 3
+        depth.view(-1)[:: 5] = 0.0
+        video.pack_frame(color.to(d), depth.to(d), rgb8[k], negd[k], state)
+        want8 = np.round(color.permute(1, 2, 0).numpy().clip(0, 1) * 255.).astype(np.uint8)
+        wantd = -(depth * (depth > 0)).numpy()
+        dmin, dmax = min(dmin, wantd.min().item()), max(dmax, wantd.max().item())
+        np.testing.assert_array_equal(rgb8[k].cpu().numpy(), want8)
+        got = negd[k].cpu().numpy()
+        np.testing.assert_array_equal(got, wantd[0])
+        np.testing.assert_array_equal(np.signbit(got), np.signbit(wantd[0]))
+    mm = torch.empty(2, device=d)
+    N.check(N.lib().gs_minmax_read(R._ctx(d.index), state.data_ptr(), mm.data_ptr(), torch.cuda.current_stream(d).cuda_stream))
+    assert (float(mm[0]), float(mm[1])) == (dmin, dmax)
+
+
+def test_render_video_frames_equals_per_frame_loop():
+    """The batched clip (one host copy) holds exactly what the reference's per-frame loop would have produced from the
+    same renders; views are sharded round-robin (rank r of 2 gets frames r, r+2, ...)."""
+    from luciddreamer_b200 import synthetic as syn, video
+    from luciddreamer_b200.rasterizer import GaussianRasterizer
+    d = dev()
+    P, W, H = 20_000, 160, 90
+    sc = {k: v.to(d) for k, v in syn.make_scene(P, 77, scale_mult=2.0).items()}
+    views = _rot_views(5, W, H, d)
+    settings = [s for _, s in views]
+    frames, depths, dmin, dmax, idx = video.render_video_frames(sc, settings)
+    assert frames.shape == (5, H, W, 3) and depths.shape == (5, H, W) and idx == [0, 1, 2, 3, 4]
+    lo, hi = 1e8, -1e8
+    for k, rs in enumerate(settings):
+        with torch.no_grad():
+            color, _r, depth = GaussianRasterizer(rs)(sc["means3D"], torch.empty(0), sc["opacities"], shs=sc["shs"],
+                                                      scales=sc["scales"], rotations=sc["rotations"])
+        np.testing.assert_array_equal(frames[k], np.round(color.permute(1, 2, 0).cpu().numpy().clip(0, 1) * 255.).astype(np.uint8))
+        wd = -(depth * (depth > 0)).cpu().numpy()
+        np.testing.assert_array_equal(depths[k], wd[0])
+        lo, hi = min(lo, wd.min().item()), max(hi, wd.max().item())
+    assert (dmin, dmax) == (lo, hi)
+    f1, _d1, _a, _b, idx1 = video.render_video_frames(sc, settings, rank=1, world=2, with_depth=False)
+    assert idx1 == [1, 3] and _d1 is None
+    np.testing.assert_array_equal(f1, frames[[1, 3]])
