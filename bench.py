@@ -452,6 +452,29 @@ def adam_leg(scene, dev, iters=10):
     return out
 
 
+def _tool(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def knn_leg():
+    """simple_knn.distCUDA2 over 1 M points (depth-map shaped cloud), ours vs the reference's own kernels."""
+    out = _tool("knn_bench").run(1_000_000, which=("depthmap",))["depthmap"]
+    out["what"] = "mean squared distance to the 3 nearest neighbours, 1 M points; reference = simple_knn.cu compiled unmodified"
+    return out
+
+
+def video_leg():
+    """forward-only clip at the bench resolution, device-side packing + one host copy vs the reference
+    rasterizer inside the per-frame loop of luciddreamer.py:250-262."""
+    out = _tool("video_bench").run(16)
+    out["what"] = "rotate360 clip, uint8 frames + masked depth + dmin/dmax delivered to host memory"
+    return out
+
+
 def shared_model_leg(scene, cam, cot, dev, D, steps, warmup, world):
     """Config-5 style step on every rank: forward+backward of its view, then the ONE exchange of the path -- the sum
     of the per-Gaussian gradients over all views.  Two implementations are timed:
@@ -616,10 +639,14 @@ def main():
             line["shared_model_step"] = shared_model_leg(scene, cam, cot, dev, D, args.steps, args.warmup, world)
 
     if rank == 0 and world == 1 and args.impl == "ours":
-        try:
-            line["next_rows"] = {"photometric_loss": loss_leg(H, W, dev), "optimizer_step": adam_leg(scene, dev)}
-        except Exception as ex:
-            line["next_rows"] = {"photometric_loss": {"error": str(ex)[:200]}}
+        nr = {}
+        for name, fn in (("photometric_loss", lambda: loss_leg(H, W, dev)), ("optimizer_step", lambda: adam_leg(scene, dev)),
+                         ("dist_cuda2", knn_leg), ("video_render", video_leg)):
+            try:
+                nr[name] = fn()
+            except Exception as ex:                      # a "next" row must never take the headline line down
+                nr[name] = {"error": str(ex)[:200]}
+        line["next_rows"] = nr
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(scene, cam, cot_cpu, D)
     if rank == 0:

@@ -12,31 +12,38 @@ import torch
 from luciddreamer_b200.simple_knn import distCUDA2
 from oracle import ref_cuda
 
-P = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-side = int(round(P ** 0.5))
-rng = np.random.default_rng(11)
-u, v = np.meshgrid(np.linspace(-1, 1, side), np.linspace(-0.6, 0.6, side))
-z = 2.0 + 0.5 * np.sin(3 * u) * np.cos(2 * v) + 0.002 * rng.normal(size=u.shape)
-clouds = {"depthmap": np.stack([u * z, v * z, z], -1).reshape(-1, 3).astype(np.float32),
-          "uniform": rng.uniform(-1, 1, size=(side * side, 3)).astype(np.float32)}
-out = {}
-for name, pts in clouds.items():
-    t = torch.from_numpy(pts).cuda()
-    res = {}
-    for impl, fn in (("ours", distCUDA2), ("reference", ref_cuda.distCUDA2 if ref_cuda.knn_available() else None)):
-        if fn is None:
-            continue
-        fn(t); torch.cuda.synchronize()
-        n = 5 if impl == "ours" else 2
-        t0 = time.perf_counter()
-        for _ in range(n):
-            r = fn(t)
-        torch.cuda.synchronize()
-        res[impl + "_ms"] = (time.perf_counter() - t0) / n * 1e3
-        res[impl] = r
-    if "reference" in res:
-        res["bit_identical"] = bool(torch.equal(res.pop("ours"), res.pop("reference")))
-    else:
-        res.pop("ours")
-    out[name] = dict(P=len(pts), **res)
-print(json.dumps(out))
+
+
+def run(P=1_000_000, which=("depthmap", "uniform")):
+    side = int(round(P ** 0.5))
+    rng = np.random.default_rng(11)
+    u, v = np.meshgrid(np.linspace(-1, 1, side), np.linspace(-0.6, 0.6, side))
+    z = 2.0 + 0.5 * np.sin(3 * u) * np.cos(2 * v) + 0.002 * rng.normal(size=u.shape)
+    clouds = {"depthmap": np.stack([u * z, v * z, z], -1).reshape(-1, 3).astype(np.float32),
+              "uniform": rng.uniform(-1, 1, size=(side * side, 3)).astype(np.float32)}
+    out = {}
+    for name in which:
+        pts = clouds[name]
+        t = torch.from_numpy(pts).cuda()
+        res = {}
+        for impl, fn in (("ours", distCUDA2), ("reference", ref_cuda.distCUDA2 if ref_cuda.knn_available() else None)):
+            if fn is None:
+                continue
+            fn(t); torch.cuda.synchronize()
+            n = 5 if impl == "ours" else 2
+            t0 = time.perf_counter()
+            for _ in range(n):
+                r = fn(t)
+            torch.cuda.synchronize()
+            res[impl + "_ms"] = (time.perf_counter() - t0) / n * 1e3
+            res[impl] = r
+        if "reference" in res:
+            res["bit_identical"] = bool(torch.equal(res.pop("ours"), res.pop("reference")))
+        else:
+            res.pop("ours")
+        out[name] = dict(P=len(pts), **res)
+    return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000)))
