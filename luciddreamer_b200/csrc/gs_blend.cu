@@ -24,6 +24,8 @@
 //    of the four pixels are summed in registers, reduced across the warp with a value-halving shuffle butterfly
 //    (12 shuffles for 9 values), across the 2 warps in shared memory, and leave the CTA as 128-bit vector
 //    reductions: one per (tile, splat).  Warps start the reverse traversal at max(n_contrib) over their pixels.
+#include <cstdlib>
+
 #include "gs_common.cuh"
 
 namespace {
@@ -40,6 +42,9 @@ struct __align__(16) SRec {           // shared-memory copy of a splat record
     uint32_t id;
     uint32_t pad;
 };
+
+constexpr float kHalfLog2e = -0.5f * 1.4426950408889634f;     // staged conic scale (see stage_batch)
+constexpr float kUnscale = -2.0f * 0.6931471805599453f;       // back to the conic for the flush of the backward pass
 
 // 2-bit mask: which of the tile's two 16x8 pixel blocks the splat can touch
 __device__ __forceinline__ uint32_t block_mask(const float4 a, const float4 b, const float thr, int tx0, int ty0) {
@@ -77,7 +82,10 @@ __device__ __forceinline__ void stage_batch(SRec* sRec, uint32_t (*sMask)[kWords
             const uint32_t id = list[beg + pos_of(j)];
             const float4* r = rec + (size_t)GS_REC_V4 * id;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-            SRec s; s.a = a; s.b = b; s.c = make_float2(c.x, c.y); s.id = id; s.pad = 0;
+            // the conic is staged pre-multiplied for the exponent in base 2:
+            //   log2(e) * power = A2 dx dx + C2 dy dy + B2 dx dy,  A2 = -0.5 log2e A, C2 = -0.5 log2e C, B2 = -log2e B
+            SRec s; s.a = make_float4(a.x, a.y, a.z * kHalfLog2e, a.w * (2.f * kHalfLog2e));
+            s.b = make_float4(b.x * kHalfLog2e, b.y, b.z, b.w); s.c = make_float2(c.x, c.y); s.id = id; s.pad = 0;
             sRec[j] = s;
             m = block_mask(a, b, c.w, tx0, ty0);
         }
@@ -97,20 +105,24 @@ struct FwdPix {
 
 // forward.cu:330-369 for the thread's four pixels, written branch-free (predicated updates) so that the four
 // independent dependency chains interleave; the arithmetic of every taken update is the reference's.
-__device__ __forceinline__ void fwd_eval4(FwdPix* P, const SRec& r, const float dx, const float* dy, const uint32_t pos1) {
-    float power[kPix], alpha[kPix];
+__device__ __forceinline__ void fwd_eval4(FwdPix* P, const SRec& r, const float dx, const float* dy, const uint32_t pos1,
+                                          const float4* __restrict__ rec) {
+    float power[kPix], alpha[kPix];       // power = log2(e) * the reference's power (same sign)
     bool band = false;
+    const float hA = r.a.z * dx * dx, hB = r.a.w * dx;
 #pragma unroll
     for (int q = 0; q < kPix; q++) {
-        power[q] = -0.5f * (r.a.z * dx * dx + r.b.x * dy[q] * dy[q]) - r.a.w * dx * dy[q];
+        power[q] = fmaf(hB, dy[q], fmaf(r.b.x * dy[q], dy[q], hA));
         float g;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(power[q] * 1.4426950408889634f));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(power[q]));
         alpha[q] = r.b.y * g;
         band = band || (fabsf(alpha[q] - 1.0f / 255.0f) < 1e-7f);
     }
-    if (band) {                       // rare: decide the 1/255 test with the reference's expf
+    if (band) {                       // rare: decide the 1/255 test with the reference's arithmetic (forward.cu:336-343)
+        const float4 a = __ldg(rec + (size_t)GS_REC_V4 * r.id), b = __ldg(rec + (size_t)GS_REC_V4 * r.id + 1);
 #pragma unroll
-        for (int q = 0; q < kPix; q++) alpha[q] = r.b.y * expf(power[q]);
+        for (int q = 0; q < kPix; q++)
+            alpha[q] = r.b.y * expf(-0.5f * (a.z * dx * dx + b.x * dy[q] * dy[q]) - a.w * dx * dy[q]);
     }
 #pragma unroll
     for (int q = 0; q < kPix; q++) {
@@ -186,7 +198,7 @@ k_blend_fwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
                 float dy[kPix];
 #pragma unroll
                 for (int q = 0; q < kPix; q++) dy[q] = r.a.y - (float)(pyb + 2 * q);
-                fwd_eval4(P, r, dx, dy, (uint32_t)(base + j + 1));
+                fwd_eval4(P, r, dx, dy, (uint32_t)(base + j + 1), rec);
             }
         }
     }
@@ -235,7 +247,7 @@ __device__ __forceinline__ void warp_reduce9(float* v, const int lane) {
 struct BwdPix {
     float T;
     float tb;                         // -T_final * (bg . dL_dpixel)
-    float ar0, ar1, ar2;              // accum_rec, already advanced past the last contributing splat
+    float AR;                         // sum_ch accum_rec_ch * dL_dpixel_ch, already advanced past the last contributing splat
     float g0, g1, g2;                 // dL_dpixel
     int last_contributor;
 };
@@ -247,13 +259,14 @@ struct BwdPix {
 __device__ __forceinline__ bool bwd_eval4(BwdPix* Q, const SRec& r, const float dx, const float* dy, const int pos,
                                           const float ddelx_dx, const float ddely_dy, float* vv) {
     float power[kPix], G[kPix], alpha[kPix];
-    const float Adx = r.a.z * dx, Bdx = r.a.w * dx, dx2 = dx * dx;
+    float s0 = 0.f, sy = 0.f, syy = 0.f;
     // no exact-exp band here: a borderline alpha ~ 1/255 decided differently from the forward changes one pixel's
     // reconstructed transmittance by 0.4 %, far below the gradient tolerance, and saves 3 instructions per pixel
+    const float hA = r.a.z * dx * dx, hB = r.a.w * dx;
 #pragma unroll
     for (int q = 0; q < kPix; q++) {
-        power[q] = -0.5f * (r.a.z * dx * dx + r.b.x * dy[q] * dy[q]) - r.a.w * dx * dy[q];
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G[q]) : "f"(power[q] * 1.4426950408889634f));
+        power[q] = fmaf(hB, dy[q], fmaf(r.b.x * dy[q], dy[q], hA));       // log2(e) * power (staged conic)
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G[q]) : "f"(power[q]));
         alpha[q] = r.b.y * G[q];
     }
     bool any = false;
@@ -267,37 +280,29 @@ __device__ __forceinline__ bool bwd_eval4(BwdPix* Q, const SRec& r, const float 
         const float inv = __frcp_rn(1.f - a_);
         const float T = p.T * inv;
         const float dchannel_dcolor = a_ * T;
-        float dL_dalpha = 0.0f;
-        const float c0 = r.b.z, c1 = r.b.w, c2 = r.c.x;
-        // backward.cu:520-528 updates accum_rec lazily (last_alpha * last_color + (1 - last_alpha) * accum_rec at
-        // the NEXT contributing splat); the same expression is evaluated here eagerly, right after use.
-        dL_dalpha += (c0 - p.ar0) * p.g0;
-        dL_dalpha += (c1 - p.ar1) * p.g1;
-        dL_dalpha += (c2 - p.ar2) * p.g2;
-        p.ar0 = a_ * c0 + (1.f - a_) * p.ar0;
-        p.ar1 = a_ * c1 + (1.f - a_) * p.ar1;
-        p.ar2 = a_ * c2 + (1.f - a_) * p.ar2;
+        // backward.cu:520-528 keeps accum_rec per channel (updated lazily with last_alpha * last_color + (1 - last_alpha)
+        // * accum_rec at the NEXT contributing splat) and forms sum_ch (c_ch - accum_rec_ch) * dL_dpixel_ch.  dL_dpixel is
+        // constant per pixel, so only the scalar AR = sum_ch accum_rec_ch * dL_dpixel_ch is carried: it obeys the same
+        // recurrence (AR' = a cg + (1 - a) AR = AR + a (cg - AR), cg = c . dL_dpixel) and is advanced eagerly.
+        const float cg = r.b.z * p.g0 + r.b.w * p.g1 + r.c.x * p.g2;
+        const float dcol = cg - p.AR;
+        p.AR = fmaf(a_, dcol, p.AR);
         p.T = T;
         vv[0] += dchannel_dcolor * p.g0; vv[1] += dchannel_dcolor * p.g1; vv[2] += dchannel_dcolor * p.g2;
-        dL_dalpha *= T;
-        dL_dalpha += p.tb * inv;
-        dL_dalpha = ok ? dL_dalpha : 0.f;
-        const float Gq = ok ? G[q] : 0.f;                   // keeps inf/NaN of skipped splats out of the sums
-        // backward.cu:563-583 with the constant factors (-0.5*W, -0.5*H for the mean, -0.5 for the conic) applied
-        // once per (tile, splat) when the CTA flushes, and the dx terms shared by the four pixels:
-        //   dL_dmean2D.x = -0.5 W * sum k (A dx + B dy)      dL_dconic.a = -0.5 * sum k dx dx
-        //   dL_dmean2D.y = -0.5 H * sum k (C dy + B dx)      dL_dconic.b = -0.5 * sum k dx dy      k = o G dL_dalpha
-        //   dL_dopacity  = sum G dL_dalpha                   dL_dconic.c = -0.5 * sum k dy dy
+        const float dL_dalpha = fmaf(dcol, T, p.tb * inv);  // finite also for a skipped splat (a_ = 0, inv = 1)
+        const float Gq = ok ? G[q] : 0.f;                   // zero weight; keeps an inf of a skipped splat out of the sums
+        // backward.cu:563-583 needs, per (pixel, splat), k = o G dL_dalpha times {A dx + B dy, C dy + B dx, dx dx, dx dy,
+        // dy dy} and G dL_dalpha itself.  Only the raw moments of g = G dL_dalpha are summed here -- dx is the same for
+        // the thread's four pixels, so three sums (g, g dy, g dy dy) per pixel and three products per thread suffice;
+        // the splat's constants (o, A, B, C, -0.5 W, -0.5 H, -0.5) are applied once per (tile, splat) at the flush.
         const float gda = Gq * dL_dalpha;
-        const float k = r.b.y * gda;
-        const float kdy = k * dy[q];
-        vv[3] += k * (Adx + r.a.w * dy[q]);
-        vv[4] += k * (r.b.x * dy[q] + Bdx);
-        vv[5] += k * dx2;
-        vv[6] += kdy * dx;
-        vv[7] += kdy * dy[q];
-        vv[8] += gda;
+        s0 += gda;
+        const float t = gda * dy[q];
+        sy += t;
+        syy = fmaf(t, dy[q], syy);
     }
+    vv[3] = s0;  vv[4] = dx * s0;  vv[5] = sy;
+    vv[6] = dx * vv[4];  vv[7] = dx * sy;  vv[8] = syy;
     return any;
 }
 
@@ -336,7 +341,7 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
         float bd = 0.f;
         bd += bgc0 * p.g0; bd += bgc1 * p.g1; bd += bgc2 * p.g2;
         p.tb = -T_final * bd;
-        p.ar0 = p.ar1 = p.ar2 = 0.f;
+        p.AR = 0.f;
         wmax = max(wmax, p.last_contributor);
     }
     const float ddelx_dx = 0.5 * v.W, ddely_dy = 0.5 * v.H;
@@ -398,8 +403,12 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
                 for (int k = 0; k < 9; k++) { r[k] = sAcc[j * 9 + k]; any = any || (r[k] != 0.f); }
                 if (any) {
                     float4* dst = acc + (size_t)3 * sRec[j].id;
-                    atomicAdd(dst, make_float4(-r[3] * ddelx_dx, -r[4] * ddely_dy, -0.5f * r[5], -0.5f * r[6]));
-                    atomicAdd(dst + 1, make_float4(-0.5f * r[7], r[8], r[0], r[1]));
+                    // r[3..8] = sums of g, g dx, g dy, g dx dx, g dx dy, g dy dy (g = G dL_dalpha) over the tile
+                    const SRec& sr = sRec[j];
+                    const float A = sr.a.z * kUnscale, B = sr.a.w * (0.5f * kUnscale), C = sr.b.x * kUnscale, o = sr.b.y;
+                    const float kx = o * r[4], ky = o * r[5], h = -0.5f * o;
+                    atomicAdd(dst, make_float4(-(A * kx + B * ky) * ddelx_dx, -(C * ky + B * kx) * ddely_dy, h * r[6], h * r[7]));
+                    atomicAdd(dst + 1, make_float4(h * r[8], r[3], r[0], r[1]));
                     atomicAdd(reinterpret_cast<float*>(dst + 2), r[2]);
                 }
             }
