@@ -179,8 +179,12 @@ class Ours:
         self.backward(color, cot)
         return color
 
-    def set_camera(self, vm, pm, cp):      # e2e: camera arrives from the host every step
-        self.vm.copy_(vm, non_blocking=True); self.pm.copy_(pm, non_blocking=True); self.cp.copy_(cp, non_blocking=True)
+    def bind_camera(self, d_cam):          # e2e: the operator reads the camera straight from the upload buffer
+        R, cam = self.R, self.cam
+        self.vm, self.pm, self.cp = d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35]
+        self.settings = R.GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
+                                                        self.bg, 1.0, self.vm, self.pm, self.D, self.cp, False, False)
+        self.rast = R.GaussianRasterizer(self.settings)
 
     def stats(self):
         idx = self.dev.index or 0
@@ -236,8 +240,8 @@ class RefCuda:
         self.backward(color, cot)
         return color
 
-    def set_camera(self, vm, pm, cp):
-        self.vm.copy_(vm, non_blocking=True); self.pm.copy_(pm, non_blocking=True); self.cp.copy_(cp, non_blocking=True)
+    def bind_camera(self, d_cam):
+        self.vm, self.pm, self.cp = d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35]
 
     def stats(self):
         return dict(P_vis=int((self.last[1] > 0).sum().item()), pairs=int(self.last[2]))
@@ -300,8 +304,7 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
         upload(base)
         for k in range(base, base + n):
             b = k & 1
-            d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream
-            impl.set_camera(d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35])
+            d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream; the operator reads it in place
             main.wait_event(ev_up[b])
             color = impl.forward()
             if fused_loss:
@@ -316,6 +319,7 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
             if k + 1 < base + n:                                  # next target: in flight during this step's backward;
                 upload(k + 1)                                     # issued last so the host reaches backward() early
 
+    impl.bind_camera(d_cam)
     for b in range(2):
         ev_free[b].record(main)
     run(warmup, 0)

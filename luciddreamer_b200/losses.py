@@ -22,9 +22,9 @@ def l1_loss_with_grad(color: torch.Tensor, target_u8: torch.Tensor, weight: floa
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     grad = torch.empty_like(color)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
-    with torch.cuda.device(idx):
+    with R._guard(idx):
         N.check(N.lib().gs_l1_loss_backward(R._ctx(idx), color.data_ptr(), target_u8.data_ptr(), H, W, float(weight),
-                                            grad.data_ptr(), loss.data_ptr(), torch.cuda.current_stream(idx).cuda_stream))
+                                            grad.data_ptr(), loss.data_ptr(), R._raw_stream(idx)))
     return loss, grad
 
 
@@ -46,10 +46,10 @@ def photometric_loss_with_grad(image: torch.Tensor, gt: torch.Tensor, lambda_dss
     scratch = torch.empty(L.gs_photometric_scratch_bytes(H, W), dtype=torch.uint8, device=dev)
     grad = torch.empty_like(image) if need_grad else None
     loss3 = torch.empty(3, dtype=torch.float32, device=dev)
-    with torch.cuda.device(idx):
+    with R._guard(idx):
         N.check(L.gs_photometric_loss_backward(R._ctx(idx), image.data_ptr(), gt.data_ptr(), H, W, float(lambda_dssim),
                                                scratch.data_ptr(), grad.data_ptr() if need_grad else None,
-                                               loss3.data_ptr(), torch.cuda.current_stream(idx).cuda_stream))
+                                               loss3.data_ptr(), R._raw_stream(idx)))
     return loss3, grad
 
 

@@ -116,10 +116,10 @@ class DensifyStats:
                     and dL_dmeans2D.dtype == torch.float32 and dL_dmeans2D.shape[-1] == 3):
                 raise RuntimeError("add_view: expects contiguous dL_dmeans2D [P,3] f32 and radii [P] int32")
             idx = dL_dmeans2D.device.index
-            with torch.cuda.device(idx):
+            with R._guard(idx):
                 N.check(N.lib().gs_densify_stats(R._ctx(idx), radii.numel(), radii.data_ptr(), dL_dmeans2D.data_ptr(),
                                                  self.xyz_gradient_accum.data_ptr(), self.denom.data_ptr(),
-                                                 self.max_radii2D.data_ptr(), torch.cuda.current_stream(idx).cuda_stream))
+                                                 self.max_radii2D.data_ptr(), R._raw_stream(idx)))
             return
         vis = radii > 0
         self.max_radii2D[vis] = torch.max(self.max_radii2D[vis], radii[vis].to(self.max_radii2D.dtype))

@@ -90,7 +90,7 @@ class FusedGaussianAdam:
             gr.lr = float(self.lrs[name])
         self.step_count += 1
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        with torch.cuda.device(idx):
+        with R._guard(idx):
             N.check(N.lib().gs_gaussian_adam_step(R._ctx(idx), groups, 6, float(self.betas[0]), float(self.betas[1]),
                                                   float(self.eps), self.step_count,
-                                                  torch.cuda.current_stream(idx).cuda_stream))
+                                                  R._raw_stream(idx)))

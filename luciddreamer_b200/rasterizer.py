@@ -39,6 +39,27 @@ def _ctx(dev_index: int) -> C.c_void_p:
     return c
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _guard(idx: int):
+    """Device guard only when the tensor's device is not already current (the context manager costs ~10 us)."""
+    return _NO_GUARD if torch.cuda.current_device() == idx else torch.cuda.device(idx)
+
+
+def _raw_stream(idx: int) -> int:
+    """cudaStream_t of torch's current stream on device idx, without building a torch.cuda.Stream object."""
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
 def _round_cap(n: int) -> int:
     return max(64, (int(n) + 63) // 64 * 64)      # multiples of 64 keep gs_binning_bytes(cap) == 12 * cap
 
@@ -94,9 +115,9 @@ def _forward_impl(prep: _Prepared):
     f, dev, P = prep.frame, prep.device, prep.P
     H, W = f.H, f.W
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    with torch.cuda.device(idx):
+    with _guard(idx):
         ctx = _ctx(idx)
-        stream = torch.cuda.current_stream(idx).cuda_stream
+        stream = _raw_stream(idx)
         u8 = dict(dtype=torch.uint8, device=dev)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
@@ -144,8 +165,8 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
         return _backward_peers(prep, radii, geom, binning, img, cap, grad_color, out, peers)
     cap, nvis = cap if isinstance(cap, tuple) else (cap, P)   # `_C` path: num_visible unknown -> bound by P
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    with torch.cuda.device(idx):
-        stream = torch.cuda.current_stream(idx).cuda_stream
+    with _guard(idx):
+        stream = _raw_stream(idx)
         f32 = dict(dtype=torch.float32, device=dev)
         # the tile pass goes to the GPU first; allocations below overlap with it
         gc = _dev_f32(grad_color, dev)
@@ -168,7 +189,7 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
                 if tuple(t.shape) != tuple(shape) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
                     raise RuntimeError(f"gradient sink '{key}' must be a contiguous f32 {tuple(shape)} tensor on {dev}")
             else:
-                t = flat[offs[key]:offs[key] + P * need[key]].view(shape)
+                t = flat.narrow(0, offs[key], P * need[key]).view(shape)
             return t.zero_() if zero else t
 
         dm3 = dst("dm3", (P, 3)); dm2 = dst("dm2", (P, 3))
@@ -198,8 +219,8 @@ def _backward_peers(prep: _Prepared, radii, geom, binning, img, cap, grad_color,
     f, dev, P = prep.frame, prep.device, prep.P
     cap, nvis = cap if isinstance(cap, tuple) else (cap, P)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    with torch.cuda.device(idx):
-        stream = torch.cuda.current_stream(idx).cuda_stream
+    with _guard(idx):
+        stream = _raw_stream(idx)
         dm2 = out.get("dm2")
         if dm2 is None:
             dm2 = torch.empty((P, 3), dtype=torch.float32, device=dev)

@@ -22,8 +22,8 @@ def distCUDA2(points: torch.Tensor) -> torch.Tensor:
     if P == 0:
         return out
     idx = pts.device.index if pts.device.index is not None else torch.cuda.current_device()
-    with torch.cuda.device(idx):
+    with R._guard(idx):
         scratch = torch.empty(N.lib().gs_knn_scratch_bytes(P), dtype=torch.uint8, device=pts.device)
         N.check(N.lib().gs_knn_mean_dist2(R._ctx(idx), P, pts.data_ptr(), scratch.data_ptr(), out.data_ptr(),
-                                          torch.cuda.current_stream(idx).cuda_stream))
+                                          R._raw_stream(idx)))
     return out

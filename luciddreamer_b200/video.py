@@ -37,11 +37,11 @@ def pack_frame(color: torch.Tensor, depth: Optional[torch.Tensor], rgb8: torch.T
         raise RuntimeError("pack_frame: CUDA tensors only (no CPU fallback)")
     _, H, W = color.shape
     idx = color.device.index
-    with torch.cuda.device(idx):
+    with R._guard(idx):
         N.check(N.lib().gs_pack_frame(R._ctx(idx), H, W, color.data_ptr(), depth.data_ptr() if depth is not None else None,
                                       rgb8.data_ptr(), neg_depth.data_ptr() if neg_depth is not None else None,
                                       minmax_state.data_ptr() if minmax_state is not None else None,
-                                      torch.cuda.current_stream(idx).cuda_stream))
+                                      R._raw_stream(idx)))
 
 
 def render_video_frames(params: dict, settings_list: Sequence, rank: int = 0, world: int = 1, with_depth: bool = True):
@@ -75,8 +75,8 @@ def render_video_frames(params: dict, settings_list: Sequence, rank: int = 0, wo
     if with_depth:
         mm = torch.empty(2, dtype=torch.float32, device=dev)
         idx = dev.index
-        with torch.cuda.device(idx):
-            N.check(N.lib().gs_minmax_read(R._ctx(idx), state.data_ptr(), mm.data_ptr(), torch.cuda.current_stream(idx).cuda_stream))
+        with R._guard(idx):
+            N.check(N.lib().gs_minmax_read(R._ctx(idx), state.data_ptr(), mm.data_ptr(), R._raw_stream(idx)))
         h_d = torch.empty((F, H, W), dtype=torch.float32, pin_memory=True)
         h_d.copy_(negd, non_blocking=True)
         h_mm = torch.empty(2, dtype=torch.float32, pin_memory=True)
