@@ -57,16 +57,6 @@ __device__ __forceinline__ uint32_t block_mask(const float4 a, const float4 b, c
     return m;
 }
 
-// opacity * exp(power): fast exponential, exact re-evaluation where the 1/255 decision could differ
-__device__ __forceinline__ float alpha_of(const float opacity, const float power, float& G) {
-    float g;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(power * 1.4426950408889634f));
-    float al = opacity * g;
-    if (fabsf(al - 1.0f / 255.0f) < 1e-7f) { g = expf(power); al = opacity * g; }
-    G = g;
-    return al;
-}
-
 // Stages up to two splats per thread into shared memory and publishes the per-block hit masks.
 // slot j of the batch holds list position pos(j); returns nothing, fills sRec / sMask.  All threads must call.
 template <typename PosFn>
@@ -257,7 +247,7 @@ struct BwdPix {
 // 1/(1-alpha) is formed once (reciprocal) for both quotients: the gradient tolerance is 1e-3 relative, the
 // difference to two IEEE divisions is ~1e-7.
 __device__ __forceinline__ bool bwd_eval4(BwdPix* Q, const SRec& r, const float dx, const float* dy, const int pos,
-                                          const float ddelx_dx, const float ddely_dy, float* vv) {
+                                          float* vv) {
     float power[kPix], G[kPix], alpha[kPix];
     float s0 = 0.f, sy = 0.f, syy = 0.f;
     // no exact-exp band here: a borderline alpha ~ 1/255 decided differently from the forward changes one pixel's
@@ -386,7 +376,7 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
                 float dy[kPix];
 #pragma unroll
                 for (int q = 0; q < kPix; q++) dy[q] = r.a.y - (float)(pyb + 2 * q);
-                const bool any = bwd_eval4(Q, r, dx, dy, p, ddelx_dx, ddely_dy, vv);
+                const bool any = bwd_eval4(Q, r, dx, dy, p, vv);
                 if (!__any_sync(0xffffffffu, any)) continue;
                 warp_reduce9(vv, lane);
                 if (owner) atomicAdd(&sAcc[j * 9 + slot], vv[0]);
