@@ -11,8 +11,9 @@ collective); value = total rays of all ranks / max-over-ranks device time.  Prin
 
 --impl reference times the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libref_rasterizer.so, compiled
 from the reference's own sources) on the same GPU, same inputs, same protocol; if that library is absent it
-falls back to the CPU oracle port.  The reference has no CPU implementation of this path, so
-`cpu_baseline` is always the oracle port on the host cores.
+falls back to the CPU oracle port.  Under torchrun (N > 1) rank 0 alone runs it (one GPU, "n_gpus": 1 in its line) and
+the other ranks exit 0, as the bench contract asks.  The reference has no CPU implementation of this path (SURVEY.md
+0.3), so `cpu_baseline` is always the oracle port on the host cores.
 """
 from __future__ import annotations
 
