@@ -18,6 +18,11 @@ def pytest_sessionstart(session):
     lib = os.path.join(ROOT, "luciddreamer_b200", "csrc", "libgsraster_b200.so")
     if not os.path.exists(lib):
         subprocess.check_call(["make", "-C", os.path.dirname(lib), "-j8"], stdout=subprocess.DEVNULL)
+    bind = os.path.join(os.path.dirname(lib), "_gsraster_torch.so")
+    if not os.path.exists(bind):                     # host-side torch binding over the same C ABI (plain g++, ~30 s)
+        import sys
+        subprocess.check_call([sys.executable, os.path.join(os.path.dirname(lib), "build_binding.py")],
+                              stdout=subprocess.DEVNULL)
     ora = os.path.join(ROOT, "oracle", "liboracle.so")
     if not os.path.exists(ora):
         subprocess.check_call(["make", "-C", os.path.dirname(ora), "liboracle.so"], stdout=subprocess.DEVNULL)

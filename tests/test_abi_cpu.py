@@ -86,3 +86,17 @@ def test_drop_in_module_name():
         "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
         "sh_degree", "campos", "prefiltered", "debug")
     assert hasattr(m, "GaussianRasterizer") and hasattr(m._C, "rasterize_gaussians_backward")
+
+
+def test_torch_binding_builds_and_exposes_forward_backward():
+    """csrc/_gsraster_torch.so (torch_binding.cpp: the RasterizeGaussiansCUDA / BackwardCUDA of rasterize_points.cu on
+    top of gsraster.h) is built in-tree, loads on a CPU-only host and is what the autograd Function dispatches to."""
+    from luciddreamer_b200 import rasterizer as R
+    mod = R._fast()
+    assert mod, "torch binding not built"
+    assert callable(mod.forward) and callable(mod.backward)
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        R.rasterize_gaussians(torch.zeros(4, 2), torch.zeros(4, 3), torch.zeros(4, 16, 3), torch.empty(0), torch.zeros(4, 1),
+                              torch.zeros(4, 3), torch.zeros(4, 4), torch.empty(0),
+                              R.GaussianRasterizationSettings(8, 8, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 3,
+                                                              torch.zeros(3), False, False))
