@@ -624,17 +624,29 @@ def main():
         N_, G_, M_ = W * H, ((W + 15) // 16) * ((H + 15) // 16), scene["shs"].shape[1]
         ab = alg_bytes(P, st["P_vis"], st["pairs"], N_, G_, M_)
         dom = max(kt, key=lambda k: kt[k])
-        traffic = None
+        traffic, warp_inst = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.scene, {}).get(dom)
+                tj = json.load(open(tp))
+                traffic = tj.get(args.scene, {}).get(dom)
+                warp_inst = tj.get(args.scene + "_warp_inst", {}).get(dom)
             except Exception:
-                traffic = None
+                traffic, warp_inst = None, None
         ach = ab[dom] / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                             "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes": ab[dom], "kernel_ms": kt[dom]}
+        if warp_inst and kt[dom] > 0 and clocks and clocks.get("sm_mhz"):
+            # the dominant kernel is FP32-issue bound, not HBM bound: its own ceiling is the warp
+            # instruction issue rate = SMs x 4 schedulers x SM clock; instructions per launch are the ncu count of this
+            # workload (profiles/traffic.json), the duration is measured live
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6
+            ach_issue = warp_inst / (kt[dom] * 1e-3)
+            line["roofline"]["issue"] = {"warp_instructions_per_launch": warp_inst, "achieved_ginst_s": ach_issue / 1e9,
+                                         "peak_ginst_s": peak_issue / 1e9, "frac": ach_issue / peak_issue,
+                                         "note": "supplementary: issue-slot ceiling of the FP32-bound blend kernel"}
         total_alg = sum(ab.values())
         line["roofline_step"] = {"algorithmic_bytes": total_alg, "achieved": total_alg / (ms / args.steps * 1e-3) / 1e9,
                                  "unit": "GB/s", "frac": total_alg / (ms / args.steps * 1e-3) / 1e9 / peak}
