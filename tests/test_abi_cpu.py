@@ -100,3 +100,13 @@ def test_torch_binding_builds_and_exposes_forward_backward():
                               torch.zeros(4, 3), torch.zeros(4, 4), torch.empty(0),
                               R.GaussianRasterizationSettings(8, 8, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 3,
                                                               torch.zeros(3), False, False))
+
+
+def test_simple_knn_drop_in_module_name_and_no_cpu_fallback():
+    """`from simple_knn._C import distCUDA2` (scene/gaussian_model.py:19) resolves to our implementation; CPU tensors
+    fail loudly."""
+    from simple_knn._C import distCUDA2
+    import luciddreamer_b200.simple_knn as ours
+    assert distCUDA2 is ours.distCUDA2
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        distCUDA2(torch.zeros(8, 3))
