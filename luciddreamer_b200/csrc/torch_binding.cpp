@@ -172,10 +172,87 @@ backward(int64_t ctx_ptr, const c10::optional<at::Tensor>& bg, const at::Tensor&
     return {dm2, dcol, dop, dm3, dcov, dsh, dsc, drot};
 }
 
+// ---- the autograd node itself in C++ (RAST/depth_diff_gaussian_rasterization_min/__init__.py:44-156): same inputs,
+// outputs (color, radii, depth), gradient order and None/zero conventions as the Python _RasterizeGaussians
+int64_t g_last_pairs[64] = {0};
+
+struct RasterizeFn : public torch::autograd::Function<RasterizeFn> {
+    static torch::autograd::variable_list forward(torch::autograd::AutogradContext* ctx, at::Tensor means3D,
+                                                  at::Tensor means2D, at::Tensor sh, at::Tensor colors, at::Tensor opacity,
+                                                  at::Tensor scales, at::Tensor rotations, at::Tensor cov3D, at::Tensor bg,
+                                                  at::Tensor viewmatrix, at::Tensor projmatrix, at::Tensor campos,
+                                                  int64_t ctx_ptr, double scale_modifier, double tan_fovx, double tan_fovy,
+                                                  int64_t H, int64_t W, int64_t degree, bool prefiltered, bool debug,
+                                                  int64_t pair_hint) {
+        auto r = ::forward(ctx_ptr, bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D, viewmatrix,
+                           projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered, debug, pair_hint);
+        at::Tensor color = std::get<1>(r), depth = std::get<2>(r), radii = std::get<3>(r);
+        const int dev = means3D.device().index();
+        if (dev >= 0 && dev < 64) g_last_pairs[dev] = std::get<9>(r);
+        ctx->save_for_backward({radii, std::get<4>(r), std::get<5>(r), std::get<6>(r), means3D, sh, colors, opacity, scales,
+                                rotations, cov3D, bg, viewmatrix, projmatrix, campos});
+        ctx->saved_data["ctx_ptr"] = ctx_ptr;
+        ctx->saved_data["scale_modifier"] = scale_modifier;
+        ctx->saved_data["tan_fovx"] = tan_fovx;
+        ctx->saved_data["tan_fovy"] = tan_fovy;
+        ctx->saved_data["H"] = H;
+        ctx->saved_data["W"] = W;
+        ctx->saved_data["degree"] = degree;
+        ctx->saved_data["debug"] = debug;
+        ctx->saved_data["cap"] = std::get<7>(r);
+        ctx->saved_data["nvis"] = std::get<8>(r);
+        ctx->mark_non_differentiable({radii});
+        ctx->set_materialize_grads(false);       // no zero-fill kernels for the unused grad_radii / grad_depth
+        return {color, radii, depth};
+    }
+
+    static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx,
+                                                   torch::autograd::variable_list grad_out) {
+        const auto sv = ctx->get_saved_variables();
+        const at::Tensor &radii = sv[0], &geom = sv[1], &binning = sv[2], &img = sv[3], &means3D = sv[4], &sh = sv[5],
+                         &colors = sv[6], &opacity = sv[7], &scales = sv[8], &rotations = sv[9], &cov3D = sv[10],
+                         &bg = sv[11], &viewmatrix = sv[12], &projmatrix = sv[13], &campos = sv[14];
+        const int64_t H = ctx->saved_data["H"].toInt(), W = ctx->saved_data["W"].toInt();
+        at::Tensor gc = grad_out[0];
+        if (!gc.defined())                       // only depth was used downstream: depth carries no gradient
+            gc = at::zeros({3, H, W}, at::TensorOptions().dtype(at::kFloat).device(means3D.device()));
+        auto has = [](const at::Tensor& t) { return t.defined() && t.numel() > 0; };
+        auto g = ::backward(ctx->saved_data["ctx_ptr"].toInt(), bg, means3D, colors, opacity, scales, rotations,
+                            ctx->saved_data["scale_modifier"].toDouble(), cov3D, viewmatrix, projmatrix,
+                            ctx->saved_data["tan_fovx"].toDouble(), ctx->saved_data["tan_fovy"].toDouble(), H, W, sh,
+                            ctx->saved_data["degree"].toInt(), campos, ctx->saved_data["debug"].toBool(), radii, geom,
+                            binning, img, ctx->saved_data["cap"].toInt(), ctx->saved_data["nvis"].toInt(), gc, has(colors),
+                            has(cov3D));
+        const at::Tensor none;
+        // (dm2, dcol, dop, dm3, dcov, dsh, dsc, drot) -> the order of the forward arguments (__init__.py:144-156)
+        return {std::get<3>(g), std::get<0>(g), has(sh) ? std::get<5>(g) : none, std::get<1>(g), std::get<2>(g),
+                has(scales) ? std::get<6>(g) : none, has(rotations) ? std::get<7>(g) : none, std::get<4>(g),
+                none, none, none, none,                                        // bg, viewmatrix, projmatrix, campos
+                none, none, none, none, none, none, none, none, none, none};   // the ten non-tensor arguments
+    }
+};
+
+std::tuple<at::Tensor, at::Tensor, at::Tensor> rasterize(at::Tensor means3D, at::Tensor means2D, at::Tensor sh,
+                                                         at::Tensor colors, at::Tensor opacity, at::Tensor scales,
+                                                         at::Tensor rotations, at::Tensor cov3D, at::Tensor bg,
+                                                         at::Tensor viewmatrix, at::Tensor projmatrix, at::Tensor campos,
+                                                         int64_t ctx_ptr, double scale_modifier, double tan_fovx,
+                                                         double tan_fovy, int64_t H, int64_t W, int64_t degree,
+                                                         bool prefiltered, bool debug, int64_t pair_hint) {
+    auto out = RasterizeFn::apply(means3D, means2D, sh, colors, opacity, scales, rotations, cov3D, bg, viewmatrix,
+                                  projmatrix, campos, ctx_ptr, scale_modifier, tan_fovx, tan_fovy, H, W, degree, prefiltered,
+                                  debug, pair_hint);
+    return {out[0], out[1], out[2]};
+}
+
+int64_t last_pairs(int64_t dev) { return dev >= 0 && dev < 64 ? g_last_pairs[dev] : 0; }
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "torch binding of libgsraster_b200 (include/gsraster.h)";
     m.def("forward", &forward);
     m.def("backward", &backward);
+    m.def("rasterize", &rasterize);
+    m.def("last_pairs", &last_pairs);
 }

@@ -61,6 +61,7 @@ def _raw_stream(idx: int) -> int:
 
 
 _fast_mod = None          # the torch binding (csrc/_gsraster_torch.so); False = not built / disabled
+_CPP_AUTOGRAD = __import__("os").environ.get("GS_CPP_AUTOGRAD", "1") != "0"
 
 
 def _fast():
@@ -311,8 +312,29 @@ class _C:
 
 # -------------------------------------------------------------------------------- reference Python surface
 
+def _t(x):
+    return x if x is not None else _EMPTY
+
+
+_EMPTY = torch.empty(0)
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings):
+    """__init__.py:21-42.  With the torch binding built, the autograd node itself is native (torch_binding.cpp:
+    RasterizeFn -- same inputs, outputs, gradient order and None conventions as _RasterizeGaussians below, which stays
+    the implementation when the binding is absent or GS_CPP_AUTOGRAD=0)."""
+    fast = _fast()
+    if fast and _CPP_AUTOGRAD and means3D.is_cuda:
+        rs = raster_settings
+        idx = means3D.device.index
+        hint = _cap_hint.get(idx)
+        color, radii, depth = fast.rasterize(
+            means3D, _t(means2D), _t(sh), _t(colors_precomp), _t(opacities), _t(scales), _t(rotations), _t(cov3Ds_precomp),
+            rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, _ctx(idx).value, rs.scale_modifier, rs.tanfovx, rs.tanfovy,
+            rs.image_height, rs.image_width, rs.sh_degree, bool(rs.prefiltered), bool(rs.debug), -1 if hint is None else hint)
+        _cap_hint[idx] = fast.last_pairs(idx)
+        return color, radii, depth
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                      cov3Ds_precomp, raster_settings)
 
