@@ -465,17 +465,18 @@ def _tool(name):
     return mod
 
 
-def knn_leg():
-    """simple_knn.distCUDA2 over 1 M points (depth-map shaped cloud), ours vs the reference's own kernels."""
-    out = _tool("knn_bench").run(1_000_000, which=("depthmap",))["depthmap"]
-    out["what"] = "mean squared distance to the 3 nearest neighbours, 1 M points; reference = simple_knn.cu compiled unmodified"
+def knn_leg(impl="ours"):
+    """simple_knn.distCUDA2 over 1 M points (depth-map shaped cloud).  The `ours` arm times our kernels, the
+    `reference` arm the reference's own simple_knn.cu compiled unmodified (oracle/_ref) -- each in its own bench run."""
+    out = _tool("knn_bench").run(1_000_000, which=("depthmap",), impls=(impl,))["depthmap"]
+    out["what"] = "mean squared distance to the 3 nearest neighbours, 1 M points (bit-identical outputs: tests/)"
     return out
 
 
-def video_leg():
-    """forward-only clip at the bench resolution, device-side packing + one host copy vs the reference
-    rasterizer inside the per-frame loop of luciddreamer.py:250-262."""
-    out = _tool("video_bench").run(16)
+def video_leg(impl="ours"):
+    """SURVEY 8f-4: forward-only clip at the bench resolution.  `ours`: device-side packing + one host copy;
+    `reference`: the reference rasterizer inside the per-frame loop of luciddreamer.py:250-262."""
+    out = _tool("video_bench").run(16, impls=(impl,))
     out["what"] = "rotate360 clip, uint8 frames + masked depth + dmin/dmax delivered to host memory"
     return out
 
@@ -658,10 +659,18 @@ def main():
     if rank == 0 and world == 1 and args.impl == "ours":
         nr = {}
         for name, fn in (("photometric_loss", lambda: loss_leg(H, W, dev)), ("optimizer_step", lambda: adam_leg(scene, dev)),
-                         ("dist_cuda2", knn_leg), ("video_render", video_leg)):
+                         ("dist_cuda2", knn_leg), ("video_render", video_leg)):     # reference side: --impl reference
             try:
                 nr[name] = fn()
             except Exception as ex:                      # a "next" row must never take the headline line down
+                nr[name] = {"error": str(ex)[:200]}
+        line["next_rows"] = nr
+    if rank == 0 and world == 1 and args.impl == "reference" and use_ref_cuda:
+        nr = {}
+        for name, fn in (("dist_cuda2", lambda: knn_leg("reference")), ("video_render", lambda: video_leg("reference"))):
+            try:
+                nr[name] = fn()
+            except Exception as ex:
                 nr[name] = {"error": str(ex)[:200]}
         line["next_rows"] = nr
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -10,11 +10,13 @@ import numpy as np
 import torch
 
 from luciddreamer_b200.simple_knn import distCUDA2
-from oracle import ref_cuda
 
 
 
-def run(P=1_000_000, which=("depthmap", "uniform")):
+def run(P=1_000_000, which=("depthmap", "uniform"), impls=("ours", "reference")):
+    ref_cuda = None
+    if "reference" in impls:
+        from oracle import ref_cuda          # the reference's own kernels (oracle/_ref), only when asked for
     side = int(round(P ** 0.5))
     rng = np.random.default_rng(11)
     u, v = np.meshgrid(np.linspace(-1, 1, side), np.linspace(-0.6, 0.6, side))
@@ -26,7 +28,8 @@ def run(P=1_000_000, which=("depthmap", "uniform")):
         pts = clouds[name]
         t = torch.from_numpy(pts).cuda()
         res = {}
-        for impl, fn in (("ours", distCUDA2), ("reference", ref_cuda.distCUDA2 if ref_cuda.knn_available() else None)):
+        for impl, fn in (("ours", distCUDA2 if "ours" in impls else None),
+                         ("reference", ref_cuda.distCUDA2 if ref_cuda is not None and ref_cuda.knn_available() else None)):
             if fn is None:
                 continue
             fn(t); torch.cuda.synchronize()
@@ -37,10 +40,9 @@ def run(P=1_000_000, which=("depthmap", "uniform")):
             torch.cuda.synchronize()
             res[impl + "_ms"] = (time.perf_counter() - t0) / n * 1e3
             res[impl] = r
-        if "reference" in res:
-            res["bit_identical"] = bool(torch.equal(res.pop("ours"), res.pop("reference")))
-        else:
-            res.pop("ours")
+        if "reference" in res and "ours" in res:
+            res["bit_identical"] = bool(torch.equal(res["ours"], res["reference"]))
+        res.pop("ours", None); res.pop("reference", None)
         out[name] = dict(P=len(pts), **res)
     return out
 

@@ -13,10 +13,12 @@ import numpy as np
 import torch
 
 from luciddreamer_b200 import GaussianRasterizationSettings, synthetic as syn, video
-from oracle import ref_cuda
 
 
-def run(F=48):
+def run(F=48, impls=("ours", "reference")):
+    ref_cuda = None
+    if "reference" in impls:
+        from oracle import ref_cuda          # the reference rasterizer (oracle/_ref), only when asked for
     d = torch.device("cuda:0")
     c = syn.CONFIGS[3]
     P, W, H = c["P"], c["W"], c["H"]
@@ -47,7 +49,8 @@ def run(F=48):
 
     out = {"frames": F, "H": H, "W": W, "P": P}
     res = {}
-    for name, fn in (("ours", ours), ("reference", reference if ref_cuda.available() else None)):
+    for name, fn in (("ours", ours if "ours" in impls else None),
+                     ("reference", reference if ref_cuda is not None and ref_cuda.available() else None)):
         if fn is None:
             continue
         fn(); torch.cuda.synchronize()
@@ -58,7 +61,7 @@ def run(F=48):
         res[name] = r
         out[name + "_ms_per_frame"] = dt / F * 1e3
         out[name + "_fps"] = F / dt
-    if "reference" in res:
+    if "reference" in res and "ours" in res:
         a, b = res["ours"], res["reference"]
         diff = np.abs(a[0].astype(np.int16) - np.stack(b[0]).astype(np.int16))
         out["max_uint8_diff_vs_reference"] = int(diff.max())
