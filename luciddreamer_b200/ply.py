@@ -112,4 +112,5 @@ def load_ply(path: str, max_sh_degree: int = 3, device="cuda") -> Dict[str, torc
     out = dict(xyz=xyz, features_dc=np.ascontiguousarray(fdc.transpose(0, 2, 1)),
                features_rest=np.ascontiguousarray(rest.transpose(0, 2, 1)),
                opacity=np.asarray(v["opacity"], dtype=np.float32)[:, None], scaling=cols("scale_"), rotation=cols("rot"))
-    return {k: torch.from_numpy(np.ascontiguousarray(a)).to(device) for k, a in out.items()}
+    # np.array(...) copies: views of the file buffer (np.frombuffer) are read-only, torch wants writable memory
+    return {k: torch.from_numpy(np.array(a, dtype=np.float32, order="C")).to(device) for k, a in out.items()}
