@@ -159,7 +159,9 @@ class Ours:
         self.settings = R.GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
                                                         self.bg, 1.0, self.vm, self.pm, D, self.cp, False, False)
         self.rast = R.GaussianRasterizer(self.settings)
-        self.kernels_per_step = 10
+        # k_project, k_count_tiles, k_tile_scan, k_shade_emit, k_tile_sort, k_tile_sort_mid, k_tile_sort_big, k_blend_fwd,
+        # k_blend_bwd, k_grad_vis, k_grad_write (profiles/r01_launches_ours.csv) -- our kernels only, no torch kernels
+        self.kernels_per_step = 11
         self.last = None
 
     def forward(self):
