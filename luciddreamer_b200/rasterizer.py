@@ -75,10 +75,14 @@ def _fast():
         if os.environ.get("GS_NO_TORCH_BINDING", "0") != "1" and os.path.exists(path):
             import importlib.util
             N.lib()                                   # libgsraster_b200.so first (fails loudly if missing)
-            spec = importlib.util.spec_from_file_location("_gsraster_torch", path)
-            mod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(mod)
-            _fast_mod = mod
+            try:
+                spec = importlib.util.spec_from_file_location("_gsraster_torch", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _fast_mod = mod
+            except Exception as ex:                   # host glue only: the ctypes path drives the same CUDA library
+                import warnings
+                warnings.warn(f"luciddreamer_b200: torch binding {path} failed to load ({ex}); using the ctypes host path")
     return _fast_mod
 
 
