@@ -135,10 +135,17 @@ def make_workload(args, rank):
     if args.W and args.H:
         W, H = args.W, args.H
     scale_mult = 4.0 if args.scene == "stress" else 1.0
-    scene = syn.make_scene(P, 1000 + CFG_ID, scale_mult=scale_mult)
+    if args.scene == "frustum":          # LucidDreamer-shaped population (synthetic.make_frustum_scene)
+        scene = syn.make_frustum_scene(P, 1000 + CFG_ID, W, H)
+    else:
+        scene = syn.make_scene(P, 1000 + CFG_ID, scale_mult=scale_mult)
     cam = syn.make_camera(W, H, c2w=view_pose(rank))
     cot = syn.make_cotangent(H, W, 1000 + CFG_ID)
-    return scene, cam, cot, dict(P=P, W=W, H=H, D=D, scale_mult=scale_mult)
+    wl = dict(P=P, W=W, H=H, D=D, scale_mult=scale_mult, cams=None)
+    if getattr(args, "random_camera", 0):
+        # one of N jittered training views per step, drawn pseudo-randomly (luciddreamer.py:291-292)
+        wl["cams"] = [syn.make_camera(W, H, c2w=m) for m in syn.jitter_poses(args.random_camera, 4711 + rank)]
+    return scene, cam, cot, wl
 
 
 # ------------------------------------------------------------------------------------------- implementations
@@ -163,14 +170,27 @@ class Ours:
         # k_blend_bwd, k_grad_vis, k_grad_write (profiles/r01_launches_ours.csv) -- our kernels only, no torch kernels
         self.kernels_per_step = 11
         self.last = None
+        self.rasts, self.order, self.k = None, None, 0
+
+    def set_cameras(self, cams, seed=99):
+        """Random-camera mode: a rasterizer per training view (camera tensors resident), one drawn per step."""
+        R, dev = self.R, self.dev
+        self.rasts = [R.GaussianRasterizer(R.GaussianRasterizationSettings(
+            c.image_height, c.image_width, c.tanfovx, c.tanfovy, self.bg, 1.0, c.viewmatrix.to(dev), c.projmatrix.to(dev),
+            self.D, c.campos.to(dev), False, False)) for c in cams]
+        self.order = np.random.RandomState(seed).randint(0, len(cams), size=4096)
 
     def forward(self):
         L = self.leaves
         for t in L.values():
             t.grad = None
         self.m2.grad = None
-        color, radii, depth = self.rast(L["means3D"], self.m2, L["opacities"], shs=L["shs"], scales=L["scales"],
-                                        rotations=L["rotations"])
+        rast = self.rast
+        if self.rasts is not None:
+            rast = self.rasts[self.order[self.k & 4095]]
+            self.k += 1
+        color, radii, depth = rast(L["means3D"], self.m2, L["opacities"], shs=L["shs"], scales=L["scales"],
+                                   rotations=L["rotations"])
         self.last = (color, radii)
         return color
 
@@ -191,7 +211,7 @@ class Ours:
 
     def stats(self):
         idx = self.dev.index or 0
-        pairs = self.R._cap_hint.get(idx, 0)
+        pairs = self.R._last_pairs.get(idx, 0)
         radii = self.last[1]
         return dict(P_vis=int((radii > 0).sum().item()), pairs=int(pairs))
 
@@ -226,12 +246,21 @@ class RefCuda:
         self.vm, self.pm, self.cp = cam.viewmatrix.to(dev), cam.projmatrix.to(dev), cam.campos.to(dev)
         self.cam = cam
         self.kernels_per_step = 0
+        self.cams, self.order, self.k = None, None, 0
+
+    def set_cameras(self, cams, seed=99):
+        dev = self.dev
+        self.cams = [(c, c.viewmatrix.to(dev), c.projmatrix.to(dev), c.campos.to(dev)) for c in cams]
+        self.order = np.random.RandomState(seed).randint(0, len(cams), size=4096)
 
     def forward(self):
-        t, cam = self.t, self.cam
+        t, cam, vm, pm, cp = self.t, self.cam, self.vm, self.pm, self.cp
+        if self.cams is not None:
+            cam, vm, pm, cp = self.cams[self.order[self.k & 4095]]
+            self.k += 1
         R, color, depth, radii = self.rc.rasterize_gaussians(
-            self.ctx, self.bg, t["means3D"], None, t["opacities"], t["scales"], t["rotations"], 1.0, None, self.vm,
-            self.pm, cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, t["shs"], self.D, self.cp)
+            self.ctx, self.bg, t["means3D"], None, t["opacities"], t["scales"], t["rotations"], 1.0, None, vm,
+            pm, cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, t["shs"], self.D, cp)
         self.last = (color, radii, R)
         return color
 
@@ -459,6 +488,47 @@ def adam_leg(scene, dev, iters=10):
     return out
 
 
+SHAPED = [
+    # BASELINE.json configs[1]: the reference's own resolution, 100 k Gaussians (shell scene, seed 1002)
+    ("config2_100k_512", dict(scene="shell", P=100_000, W=512, H=512, seed=1002, cams=0)),
+    # what the reference's optimisation loop renders (luciddreamer.py:283-327, arguments.py:42-46): 512x512, 1-2 M Gaussians
+    # nearly all inside the frustum, about a pixel in size, a random training camera per iteration
+    ("frustum_1M_512_randcam", dict(scene="frustum", P=1_000_000, W=512, H=512, seed=2001, cams=16)),
+    ("frustum_2M_512_randcam", dict(scene="frustum", P=2_000_000, W=512, H=512, seed=2002, cams=16)),
+    ("frustum_1M_1080p", dict(scene="frustum", P=1_000_000, W=1920, H=1080, seed=2003, cams=0)),
+]
+
+
+def shaped_legs(impl_cls, dev, D=3, steps=10, warmup=3, only=None):
+    """`next` rows of the measurement: forward+backward on the reference's real workload shape and on
+    BASELINE config 2, same protocol as the headline (CUDA events, parameters resident in HBM).  The product arm and the
+    reference arm (`--impl reference`) each report their own side."""
+    out = {}
+    for name, s in SHAPED:
+        if only and name not in only:
+            continue
+        try:
+            W, H = s["W"], s["H"]
+            scene = (syn.make_frustum_scene(s["P"], s["seed"], W, H) if s["scene"] == "frustum"
+                     else syn.make_scene(s["P"], s["seed"]))
+            cam = syn.make_camera(W, H)
+            cot = syn.make_cotangent(H, W, s["seed"]).to(dev)
+            impl = impl_cls(scene, cam, dev, D)
+            if s["cams"]:
+                impl.set_cameras([syn.make_camera(W, H, c2w=m) for m in syn.jitter_poses(s["cams"], s["seed"])])
+            ms = time_steps(impl, cot, steps, warmup, 1) / steps
+            st = impl.stats()
+            out[name] = {"ms_per_step": ms, "value": W * H / ms / 1e3, "unit": "Mrays/s", "P": s["P"], "W": W, "H": H,
+                         "P_vis": st["P_vis"], "pairs": st["pairs"], "random_cameras": s["cams"], "steps": steps}
+            if hasattr(impl, "profile"):
+                out[name]["kernels_ms"] = impl.profile(cot, n=3)
+            del impl, scene, cot
+            torch.cuda.empty_cache()
+        except Exception as ex:                      # a `next` row must never take the headline line down
+            out[name] = {"error": str(ex)[:200]}
+    return out
+
+
 def _tool(name):
     import importlib.util
     spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
@@ -550,7 +620,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scene", default="shell", choices=["shell", "stress"])
+    ap.add_argument("--scene", default="shell", choices=["shell", "stress", "frustum"])
+    ap.add_argument("--random-camera", type=int, default=0, help="N jittered training views, one drawn per step")
+    ap.add_argument("--no-next-rows", action="store_true")
     ap.add_argument("--P", type=int, default=0); ap.add_argument("--W", type=int, default=0); ap.add_argument("--H", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared-model", action="store_true")
@@ -595,6 +667,9 @@ def main():
         impl = RefCuda(scene, cam, dev, D)
     else:
         impl = Ours(scene, cam, dev, D)
+
+    if wl["cams"]:
+        impl.set_cameras(wl["cams"])
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -658,18 +733,20 @@ def main():
         if world > 1 and not args.no_shared_model:
             line["shared_model_step"] = shared_model_leg(scene, cam, cot, dev, D, args.steps, args.warmup, world)
 
-    if rank == 0 and world == 1 and args.impl == "ours":
+    if rank == 0 and world == 1 and args.impl == "ours" and not args.no_next_rows:
         nr = {}
         for name, fn in (("photometric_loss", lambda: loss_leg(H, W, dev)), ("optimizer_step", lambda: adam_leg(scene, dev)),
-                         ("dist_cuda2", knn_leg), ("video_render", video_leg)):     # reference side: --impl reference
+                         ("dist_cuda2", knn_leg), ("video_render", video_leg),
+                         ("luciddreamer_shaped", lambda: shaped_legs(Ours, dev))):     # reference side: --impl reference
             try:
                 nr[name] = fn()
             except Exception as ex:                      # a "next" row must never take the headline line down
                 nr[name] = {"error": str(ex)[:200]}
         line["next_rows"] = nr
-    if rank == 0 and world == 1 and args.impl == "reference" and use_ref_cuda:
+    if rank == 0 and world == 1 and args.impl == "reference" and use_ref_cuda and not args.no_next_rows:
         nr = {}
-        for name, fn in (("dist_cuda2", lambda: knn_leg("reference")), ("video_render", lambda: video_leg("reference"))):
+        for name, fn in (("dist_cuda2", lambda: knn_leg("reference")), ("video_render", lambda: video_leg("reference")),
+                         ("luciddreamer_shaped", lambda: shaped_legs(RefCuda, dev))):
             try:
                 nr[name] = fn()
             except Exception as ex:
@@ -687,7 +764,9 @@ def main():
 def config_dict(wl, args, world):
     return {"workload": f"BASELINE config {CFG_ID}: {wl['P']} Gaussians, {wl['W']}x{wl['H']}, SH degree {wl['D']}, "
                         f"forward+backward, one view per GPU per step",
-            "scene": f"{args.scene} (SURVEY.md 8d shell, seed {1000 + CFG_ID}, scale x{wl['scale_mult']})",
+            "scene": (f"{args.scene} (SURVEY.md 8d shell, seed {1000 + CFG_ID}, scale x{wl['scale_mult']})" if args.scene != "frustum"
+                      else f"frustum (LucidDreamer-shaped, synthetic.make_frustum_scene, seed {1000 + CFG_ID})"),
+            "random_cameras": len(wl["cams"]) if wl.get("cams") else 0,
             "views_per_step": world, "parallelism": f"view-parallel x{world}",
             "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 25 MB cotangent per step)"}
 

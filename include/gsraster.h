@@ -65,11 +65,12 @@ typedef struct GsFrame {
     int32_t debug;           /* != 0: synchronize + check after every stage (auxiliary.h:166-173) */
     const float* bg;             /* [3] */
     const float* means3D;        /* [P,3] */
-    const float* shs;            /* [P,M,3] or NULL */
+    const float* shs;            /* [P,M,3] or NULL; base pointer 16-byte aligned (128-bit loads) */
     const float* colors_precomp; /* [P,3]   or NULL */
     const float* opacities;      /* [P,1] */
     const float* scales;         /* [P,3]   or NULL */
-    const float* rotations;      /* [P,4]   or NULL (r,x,y,z), used un-normalised like forward.cu:127 */
+    const float* rotations;      /* [P,4]   or NULL (r,x,y,z), used un-normalised like forward.cu:127; base pointer
+                                    16-byte aligned.  The Python / torch hosts clone misaligned views. */
     const float* cov3D_precomp;  /* [P,6]   or NULL */
     const float* viewmatrix;     /* [16] m[r+4c] = W2C[r][c]        (scene/cameras.py:58) */
     const float* projmatrix;     /* [16] (Proj.W2C), same layout    (scene/cameras.py:60) */

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/gsraster.h"
@@ -44,6 +45,9 @@ int check_frame(const GsFrame* f) {
         ((f->scales != nullptr || f->rotations != nullptr) && f->cov3D_precomp != nullptr))
         return fail(GS_EINVAL, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
     (void)has_sr;
+    // k_project / k_grad_vis / sh_to_rgb read rotations and SH rows with 128-bit loads
+    if ((reinterpret_cast<uintptr_t>(f->rotations) & 15) || (reinterpret_cast<uintptr_t>(f->shs) & 15))
+        return fail(GS_EINVAL, "rotations and shs must be 16-byte aligned (see gsraster.h)");
     if (f->shs && (f->M <= 0 || f->D < 0 || f->D > 3 || (f->D + 1) * (f->D + 1) > f->M))
         return fail(GS_EINVAL, "SH degree %d needs %d coefficients, M=%d", f->D, (f->D + 1) * (f->D + 1), f->M);
     return GS_OK;
@@ -89,7 +93,7 @@ struct GsContext {
     bool pev_used[kNumKernels];
     GsDevStatus* slots;            // pinned, mapped
     cudaEvent_t events[kSlots];
-    std::atomic<int> next;
+    std::atomic<unsigned> next;
 };
 
 // Brackets a launch with timing events on the launching stream when profiling is on (bench.py's roofline leg).
@@ -139,12 +143,25 @@ int gs_context_create(int device, GsContext** out) {
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     gs_tile_sort_init();
     gs_grad_write_init();
+    if (const char* e = getenv("GS_BLEND_VARIANT")) g_gs_blend_variant = atoi(e);
     cudaError_t e = cudaHostAlloc((void**)&c->slots, sizeof(GsDevStatus) * kSlots, cudaHostAllocMapped | cudaHostAllocPortable);
-    if (e != cudaSuccess) { delete c; cudaSetDevice(prev); return fail(GS_ECUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) {
+        for (int j = 0; j < 2 * kNumKernels; j++) cudaEventDestroy(c->pev[j]);
+        delete c;
+        cudaSetDevice(prev);
+        return fail(GS_ECUDA, "cudaHostAlloc: %s", cudaGetErrorString(e));
+    }
     memset(c->slots, 0, sizeof(GsDevStatus) * kSlots);
     for (int i = 0; i < kSlots; i++) {
         e = cudaEventCreateWithFlags(&c->events[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) { cudaSetDevice(prev); return fail(GS_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) {
+            for (int j = 0; j < i; j++) cudaEventDestroy(c->events[j]);
+            for (int j = 0; j < 2 * kNumKernels; j++) cudaEventDestroy(c->pev[j]);
+            cudaFreeHost(c->slots);
+            delete c;
+            cudaSetDevice(prev);
+            return fail(GS_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+        }
     }
     cudaSetDevice(prev);
     *out = c;
@@ -173,7 +190,7 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     const GsView v = make_view(f);
     const int G = v.gx * v.gy;
     GsImageLayout il = gs_image_layout(image_buffer, f->W, f->H);
-    const int slot = ctx->next.fetch_add(1) % kSlots;
+    const int slot = (int)(ctx->next.fetch_add(1u) % (unsigned)kSlots);
     GsDevStatus* host_slot = ctx->slots + slot;
     host_slot->overflow = 0;                             // cleared; kernel writes 0xC0FFEE when done
     // zero tile histogram + status in one memset (they are adjacent)

@@ -1,29 +1,33 @@
-// Tile compositing, forward and backward (sm_100a).
+// Tile compositing, forward and backward (sm_100a), round-2 kernels.
 //
 // k_blend_fwd replaces RAST/cuda_rasterizer/forward.cu:261-391 (renderCUDA): front-to-back alpha compositing of
 //   colour + depth per 16x16 tile, same formulas per (pixel, splat).
 // k_blend_bwd replaces backward.cu:399-586 (renderCUDA backward), same formulas per (pixel, splat).
 //
-// Both kernels are FP32-issue bound (ncu: ~90 % issue-slot utilisation, <2 % DRAM), so the design minimises
-// instructions per (pixel, splat) evaluation and skips evaluations that cannot contribute:
+// Both kernels are instruction-issue bound (ncu round 1: 83 % / 73 % issue utilisation, < 2 % DRAM), so the
+// design minimises issued instructions per (pixel, splat) evaluation:
 //  * one CTA of 64 threads per tile; a warp owns a 16x8 pixel block and every thread FOUR pixels of one column
-//    (x, y), (x, y+2), (x, y+4), (x, y+6): the shared-memory record fetch, the loop bookkeeping, the dx terms of
-//    the quadratic form and -- in the backward -- the cross-lane reduction are paid once per four pixels;
+//    (x, y), (x, y+2), (x, y+4), (x, y+6), held as two float2 PAIRS: all per-pixel arithmetic is issued as
+//    sm_100 packed FP32 (fma.rn.f32x2 / mul.f32x2 / add.f32x2 -> FFMA2 / FMUL2 / FADD2, one issue slot for
+//    two pixels; per-splat scalars ride along as broadcast operands);
 //  * the per-splat record (xy, conic, opacity, rgb, depth) is fetched ONCE per (tile, splat) with 128-bit loads
-//    into shared memory; the reference gathers colour and depth from global memory per contributing
-//    (pixel, splat) (forward.cu:359,364);
-//  * while a batch of 128 splats is staged, the staging thread tests its splats against the two 16x8 blocks of
-//    the tile (exact ellipse-vs-box test, gs_box_hit) and the warps ballot the results into a 128-bit mask per
-//    block.  A warp whose mask is sparse walks only the set bits; a dense mask falls back to the plain loop.
-//    Skipped splats cannot reach alpha >= 1/255 anywhere in the block (every pixel would skip them in the
-//    reference too, forward.cu:336-346), so no output changes;
-//  * exp(): ex2.approx of power*log2(e) (2 instructions instead of the 10 of expf).  Its ~5e-7 relative error is
-//    far inside the 1e-4 colour tolerance, but alpha is compared against 1/255; inside a band of 1e-7 around
-//    that threshold alpha is re-evaluated with expf so the skip decision is the reference's;
+//    into shared memory; the staging thread also tests its splat against the tile's two 16x8 blocks (exact
+//    ellipse-vs-box test) and the warps ballot the results into a bit mask per block, walked with one FLO per hit;
+//  * per-splat FAST-PATH eligibility is decided once at staging (warp-uniform): opacity <= 0.99 (the
+//    min(0.99, alpha) clamp of forward.cu:343 can never bind) and a well-conditioned positive-definite conic
+//    (power <= 0 holds with a 10x margin over fp32 rounding, so forward.cu:336's `power > 0` test can never
+//    fire).  Eligible splats skip both per-pixel tests; everything else takes the generic path, which is the
+//    reference's test sequence verbatim;
+//  * exp(): ex2.approx of the log2-scaled power (conic pre-multiplied at staging).  alpha is compared against
+//    1/255; inside a band of 1e-7 around that threshold a thread re-evaluates its four alphas with expf and
+//    the reference's expression (generic path), so the skip decision is the reference's.  Forward and
+//    backward run the SAME instruction sequence up to that decision, hence skip exactly the same
+//    (pixel, splat) pairs;
 //  * backward: the reference issues 9 global float atomicAdds per contributing (pixel, splat); here the 9 partials
 //    of the four pixels are summed in registers, reduced across the warp with a value-halving shuffle butterfly
-//    (12 shuffles for 9 values), across the 2 warps in shared memory, and leave the CTA as 128-bit vector
-//    reductions: one per (tile, splat).  Warps start the reverse traversal at max(n_contrib) over their pixels.
+//    (12 shuffles for 9 values), written to a per-warp shared-memory slot with a plain store (each warp visits a
+//    staged splat at most once), and leave the CTA as 128-bit vector reductions: one per (tile, splat).
+//    1/(1-alpha) is a single MUFU.RCP (the gradient tolerance is 1e-3 relative).
 #include <cstdlib>
 
 #include "gs_common.cuh"
@@ -31,20 +35,61 @@
 namespace {
 
 constexpr int kThreads = 64;          // 2 warps; warp w -> pixel rows [8w, 8w+8) of the tile, 16 wide
-constexpr int kPix = 4;               // pixels per thread: (x, y0 + 2q), q = 0..3
 constexpr int kBatch = 128;           // splats staged per round (two per thread)
 constexpr int kWords = kBatch / 32;
 
 struct __align__(16) SRec {           // shared-memory copy of a splat record
-    float4 a;                         // x, y, conic_a, conic_b
-    float4 b;                         // conic_c, opacity, r, g
+    float4 a;                         // x, y, A2 = -0.5 log2e conic_a, B2 = -log2e conic_b
+    float4 b;                         // C2 = -0.5 log2e conic_c, opacity, r, g
     float2 c;                         // b, depth
     uint32_t id;
-    uint32_t pad;
+    uint32_t generic;                 // != 0: not eligible for the fast path
 };
 
 constexpr float kHalfLog2e = -0.5f * 1.4426950408889634f;     // staged conic scale (see stage_batch)
 constexpr float kUnscale = -2.0f * 0.6931471805599453f;       // back to the conic for the flush of the backward pass
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kBand = 1e-7f;
+
+// ---- packed FP32 pairs (sm_100 FFMA2 / FMUL2 / FADD2); scalar broadcasts fold into the operand (Rx.F32)
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%6,%7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 bc(const float s) { return make_float2(s, s); }
+__device__ __forceinline__ float ex2_approx(const float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(const float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // 2-bit mask: which of the tile's two 16x8 pixel blocks the splat can touch
 __device__ __forceinline__ uint32_t block_mask(const float4 a, const float4 b, const float thr, int tx0, int ty0) {
@@ -58,7 +103,8 @@ __device__ __forceinline__ uint32_t block_mask(const float4 a, const float4 b, c
 }
 
 // Stages up to two splats per thread into shared memory and publishes the per-block hit masks.
-// slot j of the batch holds list position pos(j); returns nothing, fills sRec / sMask.  All threads must call.
+// slot j of the batch holds list position pos(j).  Mask words are bit-REVERSED (slot 32k+i -> bit 31-i) so the
+// traversal finds the next slot with one FLO (count-leading-zeros).  All threads must call.
 template <typename PosFn>
 __device__ __forceinline__ void stage_batch(SRec* sRec, uint32_t (*sMask)[kWords], const uint32_t* __restrict__ list,
                                             const float4* __restrict__ rec, uint32_t beg, int cnt, int tx0, int ty0,
@@ -75,74 +121,101 @@ __device__ __forceinline__ void stage_batch(SRec* sRec, uint32_t (*sMask)[kWords
             // the conic is staged pre-multiplied for the exponent in base 2:
             //   log2(e) * power = A2 dx dx + C2 dy dy + B2 dx dy,  A2 = -0.5 log2e A, C2 = -0.5 log2e C, B2 = -log2e B
             SRec s; s.a = make_float4(a.x, a.y, a.z * kHalfLog2e, a.w * (2.f * kHalfLog2e));
-            s.b = make_float4(b.x * kHalfLog2e, b.y, b.z, b.w); s.c = make_float2(c.x, c.y); s.id = id; s.pad = 0;
+            s.b = make_float4(b.x * kHalfLog2e, b.y, b.z, b.w); s.c = make_float2(c.x, c.y); s.id = id;
+            // fast-path eligibility (NaNs answer "generic"): alpha = opacity * G can exceed neither 0.99 nor, with
+            // det >= 1e-5 trace^2 (smallest eigenvalue >= 1e-5 trace: ~100x the fp32 rounding of the three products),
+            // can the computed power be positive
+            const float A = a.z, B = a.w, Cc = b.x, tr = A + Cc;
+            const bool fast = (b.y <= 0.99f) && (A > 0.f) && (Cc > 0.f) && (A * Cc - B * B > 1e-5f * tr * tr) &&
+                              (fabsf(a.x) < 1e7f) && (fabsf(a.y) < 1e7f) && (tr < 1e7f);
+            s.generic = fast ? 0u : 1u;
             sRec[j] = s;
             m = block_mask(a, b, c.w, tx0, ty0);
         }
 #pragma unroll
         for (int w = 0; w < 2; w++) {
-            const uint32_t bits = __ballot_sync(0xffffffffu, (m >> w) & 1u);
+            const uint32_t bits = __brev(__ballot_sync(0xffffffffu, (m >> w) & 1u));
             if (lane == 0) sMask[w][wid + 2 * h] = bits;      // word index = j / 32
         }
     }
 }
 
+// the thread's four pixels as two packed pairs: pair h holds rows (2h) and (2h+1) of the thread, i.e. image rows
+// pyb + 4h and pyb + 4h + 2
 struct FwdPix {
-    float T;                          // > 0: live transmittance; <= 0: pixel terminated (|T| is the value to report)
-    float C0, C1, C2, D, acc;         //      or outside the image
-    uint32_t last;
+    float2 T[2];                      // > 0: live transmittance; <= 0: pixel terminated (|T| is the value to report)
+    float2 C0[2], C1[2], C2[2], D[2], acc[2];                                            // or outside the image
+    uint32_t last[4];
 };
 
-// forward.cu:330-369 for the thread's four pixels, written branch-free (predicated updates) so that the four
-// independent dependency chains interleave; the arithmetic of every taken update is the reference's.
-__device__ __forceinline__ void fwd_eval4(FwdPix* P, const SRec& r, const float dx, const float* dy, const uint32_t pos1,
-                                          const float4* __restrict__ rec) {
-    float power[kPix], alpha[kPix];       // power = log2(e) * the reference's power (same sign)
-    bool band = false;
-    const float hA = r.a.z * dx * dx, hB = r.a.w * dx;
+#define GS_Q(v, q) (((q) & 1) ? (v)[(q) >> 1].y : (v)[(q) >> 1].x)
+
+// The approximate evaluation shared by forward and backward: p = log2(e) * power, g = 2^p, a = opacity * g,
+// d = a - 1/255 (sign-exact).  Returns true when one of the four alphas sits inside the re-evaluation band.
+__device__ __forceinline__ bool eval_alpha4(const SRec& r, const float dx, const float2* dy, float2* p, float2* g,
+                                            float2* a, float2* d) {
+    const float hA = (r.a.z * dx) * dx, hB = r.a.w * dx;
 #pragma unroll
-    for (int q = 0; q < kPix; q++) {
-        power[q] = fmaf(hB, dy[q], fmaf(r.b.x * dy[q], dy[q], hA));
-        float g;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(power[q]));
-        alpha[q] = r.b.y * g;
-        band = band || (fabsf(alpha[q] - 1.0f / 255.0f) < 1e-7f);
+    for (int h = 0; h < 2; h++) {
+        const float2 u = fma2(bc(r.b.x), dy[h], bc(hB));          // C2 dy + B2 dx
+        p[h] = fma2(u, dy[h], bc(hA));                            // (C2 dy + B2 dx) dy + A2 dx dx
+        g[h] = make_float2(ex2_approx(p[h].x), ex2_approx(p[h].y));
+        a[h] = mul2(bc(r.b.y), g[h]);
+        d[h] = add2(a[h], bc(-kAlphaMin));
     }
-    if (band) {                       // rare: decide the 1/255 test with the reference's arithmetic (forward.cu:336-343)
-        const float4 a = __ldg(rec + (size_t)GS_REC_V4 * r.id), b = __ldg(rec + (size_t)GS_REC_V4 * r.id + 1);
+    const float m = fminf(fminf(fabsf(d[0].x), fabsf(d[0].y)), fminf(fabsf(d[1].x), fabsf(d[1].y)));
+    return m < kBand;
+}
+
+// alpha of the thread's four pixels with the reference's arithmetic (forward.cu:330-343), from the unscaled record
+__device__ __forceinline__ void exact_alpha4(const SRec& r, const float dx, const float2* dy,
+                                             const float4* __restrict__ rec, float* alpha) {
+    const float4 ra = __ldg(rec + (size_t)GS_REC_V4 * r.id), rb = __ldg(rec + (size_t)GS_REC_V4 * r.id + 1);
 #pragma unroll
-        for (int q = 0; q < kPix; q++)
-            alpha[q] = r.b.y * expf(-0.5f * (a.z * dx * dx + b.x * dy[q] * dy[q]) - a.w * dx * dy[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < kPix; q++) {
-        FwdPix& p = P[q];
-        const float al = fminf(0.99f, alpha[q]);
-        const bool ok = !(power[q] > 0.0f) && !(al < 1.0f / 255.0f);
-        const float test_T = p.T * (1.f - al);
-        const bool term = ok && (test_T < 0.0001f);       // forward.cu:348-352 (also true for T <= 0)
-        const bool upd = ok && !term;
-        if (upd) {
-            const float w = al * p.T;                     // one weight for colour, depth and coverage
-            p.C0 += r.b.z * w;
-            p.C1 += r.b.w * w;
-            p.C2 += r.c.x * w;
-            p.D += r.c.y * w;
-            p.acc += w;
-            p.last = pos1;
-        }
-        p.T = upd ? test_T : (term ? -fabsf(p.T) : p.T);
+    for (int q = 0; q < 4; q++) {
+        const float dyq = GS_Q(dy, q);
+        alpha[q] = r.b.y * expf(-0.5f * (ra.z * dx * dx + rb.x * dyq * dyq) - ra.w * dx * dyq);
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 16)
+// forward.cu:330-369, generic path: the reference's full test sequence per pixel (power > 0, min(0.99, alpha),
+// alpha < 1/255, T < 1e-4).  Taken by splats that are not fast-path eligible and by threads with an alpha in the band.
+__device__ __forceinline__ void fwd_generic(FwdPix& P, const SRec& r, const float dx, const float2* dy, const float2* p,
+                                         const float2* a, const bool band, const uint32_t pos1,
+                                         const float4* __restrict__ rec) {
+    float alpha[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) alpha[q] = GS_Q(a, q);
+    if (band) exact_alpha4(r, dx, dy, rec, alpha);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        float& T = GS_Q(P.T, q);
+        const float al = fminf(0.99f, alpha[q]);
+        const bool ok = !(GS_Q(p, q) > 0.0f) && !(al < kAlphaMin);
+        const float test_T = T * (1.f - al);
+        const bool low = test_T < 0.0001f;                // forward.cu:348-352 (also true for T <= 0)
+        const bool upd = ok && !low;
+        if (upd) {
+            const float w = al * T;                       // one weight for colour, depth and coverage
+            GS_Q(P.C0, q) += r.b.z * w;
+            GS_Q(P.C1, q) += r.b.w * w;
+            GS_Q(P.C2, q) += r.c.x * w;
+            GS_Q(P.D, q) += r.c.y * w;
+            GS_Q(P.acc, q) += w;
+            P.last[q] = pos1;
+        }
+        T = ok ? (low ? -fabsf(T) : test_T) : T;          // see the note at the fast path about this form
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 12)
 k_blend_fwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ list,
             const float4* __restrict__ rec, const GsDevStatus* __restrict__ status, long long capacity,
             float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
             float* __restrict__ out_depth) {
     if ((long long)status->num_pairs > capacity) return;
     __shared__ SRec sRec[kBatch];
-    __shared__ uint32_t sMask[2][kWords];                // [pixel block][32-splat word]
+    __shared__ uint32_t sMask[2][kWords];                // [pixel block][32-splat word], bit-reversed
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float bg0 = __ldg(v.bg), bg1 = __ldg(v.bg + 1), bg2 = __ldg(v.bg + 2);
     const int tile = blockIdx.y * v.gx + blockIdx.x;
@@ -150,21 +223,21 @@ k_blend_fwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
     const uint32_t px = tx0 + (lane & 15);
     const uint32_t pyb = ty0 + 8 * wid + (lane >> 4);    // rows pyb + 2q
     const float pixx = (float)px;
+    const float2 npy[2] = {make_float2(-(float)pyb, -(float)(pyb + 2)), make_float2(-(float)(pyb + 4), -(float)(pyb + 6))};
     const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
     const int n = (int)(end - beg);
 
-    FwdPix P[kPix];
+    FwdPix P;
 #pragma unroll
-    for (int q = 0; q < kPix; q++) {
+    for (int q = 0; q < 4; q++) {
         const bool in = px < (uint32_t)v.W && (pyb + 2 * q) < (uint32_t)v.H;
-        P[q].T = in ? 1.0f : -1.0f;
-        P[q].C0 = P[q].C1 = P[q].C2 = P[q].D = 0.f; P[q].acc = 0.000001f; P[q].last = 0u;
+        GS_Q(P.T, q) = in ? 1.0f : -1.0f;
+        GS_Q(P.C0, q) = 0.f; GS_Q(P.C1, q) = 0.f; GS_Q(P.C2, q) = 0.f; GS_Q(P.D, q) = 0.f;
+        GS_Q(P.acc, q) = 0.000001f; P.last[q] = 0u;
     }
 
     for (int base = 0; base < n; base += kBatch) {
-        bool alldone = true;
-#pragma unroll
-        for (int q = 0; q < kPix; q++) alldone = alldone && (P[q].T <= 0.f);
+        bool alldone = fmaxf(fmaxf(P.T[0].x, P.T[0].y), fmaxf(P.T[1].x, P.T[1].y)) <= 0.f;
         if (__syncthreads_and(alldone)) break;
         const int cnt = min(kBatch, n - base);
         stage_batch(sRec, sMask, list, rec, beg, cnt, tx0, ty0, [&](int j) { return base + j; });
@@ -173,38 +246,66 @@ k_blend_fwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
         for (int k = 0; k < kWords; k++) {
             uint32_t bits = sMask[wid][k];
             if (bits == 0) continue;
-            alldone = true;
-#pragma unroll
-            for (int q = 0; q < kPix; q++) alldone = alldone && (P[q].T <= 0.f);
+            alldone = fmaxf(fmaxf(P.T[0].x, P.T[0].y), fmaxf(P.T[1].x, P.T[1].y)) <= 0.f;
             if (__all_sync(0xffffffffu, alldone)) break;
-            const int wcnt = min(32, cnt - 32 * k);
-            // dense mask: visit every splat of the word (the per-pixel tests skip the misses anyway)
-            if (__popc(bits) * 4 >= wcnt * 3) bits = wcnt >= 32 ? 0xffffffffu : ((1u << wcnt) - 1u);
             while (bits) {
-                const int j = 32 * k + __ffs(bits) - 1;
-                bits &= bits - 1;
+                const int lz = __clz(bits);
+                bits &= ~(0x80000000u >> lz);
+                const int j = 32 * k + lz;
                 const SRec& r = sRec[j];
+                const uint32_t pos1 = (uint32_t)(base + j + 1);
                 const float dx = r.a.x - pixx;
-                float dy[kPix];
+                const float2 dy[2] = {add2(bc(r.a.y), npy[0]), add2(bc(r.a.y), npy[1])};
+                float2 p[2], g[2], a[2], d[2];
+                const bool band = eval_alpha4(r, dx, dy, p, g, a, d);
+                if (band || r.generic) {
+                    fwd_generic(P, r, dx, dy, p, a, band, pos1, rec);
+                    continue;
+                }
+                // fast path: alpha = a (no clamp), ok <=> a >= 1/255 <=> d >= 0 (forward.cu:336-346)
+                float2 tT[2], w[2];
 #pragma unroll
-                for (int q = 0; q < kPix; q++) dy[q] = r.a.y - (float)(pyb + 2 * q);
-                fwd_eval4(P, r, dx, dy, (uint32_t)(base + j + 1), rec);
+                for (int h = 0; h < 2; h++) {
+                    const float2 om = fma2(a[h], bc(-1.f), bc(1.f));      // 1 - alpha
+                    tT[h] = mul2(P.T[h], om);                             // test_T = T * (1 - alpha)
+                    w[h] = mul2(a[h], P.T[h]);                            // alpha * T
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const bool ok = GS_Q(d, q) >= 0.f;
+                    const bool low = GS_Q(tT, q) < 0.0001f;               // forward.cu:348-352 (also true for T <= 0)
+                    const bool upd = ok && !low;
+                    GS_Q(w, q) = upd ? GS_Q(w, q) : 0.f;
+                    P.last[q] = upd ? pos1 : P.last[q];
+                    float& T = GS_Q(P.T, q);
+                    // NB: written as nested selects on `ok`; nvcc 12.9 miscompiles `upd ? tT : (term ? -|T| : T)`
+                    // (drops the middle arm) -- tests/test_parity_gpu.py::test_early_termination pins this
+                    T = ok ? (low ? -fabsf(T) : GS_Q(tT, q)) : T;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    P.C0[h] = fma2(bc(r.b.z), w[h], P.C0[h]);
+                    P.C1[h] = fma2(bc(r.b.w), w[h], P.C1[h]);
+                    P.C2[h] = fma2(bc(r.c.x), w[h], P.C2[h]);
+                    P.D[h] = fma2(bc(r.c.y), w[h], P.D[h]);
+                    P.acc[h] = add2(P.acc[h], w[h]);
+                }
             }
         }
     }
     const size_t HW = (size_t)v.H * v.W;
 #pragma unroll
-    for (int q = 0; q < kPix; q++) {
+    for (int q = 0; q < 4; q++) {
         const uint32_t py = pyb + 2 * q;
         if (px < (uint32_t)v.W && py < (uint32_t)v.H) {
             const uint32_t pix_id = (uint32_t)v.W * py + px;
-            const float T = fabsf(P[q].T);
+            const float T = fabsf(GS_Q(P.T, q));
             final_T[pix_id] = T;
-            n_contrib[pix_id] = P[q].last;
-            out_color[pix_id] = P[q].C0 + T * bg0;
-            out_color[HW + pix_id] = P[q].C1 + T * bg1;
-            out_color[2 * HW + pix_id] = P[q].C2 + T * bg2;
-            out_depth[pix_id] = (P[q].acc > 0.5f) ? P[q].D / P[q].acc : 0.f;
+            n_contrib[pix_id] = P.last[q];
+            out_color[pix_id] = GS_Q(P.C0, q) + T * bg0;
+            out_color[HW + pix_id] = GS_Q(P.C1, q) + T * bg1;
+            out_color[2 * HW + pix_id] = GS_Q(P.C2, q) + T * bg2;
+            out_depth[pix_id] = (GS_Q(P.acc, q) > 0.5f) ? GS_Q(P.D, q) / GS_Q(P.acc, q) : 0.f;
         }
     }
 }
@@ -235,61 +336,57 @@ __device__ __forceinline__ void warp_reduce9(float* v, const int lane) {
 }
 
 struct BwdPix {
-    float T;
-    float tb;                         // -T_final * (bg . dL_dpixel)
-    float AR;                         // sum_ch accum_rec_ch * dL_dpixel_ch, already advanced past the last contributing splat
-    float g0, g1, g2;                 // dL_dpixel
-    int last_contributor;
+    float2 T[2];
+    float2 tb[2];                     // -T_final * (bg . dL_dpixel)
+    float2 AR[2];                     // sum_ch accum_rec_ch * dL_dpixel_ch, already advanced past the last contributing splat
+    float2 g0[2], g1[2], g2[2];       // dL_dpixel
+    int last[4];                      // last contributor (1-based list position)
 };
 
-// backward.cu:487-584 for the thread's four pixels, branch-free: every pixel evaluates the full expression and a
-// predicate zeroes what a skipped (pixel, splat) would add.  Returns whether any of the four contributed.
-// 1/(1-alpha) is formed once (reciprocal) for both quotients: the gradient tolerance is 1e-3 relative, the
-// difference to two IEEE divisions is ~1e-7.
-__device__ __forceinline__ bool bwd_eval4(BwdPix* Q, const SRec& r, const float dx, const float* dy, const int pos,
-                                          float* vv) {
-    float power[kPix], G[kPix], alpha[kPix];
-    float s0 = 0.f, sy = 0.f, syy = 0.f;
-    // no exact-exp band here: a borderline alpha ~ 1/255 decided differently from the forward changes one pixel's
-    // reconstructed transmittance by 0.4 %, far below the gradient tolerance, and saves 3 instructions per pixel
-    const float hA = r.a.z * dx * dx, hB = r.a.w * dx;
+// What both backward paths sum per (thread, splat), for w = opacity * G * dL_dalpha of the contributing pixels:
+//   vv[0..2] = sum alpha T dL_dpixel_ch          (dL_dcolor)
+//   vv[3..8] = sum w, dx w, sum w dy, dx dx w, dx sum w dy, sum w dy dy
+// backward.cu:563-583 needs G dL_dalpha times {1, dx, dy, dx dx, dx dy, dy dy} and the splat's constants (A, B, C,
+// -0.5 W, -0.5 H, -0.5, 1/opacity), which are applied once per (tile, splat) at the flush.
+//
+// backward.cu:520-528 keeps accum_rec per channel and forms sum_ch (c_ch - accum_rec_ch) * dL_dpixel_ch.  dL_dpixel is
+// constant per pixel, so only the scalar AR = sum_ch accum_rec_ch * dL_dpixel_ch is carried: it obeys the same
+// recurrence (AR' = a cg + (1 - a) AR = AR + a (cg - AR), cg = c . dL_dpixel) and is advanced eagerly.
+
+// generic path of the backward: the reference's test sequence per pixel, exact alpha inside the band
+__device__ __forceinline__ bool bwd_generic(BwdPix& Q, const SRec& r, const float dx, const float2* dy, const float2* p,
+                                         const float2* g, const float2* a, const bool band, const int pos,
+                                         const float4* __restrict__ rec, float* vv) {
+    float alpha[4];
 #pragma unroll
-    for (int q = 0; q < kPix; q++) {
-        power[q] = fmaf(hB, dy[q], fmaf(r.b.x * dy[q], dy[q], hA));       // log2(e) * power (staged conic)
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G[q]) : "f"(power[q]));
-        alpha[q] = r.b.y * G[q];
-    }
+    for (int q = 0; q < 4; q++) alpha[q] = GS_Q(a, q);
+    if (band) exact_alpha4(r, dx, dy, rec, alpha);
     bool any = false;
+    float s0 = 0.f, sy = 0.f, syy = 0.f;
 #pragma unroll
-    for (int q = 0; q < kPix; q++) {
-        BwdPix& p = Q[q];
+    for (int q = 0; q < 4; q++) {
         const float al = fminf(0.99f, alpha[q]);
-        const bool ok = (pos < p.last_contributor) && !(power[q] > 0.0f) && !(al < 1.0f / 255.0f);
+        const bool ok = (pos < Q.last[q]) && !(GS_Q(p, q) > 0.0f) && !(al < kAlphaMin);
         any = any || ok;
         const float a_ = ok ? al : 0.f;                     // alpha = 0 makes every update below a no-op
-        const float inv = __frcp_rn(1.f - a_);
-        const float T = p.T * inv;
-        const float dchannel_dcolor = a_ * T;
-        // backward.cu:520-528 keeps accum_rec per channel (updated lazily with last_alpha * last_color + (1 - last_alpha)
-        // * accum_rec at the NEXT contributing splat) and forms sum_ch (c_ch - accum_rec_ch) * dL_dpixel_ch.  dL_dpixel is
-        // constant per pixel, so only the scalar AR = sum_ch accum_rec_ch * dL_dpixel_ch is carried: it obeys the same
-        // recurrence (AR' = a cg + (1 - a) AR = AR + a (cg - AR), cg = c . dL_dpixel) and is advanced eagerly.
-        const float cg = r.b.z * p.g0 + r.b.w * p.g1 + r.c.x * p.g2;
-        const float dcol = cg - p.AR;
-        p.AR = fmaf(a_, dcol, p.AR);
-        p.T = T;
-        vv[0] += dchannel_dcolor * p.g0; vv[1] += dchannel_dcolor * p.g1; vv[2] += dchannel_dcolor * p.g2;
-        const float dL_dalpha = fmaf(dcol, T, p.tb * inv);  // finite also for a skipped splat (a_ = 0, inv = 1)
-        const float Gq = ok ? G[q] : 0.f;                   // zero weight; keeps an inf of a skipped splat out of the sums
-        // backward.cu:563-583 needs, per (pixel, splat), k = o G dL_dalpha times {A dx + B dy, C dy + B dx, dx dx, dx dy,
-        // dy dy} and G dL_dalpha itself.  Only the raw moments of g = G dL_dalpha are summed here -- dx is the same for
-        // the thread's four pixels, so three sums (g, g dy, g dy dy) per pixel and three products per thread suffice;
-        // the splat's constants (o, A, B, C, -0.5 W, -0.5 H, -0.5) are applied once per (tile, splat) at the flush.
-        const float gda = Gq * dL_dalpha;
-        s0 += gda;
-        const float t = gda * dy[q];
+        const float inv = rcp_approx(1.f - a_);
+        float& T = GS_Q(Q.T, q);
+        T = T * inv;
+        const float g0 = GS_Q(Q.g0, q), g1 = GS_Q(Q.g1, q), g2 = GS_Q(Q.g2, q);
+        const float cg = fmaf(r.c.x, g2, fmaf(r.b.w, g1, r.b.z * g0));
+        float& AR = GS_Q(Q.AR, q);
+        const float dcol = cg - AR;
+        AR = fmaf(a_, dcol, AR);
+        const float dch = a_ * T;
+        vv[0] = fmaf(dch, g0, vv[0]); vv[1] = fmaf(dch, g1, vv[1]); vv[2] = fmaf(dch, g2, vv[2]);
+        const float dL_dalpha = fmaf(dcol, T, GS_Q(Q.tb, q) * inv);
+        const float oG = ok ? r.b.y * GS_Q(g, q) : 0.f;     // zero weight keeps an inf of a skipped splat out of the sums
+        const float wq = oG * dL_dalpha;
+        const float dyq = GS_Q(dy, q);
+        s0 += wq;
+        const float t = wq * dyq;
         sy += t;
-        syy = fmaf(t, dy[q], syy);
+        syy = fmaf(t, dyq, syy);
     }
     vv[3] = s0;  vv[4] = dx * s0;  vv[5] = sy;
     vv[6] = dx * vv[4];  vv[7] = dx * sy;  vv[8] = syy;
@@ -301,8 +398,9 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
             const float4* __restrict__ rec, const float* __restrict__ final_Ts,
             const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix, float4* __restrict__ acc) {
     __shared__ SRec sRec[kBatch];
-    __shared__ float sAcc[kBatch * 9];
+    __shared__ float sAcc[2][kBatch * 9];                // per warp: plain stores, no atomics
     __shared__ uint32_t sMask[2][kWords];
+    __shared__ uint32_t sDone[2][kWords];                // which slots of sAcc a warp has written this round
     __shared__ int sMax[kThreads / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -311,28 +409,29 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
     const uint32_t px = tx0 + (lane & 15);
     const uint32_t pyb = ty0 + 8 * wid + (lane >> 4);
     const float pixx = (float)px;
+    const float2 npy[2] = {make_float2(-(float)pyb, -(float)(pyb + 2)), make_float2(-(float)(pyb + 4), -(float)(pyb + 6))};
     const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
     if (beg == end) return;
 
     const size_t HW = (size_t)v.H * v.W;
     const float bgc0 = __ldg(v.bg), bgc1 = __ldg(v.bg + 1), bgc2 = __ldg(v.bg + 2);
-    BwdPix Q[kPix];
+    BwdPix Q;
     int wmax = 0;
 #pragma unroll
-    for (int q = 0; q < kPix; q++) {
+    for (int q = 0; q < 4; q++) {
         const uint32_t py = pyb + 2 * q;
         const bool in = px < (uint32_t)v.W && py < (uint32_t)v.H;
         const uint32_t pix_id = (uint32_t)v.W * py + px;
-        BwdPix& p = Q[q];
         const float T_final = in ? final_Ts[pix_id] : 0.f;
-        p.T = T_final;
-        p.last_contributor = in ? (int)n_contrib[pix_id] : 0;
-        p.g0 = in ? dL_dpix[pix_id] : 0.f; p.g1 = in ? dL_dpix[HW + pix_id] : 0.f; p.g2 = in ? dL_dpix[2 * HW + pix_id] : 0.f;
+        GS_Q(Q.T, q) = T_final;
+        Q.last[q] = in ? (int)n_contrib[pix_id] : 0;
+        const float g0 = in ? dL_dpix[pix_id] : 0.f, g1 = in ? dL_dpix[HW + pix_id] : 0.f, g2 = in ? dL_dpix[2 * HW + pix_id] : 0.f;
+        GS_Q(Q.g0, q) = g0; GS_Q(Q.g1, q) = g1; GS_Q(Q.g2, q) = g2;
         float bd = 0.f;
-        bd += bgc0 * p.g0; bd += bgc1 * p.g1; bd += bgc2 * p.g2;
-        p.tb = -T_final * bd;
-        p.AR = 0.f;
-        wmax = max(wmax, p.last_contributor);
+        bd += bgc0 * g0; bd += bgc1 * g1; bd += bgc2 * g2;
+        GS_Q(Q.tb, q) = -T_final * bd;
+        GS_Q(Q.AR, q) = 0.f;
+        wmax = max(wmax, Q.last[q]);
     }
     const float ddelx_dx = 0.5 * v.W, ddely_dy = 0.5 * v.H;
 
@@ -349,56 +448,94 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
     const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
     const int slot = 5 * b4 + 3 * b3 + 2 * b2 + b1;
     const bool owner = ((lane & 1) == 0) && !(b3 && b2) && !(b3 == 0 && b2 && b1) && slot < 9;
+    float* const myAcc = sAcc[wid] + (owner ? slot : 0);
 
     for (int hi = maxc; hi > 0; hi -= kBatch) {
         __syncthreads();
         const int cnt = min(kBatch, hi);
         // slot j holds list position hi-1-j: reverse traversal = increasing j
         stage_batch(sRec, sMask, list, rec, beg, cnt, tx0, ty0, [&](int j) { return hi - 1 - j; });
-#pragma unroll
-        for (int h = 0; h < kBatch / kThreads; h++)
-#pragma unroll
-            for (int k = 0; k < 9; k++) sAcc[(tid + h * kThreads) * 9 + k] = 0.f;
         __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < kWords; k++) {
             uint32_t bits = sMask[wid][k];
+            uint32_t done = 0;
             while (bits) {
-                const int j = 32 * k + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int p = hi - 1 - j;        // 0-based list position
-                if (p >= wmax) continue;         // behind every pixel of this block
+                const int lz = __clz(bits);
+                const uint32_t bit = 0x80000000u >> lz;
+                bits &= ~bit;
+                const int j = 32 * k + lz;
+                const int pos = hi - 1 - j;      // 0-based list position
+                if (pos >= wmax) continue;       // behind every pixel of this block
                 const SRec& r = sRec[j];
                 const float dx = r.a.x - pixx;
+                const float2 dy[2] = {add2(bc(r.a.y), npy[0]), add2(bc(r.a.y), npy[1])};
+                float2 p[2], g[2], a[2], d[2];
+                const bool band = eval_alpha4(r, dx, dy, p, g, a, d);
                 float vv[9];
+                bool any;
+                if (band || r.generic) {
 #pragma unroll
-                for (int q = 0; q < 9; q++) vv[q] = 0.f;
-                float dy[kPix];
+                    for (int q = 0; q < 9; q++) vv[q] = 0.f;
+                    any = bwd_generic(Q, r, dx, dy, p, g, a, band, pos, rec, vv);
+                } else {
+                    // fast path: alpha = a (no clamp), ok <=> pos < last && d >= 0; a skipped pixel runs with alpha = 0,
+                    // which makes every update a no-op (T / 1 = T, AR + 0, zero weights)
+                    float2 ae[2];
+                    ae[0].x = (pos < Q.last[0] && d[0].x >= 0.f) ? a[0].x : 0.f;
+                    ae[0].y = (pos < Q.last[1] && d[0].y >= 0.f) ? a[0].y : 0.f;
+                    ae[1].x = (pos < Q.last[2] && d[1].x >= 0.f) ? a[1].x : 0.f;
+                    ae[1].y = (pos < Q.last[3] && d[1].y >= 0.f) ? a[1].y : 0.f;
+                    any = (__float_as_uint(ae[0].x) | __float_as_uint(ae[0].y) | __float_as_uint(ae[1].x) |
+                           __float_as_uint(ae[1].y)) != 0u;
+                    float2 c0 = bc(0.f), c1 = bc(0.f), c2 = bc(0.f), s0 = bc(0.f), sy = bc(0.f), syy = bc(0.f);
 #pragma unroll
-                for (int q = 0; q < kPix; q++) dy[q] = r.a.y - (float)(pyb + 2 * q);
-                const bool any = bwd_eval4(Q, r, dx, dy, p, vv);
+                    for (int h = 0; h < 2; h++) {
+                        const float2 om = fma2(ae[h], bc(-1.f), bc(1.f));                     // 1 - alpha
+                        const float2 inv = make_float2(rcp_approx(om.x), rcp_approx(om.y));
+                        Q.T[h] = mul2(Q.T[h], inv);                                           // T of the splats in front
+                        const float2 cg = fma2(bc(r.c.x), Q.g2[h], fma2(bc(r.b.w), Q.g1[h], mul2(bc(r.b.z), Q.g0[h])));
+                        const float2 dcol = fma2(Q.AR[h], bc(-1.f), cg);                      // cg - AR
+                        Q.AR[h] = fma2(ae[h], dcol, Q.AR[h]);
+                        const float2 dch = mul2(ae[h], Q.T[h]);                               // dchannel_dcolor
+                        c0 = fma2(dch, Q.g0[h], c0); c1 = fma2(dch, Q.g1[h], c1); c2 = fma2(dch, Q.g2[h], c2);
+                        const float2 dLda = fma2(dcol, Q.T[h], mul2(Q.tb[h], inv));           // dL_dalpha
+                        const float2 wq = mul2(ae[h], dLda);                                  // opacity G dL_dalpha
+                        s0 = add2(s0, wq);
+                        const float2 t = mul2(wq, dy[h]);
+                        sy = add2(sy, t);
+                        syy = fma2(t, dy[h], syy);
+                    }
+                    vv[0] = c0.x + c0.y; vv[1] = c1.x + c1.y; vv[2] = c2.x + c2.y;
+                    const float S0 = s0.x + s0.y, SY = sy.x + sy.y;
+                    vv[3] = S0; vv[4] = dx * S0; vv[5] = SY;
+                    vv[6] = dx * vv[4]; vv[7] = dx * SY; vv[8] = syy.x + syy.y;
+                }
                 if (!__any_sync(0xffffffffu, any)) continue;
                 warp_reduce9(vv, lane);
-                if (owner) atomicAdd(&sAcc[j * 9 + slot], vv[0]);
+                if (owner) myAcc[j * 9] = vv[0];
+                done |= bit;
             }
+            if (lane == 0) sDone[wid][k] = done;
         }
         __syncthreads();
 #pragma unroll
         for (int h = 0; h < kBatch / kThreads; h++) {
             const int j = tid + h * kThreads;
             if (j < cnt) {
-                float r[9];
-                bool any = false;
+                const uint32_t bit = 0x80000000u >> (j & 31);
+                const bool d0 = (sDone[0][j >> 5] & bit) != 0u, d1 = (sDone[1][j >> 5] & bit) != 0u;
+                if (d0 || d1) {
+                    float r[9];
 #pragma unroll
-                for (int k = 0; k < 9; k++) { r[k] = sAcc[j * 9 + k]; any = any || (r[k] != 0.f); }
-                if (any) {
+                    for (int k = 0; k < 9; k++) r[k] = (d0 ? sAcc[0][j * 9 + k] : 0.f) + (d1 ? sAcc[1][j * 9 + k] : 0.f);
                     float4* dst = acc + (size_t)3 * sRec[j].id;
-                    // r[3..8] = sums of g, g dx, g dy, g dx dx, g dx dy, g dy dy (g = G dL_dalpha) over the tile
+                    // r[3..8] = sums of w, w dx, w dy, w dx dx, w dx dy, w dy dy (w = opacity G dL_dalpha) over the tile
                     const SRec& sr = sRec[j];
-                    const float A = sr.a.z * kUnscale, B = sr.a.w * (0.5f * kUnscale), C = sr.b.x * kUnscale, o = sr.b.y;
-                    const float kx = o * r[4], ky = o * r[5], h = -0.5f * o;
-                    atomicAdd(dst, make_float4(-(A * kx + B * ky) * ddelx_dx, -(C * ky + B * kx) * ddely_dy, h * r[6], h * r[7]));
-                    atomicAdd(dst + 1, make_float4(h * r[8], r[3], r[0], r[1]));
+                    const float A = sr.a.z * kUnscale, B = sr.a.w * (0.5f * kUnscale), C = sr.b.x * kUnscale;
+                    const float kx = r[4], ky = r[5], hf = -0.5f;
+                    atomicAdd(dst, make_float4(-(A * kx + B * ky) * ddelx_dx, -(C * ky + B * kx) * ddely_dy, hf * r[6], hf * r[7]));
+                    atomicAdd(dst + 1, make_float4(hf * r[8], r[3] * rcp_approx(sr.b.y), r[0], r[1]));
                     atomicAdd(reinterpret_cast<float*>(dst + 2), r[2]);
                 }
             }
@@ -408,9 +545,12 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
 
 }  // namespace
 
+int g_gs_blend_variant = 0;           // GS_BLEND_VARIANT=1 selects the round-1 kernels (A/B measurements only)
+
 void gs_launch_blend_fwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const GsDevStatus* status, long long capacity, float* final_T, uint32_t* n_contrib,
                          float* out_color, float* out_depth, cudaStream_t s) {
+    if (g_gs_blend_variant == 1) { gs_launch_blend_fwd_r1(v, tile_off, list, rec, status, capacity, final_T, n_contrib, out_color, out_depth, s); return; }
     dim3 grid(v.gx, v.gy);
     k_blend_fwd<<<grid, kThreads, 0, s>>>(v, tile_off, list, rec, status, capacity, final_T, n_contrib, out_color,
                                           out_depth);
@@ -418,6 +558,7 @@ void gs_launch_blend_fwd(const GsView& v, const uint32_t* tile_off, const uint32
 void gs_launch_blend_bwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float4* acc,
                          cudaStream_t s) {
+    if (g_gs_blend_variant == 1) { gs_launch_blend_bwd_r1(v, tile_off, list, rec, final_T, n_contrib, dL_dpix, acc, s); return; }
     dim3 grid(v.gx, v.gy);
     k_blend_bwd<<<grid, kThreads, 0, s>>>(v, tile_off, list, rec, final_T, n_contrib, dL_dpix, acc);
 }

@@ -256,6 +256,9 @@ __device__ __forceinline__ void gs_sh_basis(int deg, float x, float y, float z, 
 // "max power >= thr" is a conservative superset of "some pixel has alpha >= 1/255".  NaNs answer true (keep).
 __device__ __forceinline__ bool gs_box_hit(float mx, float my, float A, float B, float C, float thr, float x0,
                                            float y0, float x1, float y1) {
+    // the edge maximisation below needs a concave power(): a conic that is not positive definite (fp32 cancellation
+    // on huge anisotropic splats, a non-PSD cov3D_precomp) is never culled
+    if (!(A > 0.f && C > 0.f && A * C - B * B > 0.f)) return true;
     const bool in_x = mx >= x0 && mx <= x1, in_y = my >= y0 && my <= y1;
     if (in_x && in_y) return !(thr > 0.f);
     float best = -3.0e38f;
@@ -303,6 +306,13 @@ void gs_launch_blend_fwd(const GsView& v, const uint32_t* tile_off, const uint32
 void gs_launch_blend_bwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float4* acc,
                          cudaStream_t s);
+extern int g_gs_blend_variant;
+void gs_launch_blend_fwd_r1(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
+                            const GsDevStatus* status, long long capacity, float* final_T, uint32_t* n_contrib,
+                            float* out_color, float* out_depth, cudaStream_t s);
+void gs_launch_blend_bwd_r1(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
+                            const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float4* acc,
+                            cudaStream_t s);
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
                         const uint32_t* vis_list, const GsDevStatus* status, float* gout, cudaStream_t s);

@@ -229,6 +229,19 @@ __device__ __forceinline__ void cta_store_rows(float* __restrict__ dst, const fl
     }
 }
 
+// zeroes rows [row0, row0 + kT) of a dense [P, nf] tensor (nf floats per row); kT * nf is a multiple of 4
+__device__ __forceinline__ void cta_zero_run(float* __restrict__ base, long long row0, int nf) {
+    if (!base || nf <= 0) return;
+    float* p = base + row0 * nf;
+    const int total = kT * nf;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int f = threadIdx.x; f < (total >> 2); f += kT) reinterpret_cast<float4*>(p)[f] = z4;
+    } else {
+        for (int f = threadIdx.x; f < total; f += kT) p[f] = 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(kT)
 k_grad_write(const int P, const int M, const int* __restrict__ radii, const float4* __restrict__ acc,
              const float* __restrict__ gout, const GsGradPtrs g) {
@@ -258,6 +271,15 @@ k_grad_write(const int P, const int M, const int* __restrict__ radii, const floa
         for (int k = 0; k < kRow / 4; k++) dstr[k] = __ldg(src + k);
     }
     __syncthreads();
+    if (s_count == 0 && row0 + kT <= P) {
+        // no visible row in this CTA (the common case when only a few per cent of the Gaussians are on screen):
+        // the 256 rows of every output are one contiguous run -> straight 128-bit zero stores, no index maths
+        const int M3z = g.dsh ? M * 3 : 0;
+        cta_zero_run(g.dmeans3D, row0, 3); cta_zero_run(g.dmeans2D, row0, 3); cta_zero_run(g.dscales, row0, 3);
+        cta_zero_run(g.dcolors, row0, 3);  cta_zero_run(g.dcov3D, row0, 6);   cta_zero_run(g.dopacity, row0, 1);
+        cta_zero_run(g.drots, row0, 4);    cta_zero_run(g.dsh, row0, M3z);
+        return;
+    }
     if (g.dmeans3D) cta_store_rows<3>(g.dmeans3D, s_row, s_slot, 0, row0, P);
     if (g.dmeans2D) {
         const long long base = row0 * 3, lim = (long long)P * 3;

@@ -22,6 +22,7 @@ at::Tensor prep(const c10::optional<at::Tensor>& t, const at::Device& dev, std::
     at::Tensor x = *t;
     if (x.device() != dev || x.scalar_type() != at::kFloat) x = x.to(dev, at::kFloat);
     x = x.contiguous();
+    if (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) x = x.clone();   // 128-bit loads in the kernels (gsraster.h)
     keep.push_back(x);
     return x;
 }

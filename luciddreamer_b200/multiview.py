@@ -137,6 +137,8 @@ def allreduce_bucket(bucket: GradBucket, group=None, average: bool = False, asyn
     """Sum (or mean) of the per-rank gradient buckets: the only collective of a shared-model step."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
+    if average and async_op:
+        raise ValueError("allreduce_bucket: average=True needs the result; divide after work.wait() when async_op=True")
     work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
     if average and not async_op:
         bucket.flat.div_(dist.get_world_size(group))

@@ -80,6 +80,7 @@ class FusedGaussianAdam:
             ("rotation", grads.rotations, P, 4, 4, 0, 3),
         ]
         dev = self.params["xyz"].device
+        spec = [s for s in spec if s[2] * s[3] > 0]        # an SH-degree-0 model (M = 1) has an empty f_rest group
         for k, (name, gt, rows, rw, grw, goff, act) in enumerate(spec):
             if not (gt.is_cuda and gt.dtype == torch.float32 and gt.is_contiguous() and gt.device == dev):
                 raise RuntimeError(f"gradient for {name} must be a contiguous float32 tensor on {dev}")
@@ -91,6 +92,6 @@ class FusedGaussianAdam:
         self.step_count += 1
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         with R._guard(idx):
-            N.check(N.lib().gs_gaussian_adam_step(R._ctx(idx), groups, 6, float(self.betas[0]), float(self.betas[1]),
+            N.check(N.lib().gs_gaussian_adam_step(R._ctx(idx), groups, len(spec), float(self.betas[0]), float(self.betas[1]),
                                                   float(self.eps), self.step_count,
                                                   R._raw_stream(idx)))

@@ -27,7 +27,17 @@ from . import _native as N
 # ---------------------------------------------------------------------------------------------- plumbing
 
 _contexts: dict = {}      # device index -> GsContext*
-_cap_hint: dict = {}      # device index -> last (tile, Gaussian) pair count seen
+_cap_hint: dict = {}      # device index -> decayed maximum of the (tile, Gaussian) pair counts seen
+_last_pairs: dict = {}    # device index -> pair count of the most recent forward (statistics only)
+_HINT_DECAY = 0.97        # per forward; a training loop that draws a random camera per iteration (luciddreamer.py:
+                          # 291-292) keeps the capacity of its largest view instead of re-rendering whenever a view
+                          # has > 25 % more pairs than the previous one
+
+
+def _note_pairs(idx: int, pairs: int) -> None:
+    prev = _cap_hint.get(idx, 0)
+    _cap_hint[idx] = max(int(pairs), int(prev * _HINT_DECAY))
+    _last_pairs[idx] = int(pairs)
 
 
 def _ctx(dev_index: int) -> C.c_void_p:
@@ -97,7 +107,10 @@ def _dev_f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
         return None
     if t.device != device or t.dtype != torch.float32:
         t = t.to(device=device, dtype=torch.float32)
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() & 15:            # a view at an odd storage offset: the kernels use 128-bit loads (gsraster.h)
+        t = t.clone()
+    return t
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -176,7 +189,7 @@ def _forward_impl(prep: _Prepared):
                 binning = torch.empty((L.gs_binning_bytes(cap),), **u8)
                 N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
                                             cap, img.data_ptr(), color.data_ptr(), depth.data_ptr(), 1, stream))
-        _cap_hint[idx] = int(counts.num_pairs)
+        _note_pairs(idx, counts.num_pairs)
     return int(counts.num_rendered), color, depth, radii, geom, binning, img, (cap, int(counts.num_visible))
 
 
@@ -196,6 +209,8 @@ def _backward_impl(prep: _Prepared, radii, geom, binning, img, cap, grad_color, 
         f32 = dict(dtype=torch.float32, device=dev)
         # the tile pass goes to the GPU first; allocations below overlap with it
         gc = _dev_f32(grad_color, dev)
+        if gc is None or gc.numel() != 3 * f.H * f.W:
+            raise RuntimeError(f"dL_dout_color must hold 3 x {f.H} x {f.W} values")   # k_blend_bwd reads exactly that many
         N.check(L.gs_backward_blend(_ctx(idx), C.byref(f), geom.data_ptr(), binning.data_ptr(), cap, img.data_ptr(),
                                     _p(gc), stream))
         g = N.GsGrads()
@@ -250,6 +265,8 @@ def _backward_peers(prep: _Prepared, radii, geom, binning, img, cap, grad_color,
         dm2 = out.get("dm2")
         if dm2 is None:
             dm2 = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        elif tuple(dm2.shape) != (P, 3) or dm2.dtype != torch.float32 or not dm2.is_contiguous() or dm2.device != dev:
+            raise RuntimeError(f"gradient sink 'dm2' must be a contiguous f32 {(P, 3)} tensor on {dev}")
         g = N.GsGrads()
         g.dL_dmeans2D = dm2.data_ptr()
         world = int(peers["world"])
@@ -260,6 +277,8 @@ def _backward_peers(prep: _Prepared, radii, geom, binning, img, cap, grad_color,
         g.peer_multicast = int(peers.get("mc") or 0) or None
         g.peer_seg_off = C.cast(seg, C.POINTER(C.c_int64))
         gc = _dev_f32(grad_color, dev)
+        if gc is None or gc.numel() != 3 * f.H * f.W:
+            raise RuntimeError(f"dL_dout_color must hold 3 x {f.H} x {f.W} values")
         nscr = L.gs_backward_scratch_bytes(nvis)
         scratch = torch.empty((nscr,), dtype=torch.uint8, device=dev)
         N.check(L.gs_backward(_ctx(idx), C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
@@ -337,7 +356,7 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
             means3D, _t(means2D), _t(sh), _t(colors_precomp), _t(opacities), _t(scales), _t(rotations), _t(cov3Ds_precomp),
             rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, _ctx(idx).value, rs.scale_modifier, rs.tanfovx, rs.tanfovy,
             rs.image_height, rs.image_width, rs.sh_degree, bool(rs.prefiltered), bool(rs.debug), -1 if hint is None else hint)
-        _cap_hint[idx] = fast.last_pairs(idx)
+        _note_pairs(idx, fast.last_pairs(idx))
         return color, radii, depth
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                      cov3Ds_precomp, raster_settings)
@@ -362,7 +381,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ctx(idx).value, rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
                 cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
                 rs.sh_degree, rs.campos, bool(rs.prefiltered), bool(rs.debug), -1 if hint is None else hint)
-            _cap_hint[idx] = npairs
+            _note_pairs(idx, npairs)
             ctx.num_rendered = num_rendered
             ctx.pair_capacity = (cap, nvis)
             ctx.prep = None

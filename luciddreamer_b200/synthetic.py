@@ -104,13 +104,16 @@ def llff_poses(n_frames: int = 400, max_deg: float = 5.0, radius: float = 0.15) 
     return out
 
 
-def make_scene(P: int, seed: int, M: int = 16, scale_mult: float = 1.0) -> Dict[str, torch.Tensor]:
+def make_scene(P: int, seed: int, M: int = 16, scale_mult: float = 1.0, opacity_shift: float = 0.0,
+               aniso_sigma: float = 0.3) -> Dict[str, torch.Tensor]:
     """Shell of Gaussians around the origin.  All tensors CPU float32, contiguous.
 
     means3D   direction = normalise(N(0,I)); radius rho = exp(U(ln1, ln8))
     scales    rho * (1.5/582.69) * exp(N(0,.5^2)) * exp(N(0,.3^2) per axis)   (post-exp, as get_scaling)
     rotations normalise(N(0,I4))       opacities sigmoid(N(0,2^2))  [P,1]
     shs       [P,M,3]: DC (U(0,1)-.5)/0.28209479, rest N(0,.05^2)
+    opacity_shift (added to the logit) and aniso_sigma (per-axis log-normal spread) only rescale the same random
+    draws: the defaults reproduce the scenes the golden fixtures were generated from.
     """
     g = torch.Generator().manual_seed(int(seed))
     d = torch.randn(P, 3, generator=g)
@@ -118,14 +121,60 @@ def make_scene(P: int, seed: int, M: int = 16, scale_mult: float = 1.0) -> Dict[
     rho = torch.exp(torch.rand(P, 1, generator=g) * math.log(8.0))
     means = (d * rho).contiguous()
     iso = torch.exp(torch.randn(P, 1, generator=g) * 0.5)
-    aniso = torch.exp(torch.randn(P, 3, generator=g) * 0.3)
+    aniso = torch.exp(torch.randn(P, 3, generator=g) * aniso_sigma)
     scales = (rho * (1.5 / REF_FOCAL) * iso * aniso * scale_mult).contiguous()
+    q = torch.randn(P, 4, generator=g)
+    rots = (q / q.norm(dim=1, keepdim=True).clamp_min(1e-12)).contiguous()
+    opac = torch.sigmoid(torch.randn(P, 1, generator=g) * 2.0 + opacity_shift).contiguous()
+    shs = torch.randn(P, M, 3, generator=g) * 0.05
+    shs[:, 0, :] = (torch.rand(P, 3, generator=g) - 0.5) / 0.28209479177387814
+    return {"means3D": means, "scales": scales, "rotations": rots, "opacities": opac, "shs": shs.contiguous()}
+
+
+def make_frustum_scene(P: int, seed: int, W: int, H: int, M: int = 16, sigma_px: float = 1.0, fovx: float = REF_FOVX,
+                       margin: float = 0.95) -> Dict[str, torch.Tensor]:
+    """LucidDreamer-shaped population: what the reference's optimisation loop actually renders (luciddreamer.py:
+    283-327).  Its Gaussians come from depth maps re-projected through the training cameras (luciddreamer.py:370-374,
+    492; one point per pixel and view), so nearly ALL of them are inside the frustum of a training view, about one
+    pixel in size (initial scale = nearest-neighbour spacing, scene/gaussian_model.py:136-137), at 512x512
+    (arguments.py:42).  Here: image-plane position uniform over `margin` of the identity camera's view, depth
+    exp(U(ln 1, ln 8)), world sigma = sigma_px pixels at that depth times exp(N(0,.3^2)) (and per axis), everything else
+    as make_scene.  CPU float32, contiguous, bit-reproducible from the seed."""
+    g = torch.Generator().manual_seed(int(seed))
+    fovy = 2.0 * math.atan(math.tan(fovx / 2) * H / W)
+    tx, ty = math.tan(fovx / 2), math.tan(fovy / 2)
+    uv = (torch.rand(P, 2, generator=g) * 2.0 - 1.0) * margin
+    z = torch.exp(torch.rand(P, 1, generator=g) * math.log(8.0))
+    means = torch.cat([uv[:, :1] * tx * z, uv[:, 1:] * ty * z, z], 1).contiguous()
+    focal_px = W / (2.0 * tx)
+    iso = torch.exp(torch.randn(P, 1, generator=g) * 0.3)
+    aniso = torch.exp(torch.randn(P, 3, generator=g) * 0.3)
+    scales = (z * (sigma_px / focal_px) * iso * aniso).contiguous()
     q = torch.randn(P, 4, generator=g)
     rots = (q / q.norm(dim=1, keepdim=True).clamp_min(1e-12)).contiguous()
     opac = torch.sigmoid(torch.randn(P, 1, generator=g) * 2.0).contiguous()
     shs = torch.randn(P, M, 3, generator=g) * 0.05
     shs[:, 0, :] = (torch.rand(P, 3, generator=g) - 0.5) / 0.28209479177387814
     return {"means3D": means, "scales": scales, "rotations": rots, "opacities": opac, "shs": shs.contiguous()}
+
+
+def jitter_poses(n: int, seed: int, max_deg: float = 3.0, max_shift: float = 0.05) -> np.ndarray:
+    """n camera poses scattered around the identity pose (small yaw / pitch and translation), the way the reference's
+    training views scatter around each generation pose (5 hemisphere jitters per pose, luciddreamer.py:516-518;
+    one of them is drawn at random per iteration, luciddreamer.py:291-292).  [n,4,4] COLMAP-convention c2w."""
+    rng = np.random.RandomState(int(seed))
+    out = np.zeros((n, 4, 4))
+    for i in range(n):
+        yaw, pitch = np.radians(rng.uniform(-max_deg, max_deg, 2))
+        cy, sy, cp, sp = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch)
+        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+        M = np.eye(4)
+        M[:3, :3] = Ry @ Rx
+        M[:3, 3] = rng.uniform(-max_shift, max_shift, 3)
+        out[i] = M
+    out[0] = np.eye(4)
+    return out
 
 
 def make_cotangent(H: int, W: int, seed: int) -> torch.Tensor:

@@ -25,6 +25,9 @@ class Case(NamedTuple):
     precomp: bool = False       # feed colors_precomp + cov3D_precomp instead of shs + scales/rotations
     pose: Optional[str] = None  # None = identity; "rot:<deg>" = yaw about the vertical axis; "llff:<frame>"
     golden: bool = True         # has a fixture under tests/golden/
+    opacity_shift: float = 0.0  # added to the opacity logits (same random draws)
+    aniso_sigma: float = 0.3    # log-normal spread of the per-axis scale factors (same random draws)
+    scene: str = "shell"        # "shell"  or "frustum" (LucidDreamer-shaped, synthetic.make_frustum_scene)
 
 
 CASES = [
@@ -38,12 +41,30 @@ CASES = [
     Case("llff_5k_128x72", 5000, 128, 72, 3, 17, scale_mult=2.0, pose="llff:37"),
     Case("cfg2_100k_512", 100_000, 512, 512, 3, 1002),
 ]
-BY_NAME = {c.name: c for c in CASES}
+# oracle-only cases (no reference fixture): the branches the shell scenes hardly reach
+EXTRA_CASES = [
+    # opacities pushed towards 1 (a third above the 0.99 clamp of forward.cu:343), thick stacks of large splats: early
+    # termination at T < 1e-4 (forward.cu:348-352) on most pixels, generic (non fast-path) evaluation of the clamped ones
+    Case("opaque_40k_64_x8", 40_000, 64, 64, 3, 21, scale_mult=8.0, opacity_shift=4.0, golden=False),
+    # needle-shaped splats: ill-conditioned 2-D conics -> generic path via the conditioning test, huge tile rectangles
+    Case("needles_2k_96", 2000, 96, 96, 2, 22, scale_mult=3.0, aniso_sigma=2.5, golden=False),
+    # LucidDreamer-shaped: everything inside the frustum, ~1.5 px sigma, long tile lists, termination
+    Case("frustum_20k_96", 20_000, 96, 96, 3, 23, golden=False, scene="frustum"),
+    Case("frustum_60k_64_bg", 60_000, 64, 64, 1, 24, bg=(0.2, 0.5, 0.1), opacity_shift=1.0, golden=False, scene="frustum"),
+]
+CASES_ALL = CASES + EXTRA_CASES
+BY_NAME = {c.name: c for c in CASES_ALL}
 
 
 def build_inputs(case: Case) -> Dict[str, object]:
     """CPU float32 tensors + camera in the reference binding's vocabulary."""
-    sc = syn.make_scene(case.P, case.seed, scale_mult=case.scale_mult)
+    if case.scene == "frustum":
+        sc = syn.make_frustum_scene(case.P, case.seed, case.W, case.H, sigma_px=1.5)
+        if case.opacity_shift:
+            sc["opacities"] = torch.sigmoid(torch.logit(sc["opacities"]) + case.opacity_shift).contiguous()
+    else:
+        sc = syn.make_scene(case.P, case.seed, scale_mult=case.scale_mult, opacity_shift=case.opacity_shift,
+                            aniso_sigma=case.aniso_sigma)
     c2w = None
     swap = False
     if case.pose:

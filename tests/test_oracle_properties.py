@@ -161,3 +161,50 @@ def test_backward_matches_finite_differences_f64(param, col):
         if abs(fd - an) <= 2e-4 * max(1.0, abs(an), abs(fd)):
             checked += 1
     assert checked >= 9, f"only {checked}/12 finite-difference probes of {param} agree"
+
+
+def test_flip_audit_replay_is_faithful():
+    """tests/flip_audit.py replays single pixels from the oracle's state; its final T must be the oracle's, and a
+    synthetic "flip" (a pixel perturbed by more than the tolerance) with no operand near a threshold must be
+    reported as unexplained."""
+    import flip_audit
+    case = cases.BY_NAME["opaque_40k_64_x8"]
+    inp = cases.build_inputs(case)
+    f = _fwd(inp, "f32")
+    fT = f.final_T
+    rng = np.random.RandomState(0)
+    for _ in range(40):
+        x, y = int(rng.randint(case.W)), int(rng.randint(case.H))
+        m = flip_audit.pixel_margins(f, x, y)
+        assert abs(m["final_T"] - float(fT[y, x])) <= 1e-5 * max(float(fT[y, x]), 1e-4) + 1e-9
+    bad = f.color.copy()
+    # pick a pixel whose margins are all wide, perturb it: the audit must refuse to explain it
+    for y in range(case.H):
+        for x in range(case.W):
+            m = flip_audit.pixel_margins(f, x, y)
+            if min(m["alpha"], m["T"], m["acc"], m["power"]) > 1e-2:
+                bad[0, y, x] += 1e-2
+                ex, un = flip_audit.explain_outliers(f, bad, f.depth, f.color, f.depth)
+                assert len(un) == 1 and not ex and un[0][:2] == (x, y)
+                return
+    raise AssertionError("no wide-margin pixel found")
+
+
+@pytest.mark.parametrize("name", [c.name for c in cases.EXTRA_CASES])
+def test_extra_cases_reach_their_branches(name):
+    """The oracle-only cases exist to reach early termination, the 0.99 clamp, ill-conditioned conics and long
+    tile lists; make sure the scenes really do (otherwise the GPU parity tests on them prove nothing)."""
+    case = cases.BY_NAME[name]
+    inp = cases.build_inputs(case)
+    f = _fwd(inp, "f32")
+    rg = f.ranges
+    longest = int((rg[:, 1].astype(np.int64) - rg[:, 0].astype(np.int64)).max())
+    terminated = float((f.final_T < 1e-3).mean())
+    if name.startswith("opaque"):
+        assert terminated > 0.5 and float((inp["opacities"] > 0.99).float().mean()) > 0.2
+    elif name.startswith("needles"):
+        co = f.geom("conic_opacity", 4)[f.radii > 0].astype(np.float64)
+        det, tr = co[:, 0] * co[:, 2] - co[:, 1] ** 2, co[:, 0] + co[:, 2]
+        assert (det < 1e-5 * tr * tr).mean() > 0.02          # the blend kernels' conditioning test routes these
+    else:
+        assert terminated > 0.5 and longest > 1500

@@ -29,10 +29,12 @@ def rel_err(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-def assert_forward_close(color, depth, radii, gold, what=""):
+def assert_forward_close(color, depth, radii, gold, what="", audit=None):
     """Colour/depth within 1e-4 abs.  Discontinuities (alpha<1/255, T<1e-4, the
     acc>0.5 depth gate) may flip for isolated pixels when two implementations differ in the last ulp; those
-    are counted and bounded instead of hidden: at most 1 pixel in 20 000 may exceed the tolerance."""
+    are counted and bounded instead of hidden: at most 1 pixel in 20 000 may exceed the tolerance, and -- when the
+    oracle's forward state is passed as `audit` -- every one of them must be ATTRIBUTED to a branch operand sitting on
+    its threshold (tests/flip_audit.py); an unexplained outlier fails."""
     color = np.asarray(color); depth = np.asarray(depth)
     dc = np.abs(color - gold["color"]).max(axis=0)
     dd = np.abs(depth - gold["depth"]).reshape(dc.shape)
@@ -40,6 +42,11 @@ def assert_forward_close(color, depth, radii, gold, what=""):
     bad_c, bad_d = int((dc > FWD_ABS_TOL).sum()), int((dd > FWD_ABS_TOL).sum())
     assert bad_c <= n // 20000, f"{what}: {bad_c}/{n} pixels off by > {FWD_ABS_TOL} in colour (max {dc.max():.3e})"
     assert bad_d <= n // 20000, f"{what}: {bad_d}/{n} pixels off by > {FWD_ABS_TOL} in depth (max {dd.max():.3e})"
+    if audit is not None and (bad_c or bad_d):
+        import flip_audit
+        explained, unexplained = flip_audit.explain_outliers(audit, color, depth, gold["color"], gold["depth"], FWD_ABS_TOL)
+        print(f"[flip audit] {what}: {len(explained)} outlier pixel(s) attributed to branch flips: {explained}")
+        assert not unexplained, f"{what}: outliers with no branch operand near a threshold: {unexplained}"
     mism = int((np.asarray(radii) != gold["radii"]).sum())
     assert mism <= max(0, len(gold["radii"]) // 50000), f"{what}: {mism} radii differ"
     return dict(max_color=float(dc.max()), max_depth=float(dd.max()), flips_color=bad_c, flips_depth=bad_d,
