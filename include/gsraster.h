@@ -130,7 +130,9 @@ size_t gs_binning_bytes(int64_t pair_capacity);
 int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, void* image_buffer, int32_t* radii,
                           gs_stream_t stream, int32_t* ticket);
 
-/* Blocks the host until the preprocess of `ticket` has finished (event wait; later work keeps running). */
+/* Blocks the host until the preprocess of `ticket` has finished (event wait; later work keeps running).
+ * A context keeps 64 status slots: a ticket whose slot has been handed out again (more than 64 forwards enqueued on
+ * the context since) is rejected with GS_EINVAL instead of returning another forward's counts. */
 int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out);
 
 /* replaces the second half of Rasterizer::forward (rasterizer_impl.cu:284-338).
@@ -140,6 +142,36 @@ int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out);
 int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, void* geom_buffer, void* binning_buffer,
                       int64_t pair_capacity, void* image_buffer, float* out_color, float* out_depth,
                       int32_t rerender, gs_stream_t stream);
+
+/* Batched forward (SURVEY.md 8b "batched variants (n_views, arrays of camera structs)", 8e ">= 2 views in flight"):
+ * renders n_views frames (normally the same Gaussians under different cameras: the reference's render_video loop,
+ * luciddreamer.py:250-262, or the views of one optimisation step) with up to n_streams views IN FLIGHT on internal
+ * streams of the context, forked from and joined back into `stream`.  The reference renders views one by one on
+ * the legacy default stream and blocks the host once per view (rasterizer_impl.cu:282); here nothing blocks until
+ * every view is enqueued, then the call collects the counts of all views.
+ *   scratch[s], s < n_streams (<= 8): geometry / image / binning buffers (+ radii) shared by the views that run on
+ *   internal stream s (view k runs on stream k % n_streams; views of one stream are ordered, so they may share).
+ *   results[k].out_color / out_depth: per-view outputs ([3,H,W] / [1,H,W]); radii optional (NULL: scratch radii).
+ *   results[k].counts and .status are filled on return: GS_OK, or GS_ECAPACITY when the view had more pairs than
+ *   scratch[k % n_streams].pair_capacity -- its outputs are then undefined and the caller re-renders that view with
+ *   a larger buffer (gs_forward_preprocess / gs_forward_render).  Returns GS_ECAPACITY if any view overflowed. */
+typedef struct GsViewScratch {
+    void* geom_buffer;      /* gs_geom_bytes(P) */
+    void* image_buffer;     /* gs_image_bytes(W, H) */
+    void* binning_buffer;   /* gs_binning_bytes(pair_capacity) */
+    int64_t pair_capacity;
+    int32_t* radii;         /* [P] */
+} GsViewScratch;
+typedef struct GsViewResult {
+    float* out_color;       /* in: [3,H,W] */
+    float* out_depth;       /* in: [1,H,W] */
+    int32_t* radii;         /* in: [P] or NULL */
+    GsCounts counts;        /* out */
+    int32_t status;         /* out */
+    int32_t pad;
+} GsViewResult;
+int gs_forward_views(GsContext* ctx, const GsFrame* frames, int32_t n_views, const GsViewScratch* scratch,
+                     int32_t n_streams, GsViewResult* results, gs_stream_t stream);
 
 /* replaces Rasterizer::backward (rasterizer_impl.cu:343-444) + the nine torch::zeros of its binding.
  * dL_dout_depth is accepted and ignored: the reference's depth gradient is commented out

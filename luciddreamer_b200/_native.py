@@ -43,6 +43,16 @@ class GsCounts(C.Structure):
     _fields_ = [("num_rendered", C.c_int64), ("num_pairs", C.c_int64), ("num_visible", C.c_int64)]
 
 
+class GsViewScratch(C.Structure):
+    _fields_ = [("geom_buffer", C.c_void_p), ("image_buffer", C.c_void_p), ("binning_buffer", C.c_void_p),
+                ("pair_capacity", C.c_int64), ("radii", C.c_void_p)]
+
+
+class GsViewResult(C.Structure):
+    _fields_ = [("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("radii", C.c_void_p), ("counts", GsCounts),
+                ("status", C.c_int32), ("pad", C.c_int32)]
+
+
 # every symbol include/gsraster.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("gs_abi_version", C.c_int, []),
@@ -57,6 +67,8 @@ SYMBOLS = [
     ("gs_forward_counts", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GsCounts)]),
     ("gs_forward_render", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    ("gs_forward_views", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_int32, C.POINTER(GsViewScratch), C.c_int32,
+                                   C.POINTER(GsViewResult), C.c_void_p]),
     ("gs_backward_scratch_bytes", C.c_size_t, [C.c_int64]),
     ("gs_backward", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(GsGrads),

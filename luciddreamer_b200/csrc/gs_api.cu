@@ -30,6 +30,7 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int kSlots = 64;
+constexpr int kMaxViewStreams = 8;
 
 int check_frame(const GsFrame* f) {
     if (!f) return fail(GS_EINVAL, "frame is NULL");
@@ -93,7 +94,11 @@ struct GsContext {
     bool pev_used[kNumKernels];
     GsDevStatus* slots;            // pinned, mapped
     cudaEvent_t events[kSlots];
+    unsigned slot_gen[kSlots];     // generation of the ticket that currently owns the slot
     std::atomic<unsigned> next;
+    cudaStream_t vstreams[kMaxViewStreams];   // internal streams of gs_forward_views (created on first use)
+    cudaEvent_t vfork, vjoin[kMaxViewStreams];
+    bool vstreams_ready;
 };
 
 // Brackets a launch with timing events on the launching stream when profiling is on (bench.py's roofline leg).
@@ -137,6 +142,8 @@ int gs_context_create(int device, GsContext** out) {
     c->device = device;
     c->next = 0;
     c->profile = 0;
+    c->vstreams_ready = false;
+    for (int i = 0; i < kSlots; i++) c->slot_gen[i] = 0;
     for (int i = 0; i < kNumKernels; i++) c->pev_used[i] = false;
     for (int i = 0; i < 2 * kNumKernels; i++) cudaEventCreate(&c->pev[i]);
     c->num_sms = 148;
@@ -172,6 +179,10 @@ void gs_context_destroy(GsContext* c) {
     if (!c) return;
     for (int i = 0; i < kSlots; i++) cudaEventDestroy(c->events[i]);
     for (int i = 0; i < 2 * kNumKernels; i++) cudaEventDestroy(c->pev[i]);
+    if (c->vstreams_ready) {
+        cudaEventDestroy(c->vfork);
+        for (int i = 0; i < kMaxViewStreams; i++) { cudaEventDestroy(c->vjoin[i]); cudaStreamDestroy(c->vstreams[i]); }
+    }
     cudaFreeHost(c->slots);
     delete c;
 }
@@ -190,8 +201,13 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     const GsView v = make_view(f);
     const int G = v.gx * v.gy;
     GsImageLayout il = gs_image_layout(image_buffer, f->W, f->H);
-    const int slot = (int)(ctx->next.fetch_add(1u) % (unsigned)kSlots);
+    const unsigned seq = ctx->next.fetch_add(1u);
+    const int slot = (int)(seq % (unsigned)kSlots);
+    const unsigned gen = (seq / (unsigned)kSlots) & 0x00ffffffu;
     GsDevStatus* host_slot = ctx->slots + slot;
+    // the slot's previous owner (64 forwards ago) must have written its status before the slot is cleared
+    if (seq >= (unsigned)kSlots) GS_CUDA(cudaEventSynchronize(ctx->events[slot]));
+    ctx->slot_gen[slot] = gen;
     host_slot->overflow = 0;                             // cleared; kernel writes 0xC0FFEE when done
     // zero tile histogram + status in one memset (they are adjacent)
     GS_CUDA(cudaMemsetAsync(il.tile_cnt, 0, (size_t)((char*)il.status - (char*)il.tile_cnt) + sizeof(GsDevStatus), s));
@@ -208,15 +224,21 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     GS_TIMED(ctx, 1, s, gs_launch_tile_scan(G, il.tile_cnt, il.tile_off, il.status, dev_slot, s));
     if ((rc = debug_sync(f, s, "tile_scan"))) return rc;
     GS_CUDA(cudaEventRecord(ctx->events[slot], s));
-    *ticket = slot;
+    *ticket = (int32_t)((gen << 6) | (unsigned)slot);     // slot in the low 6 bits, generation above
     return GS_OK;
 }
 
 int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out) {
-    if (!ctx || !out || ticket < 0 || ticket >= kSlots) return fail(GS_EINVAL, "bad ctx/ticket/out");
-    GS_CUDA(cudaEventSynchronize(ctx->events[ticket]));
-    const volatile GsDevStatus* h = ctx->slots + ticket;
-    if (h->overflow != 0xC0FFEEu) return fail(GS_ECUDA, "status slot %d was not written by the device", ticket);
+    if (!ctx || !out || ticket < 0) return fail(GS_EINVAL, "bad ctx/ticket/out");
+    const int slot = ticket & (kSlots - 1);
+    const unsigned gen = (unsigned)ticket >> 6;
+    if (ctx->slot_gen[slot] != gen)
+        return fail(GS_EINVAL, "ticket expired: more than %d forwards were enqueued on this context since", kSlots);
+    GS_CUDA(cudaEventSynchronize(ctx->events[slot]));
+    const volatile GsDevStatus* h = ctx->slots + slot;
+    if (ctx->slot_gen[slot] != gen)
+        return fail(GS_EINVAL, "ticket expired: more than %d forwards were enqueued on this context since", kSlots);
+    if (h->overflow != 0xC0FFEEu) return fail(GS_ECUDA, "status slot %d was not written by the device", slot);
     out->num_rendered = (int64_t)h->num_rendered;
     out->num_pairs = (int64_t)h->num_pairs;
     out->num_visible = (int64_t)h->num_visible;
@@ -258,6 +280,55 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
                                                 il.n_contrib, out_color, out_depth, s));
     if ((rc = debug_sync(f, s, "blend_fwd"))) return rc;
     return GS_OK;
+}
+
+int gs_forward_views(GsContext* ctx, const GsFrame* frames, int32_t n_views, const GsViewScratch* scratch,
+                     int32_t n_streams, GsViewResult* results, gs_stream_t stream) {
+    if (!ctx || !frames || !scratch || !results) return fail(GS_EINVAL, "NULL argument");
+    if (n_views < 0 || n_views > kSlots) return fail(GS_EINVAL, "n_views must be in [0, %d]", kSlots);
+    if (n_streams < 1 || n_streams > kMaxViewStreams) return fail(GS_EINVAL, "n_streams must be in [1, %d]", kMaxViewStreams);
+    if (n_views == 0) return GS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int prev = 0;
+    GS_CUDA(cudaGetDevice(&prev));
+    GS_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->vstreams_ready) {
+        GS_CUDA(cudaEventCreateWithFlags(&ctx->vfork, cudaEventDisableTiming));
+        for (int i = 0; i < kMaxViewStreams; i++) {
+            GS_CUDA(cudaStreamCreateWithFlags(&ctx->vstreams[i], cudaStreamNonBlocking));
+            GS_CUDA(cudaEventCreateWithFlags(&ctx->vjoin[i], cudaEventDisableTiming));
+        }
+        ctx->vstreams_ready = true;
+    }
+    const int ns = n_streams < n_views ? n_streams : n_views;
+    GS_CUDA(cudaEventRecord(ctx->vfork, s));                       // fork: the views start after the caller's work
+    for (int i = 0; i < ns; i++) GS_CUDA(cudaStreamWaitEvent(ctx->vstreams[i], ctx->vfork, 0));
+    int32_t tickets[kSlots];
+    int rc = GS_OK;
+    for (int k = 0; k < n_views && rc == GS_OK; k++) {
+        const GsViewScratch& sc = scratch[k % ns];
+        GsViewResult& r = results[k];
+        cudaStream_t vs = ctx->vstreams[k % ns];
+        int32_t* radii = r.radii ? r.radii : sc.radii;
+        r.status = GS_OK;
+        rc = gs_forward_preprocess(ctx, &frames[k], sc.geom_buffer, sc.image_buffer, radii, vs, &tickets[k]);
+        if (rc == GS_OK)       // speculative: the device-side capacity guard skips the render if the buffer is too small
+            rc = gs_forward_render(ctx, &frames[k], radii, sc.geom_buffer, sc.binning_buffer, sc.pair_capacity,
+                                   sc.image_buffer, r.out_color, r.out_depth, 0, vs);
+    }
+    for (int i = 0; i < ns; i++) {                                 // join, also on the error path
+        cudaEventRecord(ctx->vjoin[i], ctx->vstreams[i]);
+        cudaStreamWaitEvent(s, ctx->vjoin[i], 0);
+    }
+    cudaSetDevice(prev);
+    if (rc != GS_OK) return rc;
+    for (int k = 0; k < n_views; k++) {                            // only now does the host wait, once per view
+        const int rc2 = gs_forward_counts(ctx, tickets[k], &results[k].counts);
+        if (rc2 != GS_OK) return rc2;
+        if (results[k].counts.num_pairs > scratch[k % ns].pair_capacity) { results[k].status = GS_ECAPACITY; rc = GS_ECAPACITY; }
+    }
+    if (rc == GS_ECAPACITY) fail(GS_ECAPACITY, "at least one view needs a larger binning buffer (see results[].status)");
+    return rc;
 }
 
 size_t gs_backward_scratch_bytes(int64_t num_visible) {

@@ -106,3 +106,31 @@ def test_colorize_shape_background_and_monotone_hue():
     lut = video.jet_lut()
     assert lut.shape == (256, 4) and tuple(lut[0]) == (0, 0, 127, 255) and tuple(lut[-1]) == (127, 0, 0, 255)
     assert lut[96:160, 1].min() == 255                         # green plateau of jet in the middle
+
+
+def test_jet_lut_known_answers():
+    """matplotlib is not installed in this image, so video.colorize cannot be compared with the reference's
+    `matplotlib.cm.get_cmap('jet')(x, bytes=True)` (utils/depth.py:45-50) by execution.  Anchors instead: the
+    known values of matplotlib's 256-entry jet table -- jet(0) = (0, 0, 0.5), jet(255) = (0.5, 0, 0),
+    jet(128) = (0.4901960784313725, 1.0, 0.4775458570524984) -- and the properties of its construction (piecewise
+    linear in i / 255 between the published segment knots; bytes=True truncates lut * 255 to uint8)."""
+    from luciddreamer_b200 import video
+    lut = video.jet_lut()
+    assert lut.shape == (256, 4) and lut.dtype == np.uint8 and (lut[:, 3] == 255).all()
+    assert tuple(lut[0, :3]) == (0, 0, 127) and tuple(lut[255, :3]) == (127, 0, 0)
+    assert tuple(lut[128, :3]) == (int(0.4901960784313725 * 255), 255, int(0.4775458570524984 * 255))
+    # knots of the segment data: red rises on [0.35, 0.66], green on [0.125, 0.375], blue falls on [0.34, 0.65]
+    f = lut[:, :3].astype(int)
+    i = np.arange(256) / 255.0
+    assert (f[i <= 0.35, 0] == 0).all() and (f[(i >= 0.66) & (i <= 0.89), 0] == 255).all()
+    assert (f[i <= 0.125, 1] == 0).all() and (f[(i >= 0.375) & (i <= 0.64), 1] == 255).all() and (f[i >= 0.91, 1] == 0).all()
+    assert (f[(i >= 0.11) & (i <= 0.34), 2] == 255).all() and (f[i >= 0.65, 2] == 0).all()
+    for ch, lo, hi in ((0, 0.35, 0.66), (1, 0.125, 0.375)):               # monotone ramps between the knots
+        seg = f[(i >= lo) & (i <= hi), ch]
+        assert (np.diff(seg) >= 0).all()
+    # colorize(): percentile normalisation + invalid handling of utils/depth.py:25-52
+    d = np.linspace(1.0, 5.0, 64 * 48, dtype=np.float32).reshape(48, 64)
+    d[0, 0] = -99
+    img = video.colorize(d)
+    assert img.shape == (48, 64, 4) and tuple(img[0, 0]) == (128, 128, 128, 255)
+    assert tuple(img[-1, -1, :3]) == (127, 0, 0) and tuple(img[0, 1, :3]) == (0, 0, 127)     # beyond the 98th / 2nd percentile
