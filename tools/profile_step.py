@@ -10,9 +10,12 @@ ap.add_argument("--P", type=int, default=1_000_000); ap.add_argument("--W", type
 ap.add_argument("--H", type=int, default=1080); ap.add_argument("--D", type=int, default=3)
 ap.add_argument("--seed", type=int, default=1003); ap.add_argument("--scale-mult", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=3); ap.add_argument("--ref", action="store_true")
+ap.add_argument("--scene", default="shell", choices=["shell", "frustum"])
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-sc = {k: v.to(dev) for k, v in syn.make_scene(a.P, a.seed, scale_mult=a.scale_mult).items()}
+_scene = (syn.make_frustum_scene(a.P, a.seed, a.W, a.H) if a.scene == "frustum"
+          else syn.make_scene(a.P, a.seed, scale_mult=a.scale_mult))
+sc = {k: v.to(dev) for k, v in _scene.items()}
 cam = syn.make_camera(a.W, a.H)
 w = syn.make_cotangent(a.H, a.W, a.seed).to(dev)
 bg = torch.zeros(3, device=dev)
