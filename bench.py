@@ -113,6 +113,7 @@ def view_pose(rank: int, step: int = 0):
 
 def alg_bytes(P, Pv, pairs, N, G, M):
     """Algorithmic (compulsory) HBM bytes per launch of each kernel -- DESIGN.md section 4 states the model."""
+    dense = 2 * Pv > P                    # the device picks k_grad_dense over (k_grad_vis, k_grad_write) on this test
     return {
         "k_project": 12 * P + 4 * P + Pv * (12 + 16 + 4 + 32 + 4),
         "k_count_tiles": Pv * (4 + 32 + 4) + 4 * pairs,
@@ -122,8 +123,9 @@ def alg_bytes(P, Pv, pairs, N, G, M):
         "k_tile_sort_big": 0,
         "k_blend_fwd": 4 * pairs + 48 * Pv + 24 * N,
         "k_blend_bwd": 20 * N + 4 * pairs + 48 * Pv + 72 * Pv,
-        "k_grad_vis": Pv * (4 + 96 + 16 + 12 + 12 + 16 + 12 * M + 176),
-        "k_grad_write": 4 * P + (12 + 12 + 12 * M + 4 + 12 + 16) * P + Pv * (16 + 176),
+        "k_grad_vis": 0 if dense else Pv * (4 + 96 + 16 + 12 + 12 + 16 + 12 * M + 176),
+        "k_grad_write": 0 if dense else 4 * P + (12 + 12 + 12 * M + 4 + 12 + 16) * P + Pv * (16 + 176),
+        "k_grad_dense": (4 * P + Pv * (96 + 4 + 12 + 12 + 16 + 12 * M) + (12 + 12 + 12 * M + 4 + 12 + 16) * P) if dense else 0,
     }
 
 
@@ -168,7 +170,7 @@ class Ours:
         self.rast = R.GaussianRasterizer(self.settings)
         # k_project, k_count_tiles, k_tile_scan, k_shade_emit, k_tile_sort, k_tile_sort_mid, k_tile_sort_big, k_blend_fwd,
         # k_blend_bwd, k_grad_vis, k_grad_write (profiles/r01_launches_ours.csv) -- our kernels only, no torch kernels
-        self.kernels_per_step = 11
+        self.kernels_per_step = 12            # + k_grad_dense (returns at once unless most Gaussians are visible)
         self.last = None
         self.rasts, self.order, self.k = None, None, 0
 
@@ -182,6 +184,7 @@ class Ours:
 
     def forward(self):
         L = self.leaves
+        self.last = None                       # drop the previous step's autograd graph before building the next one
         for t in L.values():
             t.grad = None
         self.m2.grad = None
@@ -302,13 +305,16 @@ def time_steps(impl, cot, steps, warmup, world):
     return ms
 
 
-def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
+def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss, graphed=False):
     """Same metric end to end, shaped like one training iteration of the reference (luciddreamer.py:291-304): every
     step uploads that step's inputs from pinned host memory -- the camera (viewmatrix, projmatrix, campos: 35 floats)
     and the uint8 target image [H,W,3] -- computes the L1 photometric loss and its gradient on the device, runs
     forward+backward through the operator API, and reads the scalar loss back.  Target uploads of step k+1 overlap the
     backward of step k on a copy stream (double buffered); everything is inside the timed region.
-    fused_loss: our fused L1 kernel (luciddreamer_b200.losses); the reference arm uses plain torch ops."""
+    fused_loss: our fused L1 kernel (luciddreamer_b200.losses); the reference arm uses plain torch ops.
+    graphed: forward -> loss -> backward of a step is ONE CUDA graph (luciddreamer_b200.graphs.GraphedStep, the public
+    API for it; one graph per target buffer).  The uploads and the loss read-back stay outside the graph, per step.  The
+    reference cannot be captured: its forward blocks on a D2H copy (rasterizer_impl.cu:282)."""
     dev = impl.dev
     H, W = cam.image_height, cam.image_width
     h_tgt = target_u8_cpu.contiguous().pin_memory()
@@ -332,12 +338,21 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
             d_tgt[b].copy_(h_tgt, non_blocking=True)
             ev_up[b].record(copy_s)
 
+    graphs = None
+
     def run(n, base):
         upload(base)
         for k in range(base, base + n):
             b = k & 1
             d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream; the operator reads it in place
             main.wait_event(ev_up[b])
+            if graphs is not None:
+                loss = graphs[b].replay()
+                h_loss[k].copy_(loss.reshape(()), non_blocking=True)
+                ev_free[b].record(main)
+                if k + 1 < base + n:
+                    upload(k + 1)
+                continue
             color = impl.forward()
             if fused_loss:
                 loss, cot = losses.l1_loss_with_grad(color, d_tgt[b])
@@ -352,6 +367,20 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
                 upload(k + 1)                                     # issued last so the host reaches backward() early
 
     impl.bind_camera(d_cam)
+    d_cam.copy_(h_cam)
+    for b in range(2):
+        d_tgt[b].copy_(h_tgt)
+    if graphed:
+        from luciddreamer_b200.graphs import GraphedStep
+
+        def make_fn(b):
+            def fn():
+                color = impl.forward()
+                loss, cot = losses.l1_loss_with_grad(color, d_tgt[b])
+                impl.backward(color, cot)
+                return loss
+            return fn
+        graphs = [GraphedStep(make_fn(b), warmup=2) for b in range(2)]
     for b in range(2):
         ev_free[b].record(main)
     run(warmup, 0)
@@ -368,6 +397,9 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss):
     if world > 1:
         dist.barrier()
     ms = max(e0.elapsed_time(e1), wall_ms)      # the host-visible result is only there after the final sync
+    if graphs is not None:
+        for g in graphs:
+            g.check()                           # raises if a replay overflowed the static pair capacity
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -628,6 +660,7 @@ def main():
     ap.add_argument("--P", type=int, default=0); ap.add_argument("--W", type=int, default=0); ap.add_argument("--H", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared-model", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="e2e through the eager loop only (no CUDA-graph step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     os.environ.setdefault("OMP_PROC_BIND", "close")      # cpu_baseline: pinned OpenMP threads (read when libgomp starts)
@@ -685,13 +718,26 @@ def main():
     g = torch.Generator().manual_seed(4242)
     target_u8 = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8)
     e2e_ms, h2d, d2h, loss = time_e2e(impl, cam, target_u8, args.steps, args.warmup, world, fused_loss=(args.impl == "ours"))
+    e2e_eager = None
+    if args.impl == "ours" and not args.no_graph:
+        # headline e2e: the step as ONE CUDA graph through the public API (graphs.GraphedStep); the eager loop is kept
+        # beside it (`e2e.eager`) -- it is host-bound on boxes with slow cores, the graph is not
+        try:
+            g_ms, h2d, d2h, g_loss = time_e2e(impl, cam, target_u8, args.steps, args.warmup, world, fused_loss=True, graphed=True)
+            e2e_eager = {"value": world * rays * args.steps / e2e_ms / 1e3, "ms_per_step": e2e_ms / args.steps,
+                         "loss": loss}
+            assert abs(g_loss - loss) <= 1e-6 * max(1.0, abs(loss)), (g_loss, loss)
+            e2e_ms, loss = g_ms, g_loss
+        except Exception as ex:
+            e2e_eager = {"graph_error": str(ex)[:300]}
     e2e_val = world * rays * args.steps / e2e_ms / 1e3
 
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(wl, args, world),
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps,
+                    "ms_per_step": e2e_ms / args.steps, "loss": loss,
+                    "mode": ("cuda_graph" if (e2e_eager and "value" in e2e_eager) else "eager"), "eager": e2e_eager,
                     "protocol": "per step: H2D camera (35 floats) + uint8 target image [H,W,3] from pinned memory (copy "
                                 "stream, double buffered), forward, on-device L1 loss + gradient, backward, D2H scalar loss"},
             "clocks": clocks, "scene_stats": {"P_vis": st["P_vis"], "pairs": st["pairs"]}}

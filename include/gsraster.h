@@ -43,6 +43,7 @@ extern "C" {
 #define GS_ECUDA (-2)    /* CUDA runtime error (message has cudaGetErrorString) */
 #define GS_ECAPACITY (-3)/* binning buffer too small: see gs_forward_counts */
 #define GS_ENOMEM (-4)
+#define GS_ENOTREADY (-5)/* gs_forward_counts_peek: the device has not written the counts yet */
 
 typedef struct GsContext GsContext;
 typedef void* gs_stream_t; /* cudaStream_t */
@@ -134,6 +135,15 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
  * A context keeps 64 status slots: a ticket whose slot has been handed out again (more than 64 forwards enqueued on
  * the context since) is rejected with GS_EINVAL instead of returning another forward's counts. */
 int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out);
+
+/* Sync-free forward (no reference counterpart: the reference blocks on a D2H copy every forward).  A caller that
+ * passes its own `pair_capacity` to gs_forward_render need not call gs_forward_counts at all -- the forward is then
+ * pure stream work and can be captured into a CUDA graph (a captured gs_forward_preprocess gets a persistent status
+ * slot; at most 256 per context).  If the frame has more pairs than the capacity, the device-side guard renders
+ * NOTHING (outputs undefined); the caller finds out here, without blocking: GS_OK + counts once the device has written
+ * them (compare counts.num_pairs with the capacity used), GS_ENOTREADY before that.  For a captured forward the slot is
+ * rewritten by every replay: synchronise with the replay before trusting it. */
+int gs_forward_counts_peek(GsContext* ctx, int32_t ticket, GsCounts* out);
 
 /* replaces the second half of Rasterizer::forward (rasterizer_impl.cu:284-338).
  * out_color [3,H,W], out_depth [1,H,W] are fully written.  Returns GS_OK even if the capacity turns out
@@ -267,7 +277,7 @@ int gs_debug_export_binning(const GsFrame* f, const void* binning_buffer, int64_
  * SURVEY.md section 5).  When enabled, every kernel launch is bracketed by CUDA events on the launching stream;
  * gs_profile_read waits for them and returns the duration in ms of each kernel of the most recent forward /
  * backward (-1 = not launched).  Kernel i is named gs_profile_kernel_name(i), i < gs_profile_num_kernels(). */
-#define GS_NUM_KERNELS 10
+#define GS_NUM_KERNELS 11
 int gs_profile_enable(GsContext* ctx, int on);
 int gs_profile_num_kernels(void);
 const char* gs_profile_kernel_name(int i);

@@ -13,6 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgsraster_b200.so")
 
 GS_OK = 0
+GS_ENOTREADY = -5
 
 
 class GsFrame(C.Structure):
@@ -65,6 +66,7 @@ SYMBOLS = [
     ("gs_forward_preprocess", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.POINTER(C.c_int32)]),
     ("gs_forward_counts", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GsCounts)]),
+    ("gs_forward_counts_peek", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GsCounts)]),
     ("gs_forward_render", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     ("gs_forward_views", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_int32, C.POINTER(GsViewScratch), C.c_int32,

@@ -30,6 +30,8 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int kSlots = 64;
+constexpr int kGraphSlots = 256;       // status slots handed out to forwards that are being stream-captured (never recycled)
+constexpr int kGraphTicket = 0x40000000;
 constexpr int kMaxViewStreams = 8;
 
 int check_frame(const GsFrame* f) {
@@ -83,8 +85,8 @@ int debug_sync(const GsFrame* f, cudaStream_t s, const char* what) {
 constexpr int kNumKernels = GS_NUM_KERNELS;
 static const char* const kKernelNames[kNumKernels] = {"k_project", "k_tile_scan", "k_shade_emit", "k_tile_sort",
                                                       "k_tile_sort_big", "k_blend_fwd", "k_blend_bwd", "k_grad_vis",
-                                                      "k_count_tiles", "k_grad_write"};   // slot 9 also times
-                                                                                          // k_grad_reduce_peers
+                                                      "k_count_tiles", "k_grad_write",   // slot 9 also times
+                                                      "k_grad_dense"};                   // k_grad_reduce_peers
 
 struct GsContext {
     int device;
@@ -92,7 +94,8 @@ struct GsContext {
     int profile;                   // != 0: bracket every kernel with timing events (gs_profile_*)
     cudaEvent_t pev[2 * kNumKernels];
     bool pev_used[kNumKernels];
-    GsDevStatus* slots;            // pinned, mapped
+    GsDevStatus* slots;            // pinned, mapped: kSlots recycled slots, then kGraphSlots persistent ones
+    std::atomic<int> next_graph_slot;
     cudaEvent_t events[kSlots];
     unsigned slot_gen[kSlots];     // generation of the ticket that currently owns the slot
     std::atomic<unsigned> next;
@@ -141,6 +144,7 @@ int gs_context_create(int device, GsContext** out) {
     GsContext* c = new GsContext();
     c->device = device;
     c->next = 0;
+    c->next_graph_slot = 0;
     c->profile = 0;
     c->vstreams_ready = false;
     for (int i = 0; i < kSlots; i++) c->slot_gen[i] = 0;
@@ -148,17 +152,19 @@ int gs_context_create(int device, GsContext** out) {
     for (int i = 0; i < 2 * kNumKernels; i++) cudaEventCreate(&c->pev[i]);
     c->num_sms = 148;
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    g_gs_num_sms = c->num_sms;
     gs_tile_sort_init();
     gs_grad_write_init();
     if (const char* e = getenv("GS_BLEND_VARIANT")) g_gs_blend_variant = atoi(e);
-    cudaError_t e = cudaHostAlloc((void**)&c->slots, sizeof(GsDevStatus) * kSlots, cudaHostAllocMapped | cudaHostAllocPortable);
+    cudaError_t e = cudaHostAlloc((void**)&c->slots, sizeof(GsDevStatus) * (kSlots + kGraphSlots),
+                                cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) {
         for (int j = 0; j < 2 * kNumKernels; j++) cudaEventDestroy(c->pev[j]);
         delete c;
         cudaSetDevice(prev);
         return fail(GS_ECUDA, "cudaHostAlloc: %s", cudaGetErrorString(e));
     }
-    memset(c->slots, 0, sizeof(GsDevStatus) * kSlots);
+    memset(c->slots, 0, sizeof(GsDevStatus) * (kSlots + kGraphSlots));
     for (int i = 0; i < kSlots; i++) {
         e = cudaEventCreateWithFlags(&c->events[i], cudaEventDisableTiming);
         if (e != cudaSuccess) {
@@ -201,13 +207,28 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     const GsView v = make_view(f);
     const int G = v.gx * v.gy;
     GsImageLayout il = gs_image_layout(image_buffer, f->W, f->H);
-    const unsigned seq = ctx->next.fetch_add(1u);
-    const int slot = (int)(seq % (unsigned)kSlots);
-    const unsigned gen = (seq / (unsigned)kSlots) & 0x00ffffffu;
-    GsDevStatus* host_slot = ctx->slots + slot;
-    // the slot's previous owner (64 forwards ago) must have written its status before the slot is cleared
-    if (seq >= (unsigned)kSlots) GS_CUDA(cudaEventSynchronize(ctx->events[slot]));
-    ctx->slot_gen[slot] = gen;
+    // A forward that is being captured into a CUDA graph gets a PERSISTENT status slot (the graph bakes its address in
+    // and rewrites it on every replay); no event is involved, nothing may block.  Eager forwards recycle kSlots slots.
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    GS_CUDA(cudaStreamIsCapturing(s, &cap_st));
+    const bool capturing = cap_st != cudaStreamCaptureStatusNone;
+    int slot = -1;
+    GsDevStatus* host_slot = nullptr;
+    if (capturing) {
+        const int gsl = ctx->next_graph_slot.fetch_add(1);
+        if (gsl >= kGraphSlots) return fail(GS_ENOMEM, "more than %d forwards captured into CUDA graphs on this context", kGraphSlots);
+        host_slot = ctx->slots + kSlots + gsl;
+        *ticket = kGraphTicket | gsl;
+    } else {
+        const unsigned seq = ctx->next.fetch_add(1u);
+        slot = (int)(seq % (unsigned)kSlots);
+        const unsigned gen = (seq / (unsigned)kSlots) & 0x00ffffffu;
+        host_slot = ctx->slots + slot;
+        // the slot's previous owner (64 forwards ago) must have written its status before the slot is cleared
+        if (seq >= (unsigned)kSlots) GS_CUDA(cudaEventSynchronize(ctx->events[slot]));
+        ctx->slot_gen[slot] = gen;
+        *ticket = (int32_t)((gen << 6) | (unsigned)slot);     // slot in the low 6 bits, generation above
+    }
     host_slot->overflow = 0;                             // cleared; kernel writes 0xC0FFEE when done
     // zero tile histogram + status in one memset (they are adjacent)
     GS_CUDA(cudaMemsetAsync(il.tile_cnt, 0, (size_t)((char*)il.status - (char*)il.tile_cnt) + sizeof(GsDevStatus), s));
@@ -223,26 +244,47 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     GS_CUDA(cudaHostGetDevicePointer((void**)&dev_slot, host_slot, 0));
     GS_TIMED(ctx, 1, s, gs_launch_tile_scan(G, il.tile_cnt, il.tile_off, il.status, dev_slot, s));
     if ((rc = debug_sync(f, s, "tile_scan"))) return rc;
-    GS_CUDA(cudaEventRecord(ctx->events[slot], s));
-    *ticket = (int32_t)((gen << 6) | (unsigned)slot);     // slot in the low 6 bits, generation above
+    if (!capturing) GS_CUDA(cudaEventRecord(ctx->events[slot], s));
+    return GS_OK;
+}
+
+static int read_slot(const volatile GsDevStatus* h, int slot, GsCounts* out, bool must_be_ready) {
+    if (h->overflow != 0xC0FFEEu) {
+        if (must_be_ready) return fail(GS_ECUDA, "status slot %d was not written by the device", slot);
+        return GS_ENOTREADY;
+    }
+    out->num_rendered = (int64_t)h->num_rendered;
+    out->num_pairs = (int64_t)h->num_pairs;
+    out->num_visible = (int64_t)h->num_visible;
     return GS_OK;
 }
 
 int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out) {
     if (!ctx || !out || ticket < 0) return fail(GS_EINVAL, "bad ctx/ticket/out");
+    if (ticket & kGraphTicket)
+        return fail(GS_EINVAL, "ticket of a captured forward: replay the graph, synchronise, then gs_forward_counts_peek");
     const int slot = ticket & (kSlots - 1);
     const unsigned gen = (unsigned)ticket >> 6;
     if (ctx->slot_gen[slot] != gen)
         return fail(GS_EINVAL, "ticket expired: more than %d forwards were enqueued on this context since", kSlots);
     GS_CUDA(cudaEventSynchronize(ctx->events[slot]));
-    const volatile GsDevStatus* h = ctx->slots + slot;
     if (ctx->slot_gen[slot] != gen)
         return fail(GS_EINVAL, "ticket expired: more than %d forwards were enqueued on this context since", kSlots);
-    if (h->overflow != 0xC0FFEEu) return fail(GS_ECUDA, "status slot %d was not written by the device", slot);
-    out->num_rendered = (int64_t)h->num_rendered;
-    out->num_pairs = (int64_t)h->num_pairs;
-    out->num_visible = (int64_t)h->num_visible;
-    return GS_OK;
+    return read_slot(ctx->slots + slot, slot, out, true);
+}
+
+int gs_forward_counts_peek(GsContext* ctx, int32_t ticket, GsCounts* out) {
+    if (!ctx || !out || ticket < 0) return fail(GS_EINVAL, "bad ctx/ticket/out");
+    if (ticket & kGraphTicket) {
+        const int gsl = ticket & (kGraphTicket - 1);
+        if (gsl >= kGraphSlots) return fail(GS_EINVAL, "bad graph ticket");
+        return read_slot(ctx->slots + kSlots + gsl, kSlots + gsl, out, false);
+    }
+    const int slot = ticket & (kSlots - 1);
+    const unsigned gen = (unsigned)ticket >> 6;
+    if (ctx->slot_gen[slot] != gen)
+        return fail(GS_EINVAL, "ticket expired: more than %d forwards were enqueued on this context since", kSlots);
+    return read_slot(ctx->slots + slot, slot, out, false);
 }
 
 int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, void* geom_buffer, void* binning_buffer,
@@ -351,7 +393,7 @@ int gs_backward_blend(GsContext* ctx, const GsFrame* f, const void* geom_buffer,
     GsGeomLayout gl = gs_geom_layout(const_cast<void*>(geom_buffer), f->P);
     GsBinLayout bl = gs_bin_layout(const_cast<void*>(binning_buffer), pair_capacity > 0 ? pair_capacity : 1);
     GS_TIMED(ctx, 6, s, gs_launch_blend_bwd(v, il.tile_off, bl.list, gl.rec, il.final_T, il.n_contrib, dL_dout_color,
-                                            gl.acc, s));
+                                            gl.acc, il.status, pair_capacity, s));
     return debug_sync(f, s, "blend_bwd");
 }
 
@@ -374,10 +416,15 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
     g.dcolors = grads->dL_dcolors; g.dopacity = grads->dL_dopacity;
     g.dscales = grads->dL_dscales; g.drots = grads->dL_drotations; g.dcov3D = grads->dL_dcov3D;
     float* gout = (float*)grad_scratch;
+    // When most Gaussians are visible (decided on the device from num_visible) ONE dense kernel does the whole
+    // per-Gaussian backward and the compact pair below returns at once; otherwise the other way round.  The dense
+    // kernel covers the reference's own input mode (SH degree <= 3 stored as 16 coefficients, scales + rotations).
+    const bool dense_ok = grads->peer_world <= 0 && f->shs && f->M == 16 && !f->cov3D_precomp && f->scales && f->rotations &&
+                          !getenv("GS_NO_DENSE");
     GS_TIMED(ctx, 7, s, gs_launch_grad_vis(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs,
                                            f->cov3D_precomp ? nullptr : f->scales,
                                            f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec, gl.acc,
-                                           gl.vis_list, il.status, gout, s));
+                                           gl.vis_list, il.status, gout, dense_ok, s));
     if ((rc = debug_sync(f, s, "grad_vis"))) return rc;
     if (grads->peer_world > 0) {
         // data-parallel shared-model step: the five parameter gradients are reduced straight into every rank's
@@ -388,8 +435,13 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
                                                         (float*)grads->peer_multicast, (const long long*)grads->peer_seg_off, s));
         return debug_sync(f, s, "grad_reduce_peers");
     }
-    GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, s));
+    GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, il.status, dense_ok, s));
     if ((rc = debug_sync(f, s, "grad_write"))) return rc;
+    if (dense_ok) {
+        GS_TIMED(ctx, 10, s, gs_launch_grad_dense(v, f->means3D, f->shs, f->scales, f->rotations, radii, gl.rec, gl.acc,
+                                                  il.status, g, s));
+        if ((rc = debug_sync(f, s, "grad_dense"))) return rc;
+    }
     // outputs the fused kernel does not produce in this input mode are defined as zeros (reference: torch::zeros)
     const size_t Ps = (size_t)f->P;
     if (!f->shs && grads->dL_dsh && f->M > 0) GS_CUDA(cudaMemsetAsync(grads->dL_dsh, 0, Ps * f->M * 3 * sizeof(float), s));

@@ -34,9 +34,19 @@
 
 namespace {
 
-constexpr int kThreads = 64;          // 2 warps; warp w -> pixel rows [8w, 8w+8) of the tile, 16 wide
-constexpr int kBatch = 128;           // splats staged per round (two per thread)
+constexpr int kBatch = 128;           // splats staged per round
 constexpr int kWords = kBatch / 32;
+
+// Two geometries, chosen per launch by the number of tiles (gs_launch_blend_*):
+//   NH = 2  a warp owns a 16x8 block, a thread FOUR pixels (two float2 pairs); 2 warps (64 threads) per tile
+//   NH = 1  a warp owns a 16x4 strip, a thread TWO pixels (one pair); 4 warps (128 threads) per tile -- twice the warps
+//           for images with few tiles (512x512: 1024 tiles would leave the SMs at 14 resident warps), finer culling
+template <int NH> struct Geo {
+    static constexpr int RW = 4 * NH;             // pixel rows per warp
+    static constexpr int NW = 16 / RW;            // warps per tile
+    static constexpr int NT = 32 * NW;            // threads per CTA
+    static constexpr int NQ = 2 * NH;             // pixels per thread
+};
 
 struct __align__(16) SRec {           // shared-memory copy of a splat record
     float4 a;                         // x, y, A2 = -0.5 log2e conic_a, B2 = -log2e conic_b
@@ -50,6 +60,7 @@ constexpr float kHalfLog2e = -0.5f * 1.4426950408889634f;     // staged conic sc
 constexpr float kUnscale = -2.0f * 0.6931471805599453f;       // back to the conic for the flush of the backward pass
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kBand = 1e-7f;
+constexpr float kNegInf = -__builtin_huge_valf();
 
 // ---- packed FP32 pairs (sm_100 FFMA2 / FMUL2 / FADD2); scalar broadcasts fold into the operand (Rx.F32)
 __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
@@ -91,28 +102,30 @@ __device__ __forceinline__ float rcp_approx(const float x) {
     return y;
 }
 
-// 2-bit mask: which of the tile's two 16x8 pixel blocks the splat can touch
-__device__ __forceinline__ uint32_t block_mask(const float4 a, const float4 b, const float thr, int tx0, int ty0) {
+// NW-bit mask: which of the tile's 16 x RW pixel strips the splat can touch
+template <int NH>
+__device__ __forceinline__ uint32_t strip_mask(const float4 a, const float4 b, const float thr, int tx0, int ty0) {
     uint32_t m = 0;
 #pragma unroll
-    for (int w = 0; w < 2; w++) {
-        const float x0 = (float)tx0, y0 = (float)(ty0 + 8 * w);
-        if (gs_box_hit(a.x, a.y, a.z, a.w, b.x, thr, x0, y0, x0 + 15.f, y0 + 7.f)) m |= 1u << w;
+    for (int w = 0; w < Geo<NH>::NW; w++) {
+        const float x0 = (float)tx0, y0 = (float)(ty0 + Geo<NH>::RW * w);
+        if (gs_box_hit(a.x, a.y, a.z, a.w, b.x, thr, x0, y0, x0 + 15.f, y0 + (float)(Geo<NH>::RW - 1))) m |= 1u << w;
     }
     return m;
 }
 
-// Stages up to two splats per thread into shared memory and publishes the per-block hit masks.
+// Stages up to kBatch splats into shared memory and publishes the per-strip hit masks.
 // slot j of the batch holds list position pos(j).  Mask words are bit-REVERSED (slot 32k+i -> bit 31-i) so the
 // traversal finds the next slot with one FLO (count-leading-zeros).  All threads must call.
-template <typename PosFn>
+template <int NH, typename PosFn>
 __device__ __forceinline__ void stage_batch(SRec* sRec, uint32_t (*sMask)[kWords], const uint32_t* __restrict__ list,
                                             const float4* __restrict__ rec, uint32_t beg, int cnt, int tx0, int ty0,
                                             PosFn pos_of) {
+    constexpr int NW = Geo<NH>::NW, NT = Geo<NH>::NT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 #pragma unroll
-    for (int h = 0; h < kBatch / kThreads; h++) {
-        const int j = tid + h * kThreads;
+    for (int h = 0; h < kBatch / NT; h++) {
+        const int j = tid + h * NT;
         uint32_t m = 0;
         if (j < cnt) {
             const uint32_t id = list[beg + pos_of(j)];
@@ -130,72 +143,84 @@ __device__ __forceinline__ void stage_batch(SRec* sRec, uint32_t (*sMask)[kWords
                               (fabsf(a.x) < 1e7f) && (fabsf(a.y) < 1e7f) && (tr < 1e7f);
             s.generic = fast ? 0u : 1u;
             sRec[j] = s;
-            m = block_mask(a, b, c.w, tx0, ty0);
+            m = strip_mask<NH>(a, b, c.w, tx0, ty0);
         }
 #pragma unroll
-        for (int w = 0; w < 2; w++) {
+        for (int w = 0; w < NW; w++) {
             const uint32_t bits = __brev(__ballot_sync(0xffffffffu, (m >> w) & 1u));
-            if (lane == 0) sMask[w][wid + 2 * h] = bits;      // word index = j / 32
+            if (lane == 0) sMask[w][wid + NW * h] = bits;     // word index = j / 32
         }
     }
 }
-
-// the thread's four pixels as two packed pairs: pair h holds rows (2h) and (2h+1) of the thread, i.e. image rows
-// pyb + 4h and pyb + 4h + 2
-struct FwdPix {
-    float2 T[2];                      // > 0: live transmittance; <= 0: pixel terminated (|T| is the value to report)
-    float2 C0[2], C1[2], C2[2], D[2], acc[2];                                            // or outside the image
-    uint32_t last[4];
-};
 
 #define GS_Q(v, q) (((q) & 1) ? (v)[(q) >> 1].y : (v)[(q) >> 1].x)
 
 // The approximate evaluation shared by forward and backward: p = log2(e) * power, g = 2^p, a = opacity * g,
-// d = a - 1/255 (sign-exact).  Returns true when one of the four alphas sits inside the re-evaluation band.
-__device__ __forceinline__ bool eval_alpha4(const SRec& r, const float dx, const float2* dy, float2* p, float2* g,
-                                            float2* a, float2* d) {
+// d = a + nam (nam = -1/255 for a live pixel: sign-exact alpha >= 1/255 test; -inf for a dead one).  Returns true
+// when one of the alphas sits inside the re-evaluation band around 1/255.
+template <int NH>
+__device__ __forceinline__ bool eval_alpha(const SRec& r, const float dx, const float2* dy, const float2* nam, float2* p,
+                                           float2* g, float2* a, float2* d) {
     const float hA = (r.a.z * dx) * dx, hB = r.a.w * dx;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < NH; h++) {
         const float2 u = fma2(bc(r.b.x), dy[h], bc(hB));          // C2 dy + B2 dx
         p[h] = fma2(u, dy[h], bc(hA));                            // (C2 dy + B2 dx) dy + A2 dx dx
         g[h] = make_float2(ex2_approx(p[h].x), ex2_approx(p[h].y));
         a[h] = mul2(bc(r.b.y), g[h]);
-        d[h] = add2(a[h], bc(-kAlphaMin));
+        d[h] = add2(a[h], nam[h]);
     }
-    const float m = fminf(fminf(fabsf(d[0].x), fabsf(d[0].y)), fminf(fabsf(d[1].x), fabsf(d[1].y)));
+    float m = fminf(fabsf(d[0].x), fabsf(d[0].y));
+    if (NH == 2) m = fminf(m, fminf(fabsf(d[NH - 1].x), fabsf(d[NH - 1].y)));
     return m < kBand;
 }
 
-// alpha of the thread's four pixels with the reference's arithmetic (forward.cu:330-343), from the unscaled record
-__device__ __forceinline__ void exact_alpha4(const SRec& r, const float dx, const float2* dy,
-                                             const float4* __restrict__ rec, float* alpha) {
+// power and alpha (before the 0.99 clamp) of the thread's pixels with the reference's arithmetic (forward.cu:330-343),
+// from the unscaled record
+template <int NH>
+__device__ __forceinline__ void exact_eval(const SRec& r, const float dx, const float2* dy,
+                                           const float4* __restrict__ rec, float* power, float* alpha) {
     const float4 ra = __ldg(rec + (size_t)GS_REC_V4 * r.id), rb = __ldg(rec + (size_t)GS_REC_V4 * r.id + 1);
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 2 * NH; q++) {
         const float dyq = GS_Q(dy, q);
-        alpha[q] = r.b.y * expf(-0.5f * (ra.z * dx * dx + rb.x * dyq * dyq) - ra.w * dx * dyq);
+        power[q] = -0.5f * (ra.z * dx * dx + rb.x * dyq * dyq) - ra.w * dx * dyq;
+        alpha[q] = r.b.y * expf(power[q]);
     }
 }
 
+// the thread's pixels as packed pairs: pair h holds image rows pyb + 4h and pyb + 4h + 2
+template <int NH> struct FwdPix {
+    float2 T[NH];                     // transmittance in front of the next splat; frozen once the pixel is dead
+    float2 nam[NH];                   // -1/255 while the pixel is live; -inf once it terminated (T < 1e-4) or if it
+                                      // lies outside the image: a + nam < 0 then fails the alpha test for every splat
+    float2 C0[NH], C1[NH], C2[NH], D[NH], acc[NH];
+    uint32_t last[2 * NH];
+};
+
 // forward.cu:330-369, generic path: the reference's full test sequence per pixel (power > 0, min(0.99, alpha),
-// alpha < 1/255, T < 1e-4).  Taken by splats that are not fast-path eligible and by threads with an alpha in the band.
-__device__ __forceinline__ void fwd_generic(FwdPix& P, const SRec& r, const float dx, const float2* dy, const float2* p,
-                                         const float2* a, const bool band, const uint32_t pos1,
-                                         const float4* __restrict__ rec) {
-    float alpha[4];
+// alpha < 1/255, T < 1e-4).  Taken by splats that are not fast-path eligible, by threads with an alpha in the band and
+// whenever a pixel of the warp is about to terminate.
+template <int NH>
+__device__ __forceinline__ void fwd_generic(FwdPix<NH>& P, const SRec& r, const float dx, const float2* dy, const float2* p,
+                                            const float2* a, const bool band, const uint32_t pos1,
+                                            const float4* __restrict__ rec) {
+    // in the band around 1/255, and for every splat that is not fast-path eligible (ill-conditioned conics: the
+    // factored exponent rounds differently from the reference's expression, and the difference is amplified by the
+    // cancellation inside `power`), the decision operands are re-evaluated in the reference's own operation order
+    float alpha[2 * NH], power[2 * NH];
 #pragma unroll
-    for (int q = 0; q < 4; q++) alpha[q] = GS_Q(a, q);
-    if (band) exact_alpha4(r, dx, dy, rec, alpha);
+    for (int q = 0; q < 2 * NH; q++) { alpha[q] = GS_Q(a, q); power[q] = GS_Q(p, q); }
+    if (band || r.generic) exact_eval<NH>(r, dx, dy, rec, power, alpha);
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 2 * NH; q++) {
         float& T = GS_Q(P.T, q);
+        const bool live = GS_Q(P.nam, q) > -1.f;
         const float al = fminf(0.99f, alpha[q]);
-        const bool ok = !(GS_Q(p, q) > 0.0f) && !(al < kAlphaMin);
+        const bool ok = live && !(power[q] > 0.0f) && !(al < kAlphaMin);
         const float test_T = T * (1.f - al);
-        const bool low = test_T < 0.0001f;                // forward.cu:348-352 (also true for T <= 0)
-        const bool upd = ok && !low;
-        if (upd) {
+        const bool low = test_T < 0.0001f;                // forward.cu:348-352
+        if (ok && !low) {
             const float w = al * T;                       // one weight for colour, depth and coverage
             GS_Q(P.C0, q) += r.b.z * w;
             GS_Q(P.C1, q) += r.b.w * w;
@@ -203,51 +228,60 @@ __device__ __forceinline__ void fwd_generic(FwdPix& P, const SRec& r, const floa
             GS_Q(P.D, q) += r.c.y * w;
             GS_Q(P.acc, q) += w;
             P.last[q] = pos1;
+            T = test_T;
         }
-        T = ok ? (low ? -fabsf(T) : test_T) : T;          // see the note at the fast path about this form
+        if (ok && low) GS_Q(P.nam, q) = kNegInf;          // done = true: T stays, nothing behind contributes
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 12)
+template <int NH>
+__global__ void __launch_bounds__(Geo<NH>::NT, NH == 2 ? 12 : 6)
 k_blend_fwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ list,
             const float4* __restrict__ rec, const GsDevStatus* __restrict__ status, long long capacity,
             float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
             float* __restrict__ out_depth) {
+    constexpr int NW = Geo<NH>::NW, NQ = Geo<NH>::NQ;
     if ((long long)status->num_pairs > capacity) return;
     __shared__ SRec sRec[kBatch];
-    __shared__ uint32_t sMask[2][kWords];                // [pixel block][32-splat word], bit-reversed
+    __shared__ uint32_t sMask[NW][kWords];               // [pixel strip][32-splat word], bit-reversed
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float bg0 = __ldg(v.bg), bg1 = __ldg(v.bg + 1), bg2 = __ldg(v.bg + 2);
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int tx0 = blockIdx.x * GS_TILE, ty0 = blockIdx.y * GS_TILE;
     const uint32_t px = tx0 + (lane & 15);
-    const uint32_t pyb = ty0 + 8 * wid + (lane >> 4);    // rows pyb + 2q
+    const uint32_t pyb = ty0 + Geo<NH>::RW * wid + (lane >> 4);    // rows pyb + 2q
     const float pixx = (float)px;
-    const float2 npy[2] = {make_float2(-(float)pyb, -(float)(pyb + 2)), make_float2(-(float)(pyb + 4), -(float)(pyb + 6))};
+    float2 npy[NH];
+#pragma unroll
+    for (int h = 0; h < NH; h++) npy[h] = make_float2(-(float)(pyb + 4 * h), -(float)(pyb + 4 * h + 2));
     const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
     const int n = (int)(end - beg);
 
-    FwdPix P;
+    FwdPix<NH> P;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < NQ; q++) {
         const bool in = px < (uint32_t)v.W && (pyb + 2 * q) < (uint32_t)v.H;
-        GS_Q(P.T, q) = in ? 1.0f : -1.0f;
+        GS_Q(P.T, q) = 1.0f;
+        GS_Q(P.nam, q) = in ? -kAlphaMin : kNegInf;
         GS_Q(P.C0, q) = 0.f; GS_Q(P.C1, q) = 0.f; GS_Q(P.C2, q) = 0.f; GS_Q(P.D, q) = 0.f;
         GS_Q(P.acc, q) = 0.000001f; P.last[q] = 0u;
     }
+    auto all_dead = [&]() {
+        float m = fmaxf(P.nam[0].x, P.nam[0].y);
+        if (NH == 2) m = fmaxf(m, fmaxf(P.nam[NH - 1].x, P.nam[NH - 1].y));
+        return m < -1.f;
+    };
 
     for (int base = 0; base < n; base += kBatch) {
-        bool alldone = fmaxf(fmaxf(P.T[0].x, P.T[0].y), fmaxf(P.T[1].x, P.T[1].y)) <= 0.f;
-        if (__syncthreads_and(alldone)) break;
+        if (__syncthreads_and(all_dead())) break;
         const int cnt = min(kBatch, n - base);
-        stage_batch(sRec, sMask, list, rec, beg, cnt, tx0, ty0, [&](int j) { return base + j; });
+        stage_batch<NH>(sRec, sMask, list, rec, beg, cnt, tx0, ty0, [&](int j) { return base + j; });
         __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < kWords; k++) {
             uint32_t bits = sMask[wid][k];
             if (bits == 0) continue;
-            alldone = fmaxf(fmaxf(P.T[0].x, P.T[0].y), fmaxf(P.T[1].x, P.T[1].y)) <= 0.f;
-            if (__all_sync(0xffffffffu, alldone)) break;
+            if (__all_sync(0xffffffffu, all_dead())) break;
             while (bits) {
                 const int lz = __clz(bits);
                 bits &= ~(0x80000000u >> lz);
@@ -255,51 +289,54 @@ k_blend_fwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
                 const SRec& r = sRec[j];
                 const uint32_t pos1 = (uint32_t)(base + j + 1);
                 const float dx = r.a.x - pixx;
-                const float2 dy[2] = {add2(bc(r.a.y), npy[0]), add2(bc(r.a.y), npy[1])};
-                float2 p[2], g[2], a[2], d[2];
-                const bool band = eval_alpha4(r, dx, dy, p, g, a, d);
-                if (band || r.generic) {
-                    fwd_generic(P, r, dx, dy, p, a, band, pos1, rec);
+                float2 dy[NH], p[NH], g[NH], a[NH], d[NH];
+#pragma unroll
+                for (int h = 0; h < NH; h++) dy[h] = add2(bc(r.a.y), npy[h]);
+                const bool band = eval_alpha<NH>(r, dx, dy, P.nam, p, g, a, d);
+                // fast path: alpha = a (no clamp can bind), contributes <=> a >= 1/255 on a live pixel <=> d >= 0
+                // (forward.cu:336-346).  A pixel that does not contribute runs with alpha = 0: test_T = T exactly.
+                float2 ae[NH], tT[NH];
+                bool okq[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    okq[q] = GS_Q(d, q) >= 0.f;
+                    GS_Q(ae, q) = okq[q] ? GS_Q(a, q) : 0.f;
+                }
+#pragma unroll
+                for (int h = 0; h < NH; h++) {
+                    const float2 om = fma2(ae[h], bc(-1.f), bc(1.f));     // 1 - alpha
+                    tT[h] = mul2(P.T[h], om);                             // test_T = T * (1 - alpha)
+                }
+                float tmin = fminf(tT[0].x, tT[0].y);
+                if (NH == 2) tmin = fminf(tmin, fminf(tT[NH - 1].x, tT[NH - 1].y));
+                // a pixel about to terminate (forward.cu:348-352; dead pixels keep T >= 1e-4 and never trigger), an
+                // alpha in the band or an ineligible splat: the whole warp takes the reference's sequence
+                if (__any_sync(0xffffffffu, band || tmin < 0.0001f) || r.generic) {
+                    fwd_generic<NH>(P, r, dx, dy, p, a, band, pos1, rec);
                     continue;
                 }
-                // fast path: alpha = a (no clamp), ok <=> a >= 1/255 <=> d >= 0 (forward.cu:336-346)
-                float2 tT[2], w[2];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float2 om = fma2(a[h], bc(-1.f), bc(1.f));      // 1 - alpha
-                    tT[h] = mul2(P.T[h], om);                             // test_T = T * (1 - alpha)
-                    w[h] = mul2(a[h], P.T[h]);                            // alpha * T
-                }
+                for (int q = 0; q < NQ; q++) P.last[q] = okq[q] ? pos1 : P.last[q];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const bool ok = GS_Q(d, q) >= 0.f;
-                    const bool low = GS_Q(tT, q) < 0.0001f;               // forward.cu:348-352 (also true for T <= 0)
-                    const bool upd = ok && !low;
-                    GS_Q(w, q) = upd ? GS_Q(w, q) : 0.f;
-                    P.last[q] = upd ? pos1 : P.last[q];
-                    float& T = GS_Q(P.T, q);
-                    // NB: written as nested selects on `ok`; nvcc 12.9 miscompiles `upd ? tT : (term ? -|T| : T)`
-                    // (drops the middle arm) -- tests/test_parity_gpu.py::test_early_termination pins this
-                    T = ok ? (low ? -fabsf(T) : GS_Q(tT, q)) : T;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    P.C0[h] = fma2(bc(r.b.z), w[h], P.C0[h]);
-                    P.C1[h] = fma2(bc(r.b.w), w[h], P.C1[h]);
-                    P.C2[h] = fma2(bc(r.c.x), w[h], P.C2[h]);
-                    P.D[h] = fma2(bc(r.c.y), w[h], P.D[h]);
-                    P.acc[h] = add2(P.acc[h], w[h]);
+                for (int h = 0; h < NH; h++) {
+                    const float2 w = mul2(ae[h], P.T[h]);                 // alpha * T
+                    P.T[h] = tT[h];
+                    P.C0[h] = fma2(bc(r.b.z), w, P.C0[h]);
+                    P.C1[h] = fma2(bc(r.b.w), w, P.C1[h]);
+                    P.C2[h] = fma2(bc(r.c.x), w, P.C2[h]);
+                    P.D[h] = fma2(bc(r.c.y), w, P.D[h]);
+                    P.acc[h] = add2(P.acc[h], w);
                 }
             }
         }
     }
     const size_t HW = (size_t)v.H * v.W;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < NQ; q++) {
         const uint32_t py = pyb + 2 * q;
         if (px < (uint32_t)v.W && py < (uint32_t)v.H) {
             const uint32_t pix_id = (uint32_t)v.W * py + px;
-            const float T = fabsf(GS_Q(P.T, q));
+            const float T = GS_Q(P.T, q);
             final_T[pix_id] = T;
             n_contrib[pix_id] = P.last[q];
             out_color[pix_id] = GS_Q(P.C0, q) + T * bg0;
@@ -335,12 +372,13 @@ __device__ __forceinline__ void warp_reduce9(float* v, const int lane) {
     halving_step<1, 1>(v, lane);
 }
 
-struct BwdPix {
-    float2 T[2];
-    float2 tb[2];                     // -T_final * (bg . dL_dpixel)
-    float2 AR[2];                     // sum_ch accum_rec_ch * dL_dpixel_ch, already advanced past the last contributing splat
-    float2 g0[2], g1[2], g2[2];       // dL_dpixel
-    int last[4];                      // last contributor (1-based list position)
+template <int NH> struct BwdPix {
+    float2 T[NH];
+    float2 nam[NH];                   // -1/255 for a pixel with contributors, -inf otherwise (same role as in FwdPix)
+    float2 tb[NH];                    // -T_final * (bg . dL_dpixel)
+    float2 AR[NH];                    // sum_ch accum_rec_ch * dL_dpixel_ch, already advanced past the last contributing splat
+    float2 g0[NH], g1[NH], g2[NH];    // dL_dpixel
+    int last[2 * NH];                 // last contributor (1-based list position)
 };
 
 // What both backward paths sum per (thread, splat), for w = opacity * G * dL_dalpha of the contributing pixels:
@@ -354,19 +392,21 @@ struct BwdPix {
 // recurrence (AR' = a cg + (1 - a) AR = AR + a (cg - AR), cg = c . dL_dpixel) and is advanced eagerly.
 
 // generic path of the backward: the reference's test sequence per pixel, exact alpha inside the band
-__device__ __forceinline__ bool bwd_generic(BwdPix& Q, const SRec& r, const float dx, const float2* dy, const float2* p,
-                                         const float2* g, const float2* a, const bool band, const int pos,
-                                         const float4* __restrict__ rec, float* vv) {
-    float alpha[4];
+template <int NH>
+__device__ __forceinline__ bool bwd_generic(BwdPix<NH>& Q, const SRec& r, const float dx, const float2* dy, const float2* p,
+                                            const float2* g, const float2* a, const bool band, const int pos,
+                                            const float4* __restrict__ rec, float* vv) {
+    (void)g;
+    float alpha[2 * NH], power[2 * NH];          // alpha = opacity * G, unclamped
 #pragma unroll
-    for (int q = 0; q < 4; q++) alpha[q] = GS_Q(a, q);
-    if (band) exact_alpha4(r, dx, dy, rec, alpha);
+    for (int q = 0; q < 2 * NH; q++) { alpha[q] = GS_Q(a, q); power[q] = GS_Q(p, q); }
+    if (band || r.generic) exact_eval<NH>(r, dx, dy, rec, power, alpha);
     bool any = false;
     float s0 = 0.f, sy = 0.f, syy = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 2 * NH; q++) {
         const float al = fminf(0.99f, alpha[q]);
-        const bool ok = (pos < Q.last[q]) && !(GS_Q(p, q) > 0.0f) && !(al < kAlphaMin);
+        const bool ok = (pos < Q.last[q]) && !(power[q] > 0.0f) && !(al < kAlphaMin);
         any = any || ok;
         const float a_ = ok ? al : 0.f;                     // alpha = 0 makes every update below a no-op
         const float inv = rcp_approx(1.f - a_);
@@ -380,7 +420,7 @@ __device__ __forceinline__ bool bwd_generic(BwdPix& Q, const SRec& r, const floa
         const float dch = a_ * T;
         vv[0] = fmaf(dch, g0, vv[0]); vv[1] = fmaf(dch, g1, vv[1]); vv[2] = fmaf(dch, g2, vv[2]);
         const float dL_dalpha = fmaf(dcol, T, GS_Q(Q.tb, q) * inv);
-        const float oG = ok ? r.b.y * GS_Q(g, q) : 0.f;     // zero weight keeps an inf of a skipped splat out of the sums
+        const float oG = ok ? alpha[q] : 0.f;               // opacity * G; zero keeps an inf of a skipped splat out of the sums
         const float wq = oG * dL_dalpha;
         const float dyq = GS_Q(dy, q);
         s0 += wq;
@@ -393,38 +433,47 @@ __device__ __forceinline__ bool bwd_generic(BwdPix& Q, const SRec& r, const floa
     return any;
 }
 
-__global__ void __launch_bounds__(kThreads, 10)
+template <int NH>
+__global__ void __launch_bounds__(Geo<NH>::NT, NH == 2 ? 10 : 6)
 k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ list,
             const float4* __restrict__ rec, const float* __restrict__ final_Ts,
-            const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix, float4* __restrict__ acc) {
+            const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix, float4* __restrict__ acc,
+            const GsDevStatus* __restrict__ status, long long capacity) {
+    constexpr int NW = Geo<NH>::NW, NT = Geo<NH>::NT, NQ = Geo<NH>::NQ;
+    // a forward whose pair count exceeded the binning capacity rendered nothing (device-side guard): there is no list
+    // to walk, the accumulators stay zero (static-capacity mode reports the overflow at the next host call)
+    if ((long long)status->num_pairs > capacity) return;
     __shared__ SRec sRec[kBatch];
-    __shared__ float sAcc[2][kBatch * 9];                // per warp: plain stores, no atomics
-    __shared__ uint32_t sMask[2][kWords];
-    __shared__ uint32_t sDone[2][kWords];                // which slots of sAcc a warp has written this round
-    __shared__ int sMax[kThreads / 32];
+    __shared__ float sAcc[NW][kBatch * 9];               // per warp: plain stores, no atomics
+    __shared__ uint32_t sMask[NW][kWords];
+    __shared__ uint32_t sDone[NW][kWords];               // which slots of sAcc a warp has written this round
+    __shared__ int sMax[NW];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int tx0 = blockIdx.x * GS_TILE, ty0 = blockIdx.y * GS_TILE;
     const uint32_t px = tx0 + (lane & 15);
-    const uint32_t pyb = ty0 + 8 * wid + (lane >> 4);
+    const uint32_t pyb = ty0 + Geo<NH>::RW * wid + (lane >> 4);
     const float pixx = (float)px;
-    const float2 npy[2] = {make_float2(-(float)pyb, -(float)(pyb + 2)), make_float2(-(float)(pyb + 4), -(float)(pyb + 6))};
+    float2 npy[NH];
+#pragma unroll
+    for (int h = 0; h < NH; h++) npy[h] = make_float2(-(float)(pyb + 4 * h), -(float)(pyb + 4 * h + 2));
     const uint32_t beg = tile_off[tile], end = tile_off[tile + 1];
     if (beg == end) return;
 
     const size_t HW = (size_t)v.H * v.W;
     const float bgc0 = __ldg(v.bg), bgc1 = __ldg(v.bg + 1), bgc2 = __ldg(v.bg + 2);
-    BwdPix Q;
-    int wmax = 0;
+    BwdPix<NH> Q;
+    int wmax = 0, wmin = 0x7fffffff;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < NQ; q++) {
         const uint32_t py = pyb + 2 * q;
         const bool in = px < (uint32_t)v.W && py < (uint32_t)v.H;
         const uint32_t pix_id = (uint32_t)v.W * py + px;
         const float T_final = in ? final_Ts[pix_id] : 0.f;
         GS_Q(Q.T, q) = T_final;
         Q.last[q] = in ? (int)n_contrib[pix_id] : 0;
+        GS_Q(Q.nam, q) = Q.last[q] > 0 ? -kAlphaMin : kNegInf;
         const float g0 = in ? dL_dpix[pix_id] : 0.f, g1 = in ? dL_dpix[HW + pix_id] : 0.f, g2 = in ? dL_dpix[2 * HW + pix_id] : 0.f;
         GS_Q(Q.g0, q) = g0; GS_Q(Q.g1, q) = g1; GS_Q(Q.g2, q) = g2;
         float bd = 0.f;
@@ -432,17 +481,22 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
         GS_Q(Q.tb, q) = -T_final * bd;
         GS_Q(Q.AR, q) = 0.f;
         wmax = max(wmax, Q.last[q]);
+        if (Q.last[q] > 0) wmin = min(wmin, Q.last[q]);
     }
     const float ddelx_dx = 0.5 * v.W, ddely_dy = 0.5 * v.H;
 
-    // max of n_contrib over the warp's block / over the tile: nothing behind it contributes
+    // max of n_contrib over the warp's strip / over the tile: nothing behind it contributes.  wmin: the smallest
+    // n_contrib among the strip's pixels that have contributors -- in front of it every such pixel takes part.
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+    }
     if (lane == 0) sMax[wid] = wmax;
     __syncthreads();
     int maxc = 0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; w++) maxc = max(maxc, sMax[w]);
+    for (int w = 0; w < NW; w++) maxc = max(maxc, sMax[w]);
 
     // owner lanes / slots of the halving reduction
     const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
@@ -454,7 +508,7 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
         __syncthreads();
         const int cnt = min(kBatch, hi);
         // slot j holds list position hi-1-j: reverse traversal = increasing j
-        stage_batch(sRec, sMask, list, rec, beg, cnt, tx0, ty0, [&](int j) { return hi - 1 - j; });
+        stage_batch<NH>(sRec, sMask, list, rec, beg, cnt, tx0, ty0, [&](int j) { return hi - 1 - j; });
         __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < kWords; k++) {
@@ -466,31 +520,37 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
                 bits &= ~bit;
                 const int j = 32 * k + lz;
                 const int pos = hi - 1 - j;      // 0-based list position
-                if (pos >= wmax) continue;       // behind every pixel of this block
+                if (pos >= wmax) continue;       // behind every pixel of this strip
                 const SRec& r = sRec[j];
                 const float dx = r.a.x - pixx;
-                const float2 dy[2] = {add2(bc(r.a.y), npy[0]), add2(bc(r.a.y), npy[1])};
-                float2 p[2], g[2], a[2], d[2];
-                const bool band = eval_alpha4(r, dx, dy, p, g, a, d);
+                float2 dy[NH], p[NH], g[NH], a[NH], d[NH];
+#pragma unroll
+                for (int h = 0; h < NH; h++) dy[h] = add2(bc(r.a.y), npy[h]);
+                const bool band = eval_alpha<NH>(r, dx, dy, Q.nam, p, g, a, d);
                 float vv[9];
                 bool any;
-                if (band || r.generic) {
+                if (__any_sync(0xffffffffu, band) || r.generic) {
 #pragma unroll
                     for (int q = 0; q < 9; q++) vv[q] = 0.f;
-                    any = bwd_generic(Q, r, dx, dy, p, g, a, band, pos, rec, vv);
+                    any = bwd_generic<NH>(Q, r, dx, dy, p, g, a, band, pos, rec, vv);
                 } else {
-                    // fast path: alpha = a (no clamp), ok <=> pos < last && d >= 0; a skipped pixel runs with alpha = 0,
-                    // which makes every update a no-op (T / 1 = T, AR + 0, zero weights)
-                    float2 ae[2];
-                    ae[0].x = (pos < Q.last[0] && d[0].x >= 0.f) ? a[0].x : 0.f;
-                    ae[0].y = (pos < Q.last[1] && d[0].y >= 0.f) ? a[0].y : 0.f;
-                    ae[1].x = (pos < Q.last[2] && d[1].x >= 0.f) ? a[1].x : 0.f;
-                    ae[1].y = (pos < Q.last[3] && d[1].y >= 0.f) ? a[1].y : 0.f;
-                    any = (__float_as_uint(ae[0].x) | __float_as_uint(ae[0].y) | __float_as_uint(ae[1].x) |
-                           __float_as_uint(ae[1].y)) != 0u;
+                    // fast path: alpha = a (no clamp), contributes <=> pos < last && d >= 0 (d is -inf for a pixel
+                    // without contributors); a skipped pixel runs with alpha = 0, which makes every update a no-op
+                    // (T / 1 = T, AR + 0, zero weights).  In front of wmin the position test is true for every pixel.
+                    float2 ae[NH];
+                    if (pos < wmin) {
+#pragma unroll
+                        for (int q = 0; q < NQ; q++) GS_Q(ae, q) = GS_Q(d, q) >= 0.f ? GS_Q(a, q) : 0.f;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NQ; q++) GS_Q(ae, q) = (pos < Q.last[q] && GS_Q(d, q) >= 0.f) ? GS_Q(a, q) : 0.f;
+                    }
+                    uint32_t anyb = __float_as_uint(ae[0].x) | __float_as_uint(ae[0].y);
+                    if (NH == 2) anyb |= __float_as_uint(ae[NH - 1].x) | __float_as_uint(ae[NH - 1].y);
+                    any = anyb != 0u;
                     float2 c0 = bc(0.f), c1 = bc(0.f), c2 = bc(0.f), s0 = bc(0.f), sy = bc(0.f), syy = bc(0.f);
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
+                    for (int h = 0; h < NH; h++) {
                         const float2 om = fma2(ae[h], bc(-1.f), bc(1.f));                     // 1 - alpha
                         const float2 inv = make_float2(rcp_approx(om.x), rcp_approx(om.y));
                         Q.T[h] = mul2(Q.T[h], inv);                                           // T of the splats in front
@@ -520,15 +580,23 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
         }
         __syncthreads();
 #pragma unroll
-        for (int h = 0; h < kBatch / kThreads; h++) {
-            const int j = tid + h * kThreads;
+        for (int h = 0; h < kBatch / NT; h++) {
+            const int j = tid + h * NT;
             if (j < cnt) {
                 const uint32_t bit = 0x80000000u >> (j & 31);
-                const bool d0 = (sDone[0][j >> 5] & bit) != 0u, d1 = (sDone[1][j >> 5] & bit) != 0u;
-                if (d0 || d1) {
+                bool dn[NW];
+                bool anyd = false;
+#pragma unroll
+                for (int w = 0; w < NW; w++) { dn[w] = (sDone[w][j >> 5] & bit) != 0u; anyd = anyd || dn[w]; }
+                if (anyd) {
                     float r[9];
 #pragma unroll
-                    for (int k = 0; k < 9; k++) r[k] = (d0 ? sAcc[0][j * 9 + k] : 0.f) + (d1 ? sAcc[1][j * 9 + k] : 0.f);
+                    for (int k = 0; k < 9; k++) {
+                        float x = 0.f;
+#pragma unroll
+                        for (int w = 0; w < NW; w++) x += dn[w] ? sAcc[w][j * 9 + k] : 0.f;
+                        r[k] = x;
+                    }
                     float4* dst = acc + (size_t)3 * sRec[j].id;
                     // r[3..8] = sums of w, w dx, w dy, w dx dx, w dx dy, w dy dy (w = opacity G dL_dalpha) over the tile
                     const SRec& sr = sRec[j];
@@ -545,20 +613,34 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
 
 }  // namespace
 
-int g_gs_blend_variant = 0;           // GS_BLEND_VARIANT=1 selects the round-1 kernels (A/B measurements only)
+int g_gs_blend_variant = 0;           // GS_BLEND_VARIANT=1 selects the round-1 kernels (A/B measurements only);
+                                      // 2 / 3 force the 16x8 / 16x4 warp geometry of the current ones
+int g_gs_num_sms = 148;
+
+// 16x4 strips (4 warps per tile) when 16x8 blocks would leave the SMs with fewer than ~20 resident warps
+static bool use_strips(const GsView& v) {
+    if (g_gs_blend_variant == 2) return false;
+    if (g_gs_blend_variant == 3) return true;
+    return (long long)v.gx * v.gy * 2 < (long long)g_gs_num_sms * 20;
+}
 
 void gs_launch_blend_fwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const GsDevStatus* status, long long capacity, float* final_T, uint32_t* n_contrib,
                          float* out_color, float* out_depth, cudaStream_t s) {
     if (g_gs_blend_variant == 1) { gs_launch_blend_fwd_r1(v, tile_off, list, rec, status, capacity, final_T, n_contrib, out_color, out_depth, s); return; }
     dim3 grid(v.gx, v.gy);
-    k_blend_fwd<<<grid, kThreads, 0, s>>>(v, tile_off, list, rec, status, capacity, final_T, n_contrib, out_color,
-                                          out_depth);
+    if (use_strips(v))
+        k_blend_fwd<1><<<grid, Geo<1>::NT, 0, s>>>(v, tile_off, list, rec, status, capacity, final_T, n_contrib, out_color, out_depth);
+    else
+        k_blend_fwd<2><<<grid, Geo<2>::NT, 0, s>>>(v, tile_off, list, rec, status, capacity, final_T, n_contrib, out_color, out_depth);
 }
 void gs_launch_blend_bwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float4* acc,
-                         cudaStream_t s) {
+                         const GsDevStatus* status, long long capacity, cudaStream_t s) {
     if (g_gs_blend_variant == 1) { gs_launch_blend_bwd_r1(v, tile_off, list, rec, final_T, n_contrib, dL_dpix, acc, s); return; }
     dim3 grid(v.gx, v.gy);
-    k_blend_bwd<<<grid, kThreads, 0, s>>>(v, tile_off, list, rec, final_T, n_contrib, dL_dpix, acc);
+    if (use_strips(v))
+        k_blend_bwd<1><<<grid, Geo<1>::NT, 0, s>>>(v, tile_off, list, rec, final_T, n_contrib, dL_dpix, acc, status, capacity);
+    else
+        k_blend_bwd<2><<<grid, Geo<2>::NT, 0, s>>>(v, tile_off, list, rec, final_T, n_contrib, dL_dpix, acc, status, capacity);
 }

@@ -22,11 +22,199 @@ constexpr int kRow = GS_GOUT_FLOATS;
 
 constexpr int kVisT = 64;              // small CTAs: P_vis is often only a few 10^4, spread it over all SMs
 
+// One Gaussian's gradients from the 9 sums of the tile pass (a0, a1, a2 = its accumulator row): computeCov2DCUDA
+// (backward.cu:144-274), preprocessCUDA bwd (:346-396), SH bwd (:20-139), cov3D bwd (:278-341).  `fill_cf(cf, n)` loads
+// the first n SH coefficients of the Gaussian (global or shared memory).  Writes the 44-float row (11 float4) to o.
+template <typename FillCf>
+__device__ __forceinline__ void grad_row(const GsView& v, const GsCam& cam, const size_t i, const float4 a0, const float4 a1,
+                                         const float4 a2, const uint32_t clamped, const float* __restrict__ means3D,
+                                         const bool has_sh, const float* __restrict__ scales,
+                                         const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
+                                         FillCf fill_cf, float4* o) {
+    const float dm2x = a0.x, dm2y = a0.y, dop = a1.y;
+    const float dcx = a0.z, dcy = a0.w, dcz = a1.x;     // dL_dconic (a, b, c)
+    const float dcol0 = a1.z, dcol1 = a1.w, dcol2 = a2.x;
+    const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    float c6[6];
+    float3 sc = make_float3(0.f, 0.f, 0.f);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * i + k];
+    } else {
+        sc = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
+        q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
+        gs_cov3d(sc, v.scale_modifier, q, c6);
+    }
+    // ---- computeCov2DCUDA (backward.cu:144-274)
+    GsCov2D cc;
+    gs_cov2d(p, v, cam.vm, c6, cc);
+    const float a = cc.a, b = cc.b, cq = cc.c;
+    const float denom = a * cq - b * b;
+    float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    const float (*Tm)[3] = cc.A;
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (denom2inv != 0.f) {
+        dL_da = denom2inv * (-cq * cq * dcx + 2 * b * cq * dcy + (denom - a * cq) * dcz);
+        dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * cq) * dcx);
+        dL_db = denom2inv * 2 * (b * cq * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
+        dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
+        dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
+        dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
+        dcov[1] = 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
+        dcov[2] = 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
+        dcov[4] = 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
+    }
+    const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+    float dT[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float u0 = Tm[0][0] * S[k][0] + Tm[0][1] * S[k][1] + Tm[0][2] * S[k][2];
+        const float u1 = Tm[1][0] * S[k][0] + Tm[1][1] * S[k][1] + Tm[1][2] * S[k][2];
+        dT[0][k] = 2 * u0 * dL_da + u1 * dL_db;
+        dT[1][k] = 2 * u1 * dL_dc + u0 * dL_db;
+    }
+    const float* vm = cam.vm;
+    const float dJ00 = vm[0] * dT[0][0] + vm[4] * dT[0][1] + vm[8] * dT[0][2];
+    const float dJ02 = vm[2] * dT[0][0] + vm[6] * dT[0][1] + vm[10] * dT[0][2];
+    const float dJ11 = vm[1] * dT[1][0] + vm[5] * dT[1][1] + vm[9] * dT[1][2];
+    const float dJ12 = vm[2] * dT[1][0] + vm[6] * dT[1][1] + vm[10] * dT[1][2];
+    const float tz = 1.f / cc.tz, tz2 = tz * tz, tz3 = tz2 * tz;
+    const float dtx = cc.xmul * -v.focal_x * tz2 * dJ02;
+    const float dty = cc.ymul * -v.focal_y * tz2 * dJ12;
+    const float dtz = -v.focal_x * tz2 * dJ00 - v.focal_y * tz2 * dJ11 + (2 * v.focal_x * cc.tx) * tz3 * dJ02 +
+                      (2 * v.focal_y * cc.ty) * tz3 * dJ12;
+    float dm3x = vm[0] * dtx + vm[1] * dty + vm[2] * dtz;     // assignment (backward.cu:273)
+    float dm3y = vm[4] * dtx + vm[5] * dty + vm[6] * dtz;
+    float dm3z = vm[8] * dtx + vm[9] * dty + vm[10] * dtz;
+
+    // ---- preprocessCUDA backward (backward.cu:346-396): projection Jacobian
+    const float* pj = cam.pm;
+    const float4 m_hom = gs_xf4x4(p, pj);
+    const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+    const float mul1 = (pj[0] * p.x + pj[4] * p.y + pj[8] * p.z + pj[12]) * m_w * m_w;
+    const float mul2 = (pj[1] * p.x + pj[5] * p.y + pj[9] * p.z + pj[13]) * m_w * m_w;
+    dm3x += (pj[0] * m_w - pj[3] * mul1) * dm2x + (pj[1] * m_w - pj[3] * mul2) * dm2y;
+    dm3y += (pj[4] * m_w - pj[7] * mul1) * dm2x + (pj[5] * m_w - pj[7] * mul2) * dm2y;
+    dm3z += (pj[8] * m_w - pj[11] * mul1) * dm2x + (pj[9] * m_w - pj[11] * mul2) * dm2y;
+
+    // ---- SH backward (backward.cu:20-139)
+    float bs[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) bs[k] = 0.f;
+    float dRGB0 = 0.f, dRGB1 = 0.f, dRGB2 = 0.f;
+    if (has_sh) {
+        const float3 d0 = make_float3(p.x - cam.campos[0], p.y - cam.campos[1], p.z - cam.campos[2]);
+        const float len = sqrtf(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
+        const float x = d0.x / len, y = d0.y / len, z = d0.z / len;
+        dRGB0 = dcol0 * ((clamped & 1u) ? 0.f : 1.f);
+        dRGB1 = dcol1 * ((clamped & 2u) ? 0.f : 1.f);
+        dRGB2 = dcol2 * ((clamped & 4u) ? 0.f : 1.f);
+        gs_sh_basis(v.D, x, y, z, bs);
+        const int D = v.D;
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f;          // dL_ddir
+        if (D > 0) {
+            // all active coefficients in flight before use
+            float cf[48];
+            fill_cf(cf, (D + 1) * (D + 1) * 3);
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            const float dR[3] = {dRGB0, dRGB1, dRGB2};
+            float ax[3], ay[3], az[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+#define SHK(k) cf[3 * (k) + ch]
+                float vx = -GS_C1 * SHK(3), vy = -GS_C1 * SHK(1), vz = GS_C1 * SHK(2);
+                if (D > 1) {
+                    vx += GS_C2_0 * y * SHK(4) + GS_C2_2 * 2.f * -x * SHK(6) + GS_C2_3 * z * SHK(7) + GS_C2_4 * 2.f * x * SHK(8);
+                    vy += GS_C2_0 * x * SHK(4) + GS_C2_1 * z * SHK(5) + GS_C2_2 * 2.f * -y * SHK(6) + GS_C2_4 * 2.f * -y * SHK(8);
+                    vz += GS_C2_1 * y * SHK(5) + GS_C2_2 * 2.f * 2.f * z * SHK(6) + GS_C2_3 * x * SHK(7);
+                    if (D > 2) {
+                        vx += (GS_C3_0 * SHK(9) * 3.f * 2.f * xy + GS_C3_1 * SHK(10) * yz + GS_C3_2 * SHK(11) * -2.f * xy +
+                               GS_C3_3 * SHK(12) * -3.f * 2.f * xz + GS_C3_4 * SHK(13) * (-3.f * xx + 4.f * zz - yy) +
+                               GS_C3_5 * SHK(14) * 2.f * xz + GS_C3_6 * SHK(15) * 3.f * (xx - yy));
+                        vy += (GS_C3_0 * SHK(9) * 3.f * (xx - yy) + GS_C3_1 * SHK(10) * xz + GS_C3_2 * SHK(11) * (-3.f * yy + 4.f * zz - xx) +
+                               GS_C3_3 * SHK(12) * -3.f * 2.f * yz + GS_C3_4 * SHK(13) * -2.f * xy +
+                               GS_C3_5 * SHK(14) * -2.f * yz + GS_C3_6 * SHK(15) * -3.f * 2.f * xy);
+                        vz += (GS_C3_1 * SHK(10) * xy + GS_C3_2 * SHK(11) * 4.f * 2.f * yz + GS_C3_3 * SHK(12) * 3.f * (2.f * zz - xx - yy) +
+                               GS_C3_4 * SHK(13) * 4.f * 2.f * xz + GS_C3_5 * SHK(14) * (xx - yy));
+                    }
+                }
+#undef SHK
+                ax[ch] = vx; ay[ch] = vy; az[ch] = vz;
+            }
+            ddx = ax[0] * dR[0] + ax[1] * dR[1] + ax[2] * dR[2];
+            ddy = ay[0] * dR[0] + ay[1] * dR[1] + ay[2] * dR[2];
+            ddz = az[0] * dR[0] + az[1] * dR[1] + az[2] * dR[2];
+        }
+        // dnormvdv (auxiliary.h:107-117)
+        const float sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
+        const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+        dm3x += ((+sum2 - d0.x * d0.x) * ddx - d0.y * d0.x * ddy - d0.z * d0.x * ddz) * inv32;
+        dm3y += (-d0.x * d0.y * ddx + (sum2 - d0.y * d0.y) * ddy - d0.z * d0.y * ddz) * inv32;
+        dm3z += (-d0.x * d0.z * ddx - d0.y * d0.z * ddy + (sum2 - d0.z * d0.z) * ddz) * inv32;
+    }
+
+    // ---- cov3D backward (backward.cu:278-341)
+    float dsx = 0.f, dsy = 0.f, dsz = 0.f;
+    float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scales) {
+        float R[3][3], M[3][3];
+        gs_quat_R(q, R);
+        const float sv[3] = {v.scale_modifier * sc.x, v.scale_modifier * sc.y, v.scale_modifier * sc.z};
+#pragma unroll
+        for (int r_ = 0; r_ < 3; r_++)
+#pragma unroll
+            for (int c_ = 0; c_ < 3; c_++) M[r_][c_] = sv[r_] * R[c_][r_];
+        const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+        float dM[3][3];
+#pragma unroll
+        for (int r_ = 0; r_ < 3; r_++)
+#pragma unroll
+            for (int c_ = 0; c_ < 3; c_++)
+                dM[r_][c_] = 2.0f * (M[r_][0] * dS[0][c_] + M[r_][1] * dS[1][c_] + M[r_][2] * dS[2][c_]);
+        dsx = R[0][0] * dM[0][0] + R[1][0] * dM[0][1] + R[2][0] * dM[0][2];
+        dsy = R[0][1] * dM[1][0] + R[1][1] * dM[1][1] + R[2][1] * dM[1][2];
+        dsz = R[0][2] * dM[2][0] + R[1][2] * dM[2][1] + R[2][2] * dM[2][2];
+        float Q[3][3];
+#pragma unroll
+        for (int r_ = 0; r_ < 3; r_++)
+#pragma unroll
+            for (int c_ = 0; c_ < 3; c_++) Q[r_][c_] = dM[r_][c_] * sv[r_];
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        drot.x = 2 * z * (Q[0][1] - Q[1][0]) + 2 * y * (Q[2][0] - Q[0][2]) + 2 * x * (Q[1][2] - Q[2][1]);
+        drot.y = 2 * y * (Q[1][0] + Q[0][1]) + 2 * z * (Q[2][0] + Q[0][2]) + 2 * r * (Q[1][2] - Q[2][1]) - 4 * x * (Q[2][2] + Q[1][1]);
+        drot.z = 2 * x * (Q[1][0] + Q[0][1]) + 2 * r * (Q[2][0] - Q[0][2]) + 2 * z * (Q[1][2] + Q[2][1]) - 4 * y * (Q[2][2] + Q[0][0]);
+        drot.w = 2 * r * (Q[0][1] - Q[1][0]) + 2 * x * (Q[2][0] + Q[0][2]) + 2 * y * (Q[1][2] + Q[2][1]) - 4 * z * (Q[1][1] + Q[0][0]);
+    }
+
+    o[0] = make_float4(dm3x, dm3y, dm3z, dm2x);
+    o[1] = make_float4(dm2y, dop, dsx, dsy);
+    o[2] = make_float4(dsz, drot.x, drot.y, drot.z);
+    o[3] = make_float4(drot.w, dRGB0, dRGB1, dRGB2);
+    o[4] = make_float4(bs[0], bs[1], bs[2], bs[3]);
+    o[5] = make_float4(bs[4], bs[5], bs[6], bs[7]);
+    o[6] = make_float4(bs[8], bs[9], bs[10], bs[11]);
+    o[7] = make_float4(bs[12], bs[13], bs[14], bs[15]);
+    o[8] = make_float4(dcol0, dcol1, dcol2, dcov[0]);
+    o[9] = make_float4(dcov[1], dcov[2], dcov[3], dcov[4]);
+    o[10] = make_float4(dcov[5], 0.f, 0.f, 0.f);
+}
+
+// more than half of the Gaussians visible: the dense kernel (k_grad_dense) does the whole per-Gaussian backward
+__device__ __forceinline__ bool gs_dense_regime(const GsDevStatus* status, int P) {
+    return 2ull * status->num_visible > (unsigned long long)P;
+}
+
 __global__ void __launch_bounds__(kVisT)
 k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
            const float* __restrict__ scales, const float* __restrict__ rotations,
            const float* __restrict__ cov3D_precomp, const float4* __restrict__ rec, float4* __restrict__ acc,
-           const uint32_t* __restrict__ vis_list, const GsDevStatus* __restrict__ status, float* __restrict__ gout) {
+           const uint32_t* __restrict__ vis_list, const GsDevStatus* __restrict__ status, float* __restrict__ gout,
+           const bool dense_elsewhere) {
+    if (dense_elsewhere && gs_dense_regime(status, v.P)) return;
     __shared__ GsCam cam;
     gs_load_cam(v, &cam);
     const uint32_t nvis = (uint32_t)status->num_visible;
@@ -36,215 +224,126 @@ k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __res
         const float4 a0 = aa[0], a1 = aa[1], a2 = aa[2];
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, 0.f, 0.f, a2.w);   // re-arm, keep the compact slot
-        const float dm2x = a0.x, dm2y = a0.y, dop = a1.y;
-        const float dcx = a0.z, dcy = a0.w, dcz = a1.x;     // dL_dconic (a, b, c)
-        const float dcol0 = a1.z, dcol1 = a1.w, dcol2 = a2.x;
         const uint32_t clamped = __float_as_uint(__ldg(reinterpret_cast<const float*>(rec + (size_t)GS_REC_V4 * i + 2) + 2));
-
-        const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
-        float c6[6];
-        float3 sc = make_float3(0.f, 0.f, 0.f);
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cov3D_precomp) {
+        const float* sh = shs ? shs + (size_t)i * v.M * 3 : nullptr;
+        // scalar loads: rows need not be 16-byte aligned
+        auto fill = [&](float* cf, int na3) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * i + k];
-        } else {
-            sc = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
-            q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
-            gs_cov3d(sc, v.scale_modifier, q, c6);
-        }
-        // ---- computeCov2DCUDA (backward.cu:144-274)
-        GsCov2D cc;
-        gs_cov2d(p, v, cam.vm, c6, cc);
-        const float a = cc.a, b = cc.b, cq = cc.c;
-        const float denom = a * cq - b * b;
-        float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
-        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-        const float (*Tm)[3] = cc.A;
-        float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (denom2inv != 0.f) {
-            dL_da = denom2inv * (-cq * cq * dcx + 2 * b * cq * dcy + (denom - a * cq) * dcz);
-            dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * cq) * dcx);
-            dL_db = denom2inv * 2 * (b * cq * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
-            dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
-            dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
-            dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
-            dcov[1] = 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
-            dcov[2] = 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
-            dcov[4] = 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
-        }
-        const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
-        float dT[2][3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float u0 = Tm[0][0] * S[k][0] + Tm[0][1] * S[k][1] + Tm[0][2] * S[k][2];
-            const float u1 = Tm[1][0] * S[k][0] + Tm[1][1] * S[k][1] + Tm[1][2] * S[k][2];
-            dT[0][k] = 2 * u0 * dL_da + u1 * dL_db;
-            dT[1][k] = 2 * u1 * dL_dc + u0 * dL_db;
-        }
-        const float* vm = cam.vm;
-        const float dJ00 = vm[0] * dT[0][0] + vm[4] * dT[0][1] + vm[8] * dT[0][2];
-        const float dJ02 = vm[2] * dT[0][0] + vm[6] * dT[0][1] + vm[10] * dT[0][2];
-        const float dJ11 = vm[1] * dT[1][0] + vm[5] * dT[1][1] + vm[9] * dT[1][2];
-        const float dJ12 = vm[2] * dT[1][0] + vm[6] * dT[1][1] + vm[10] * dT[1][2];
-        const float tz = 1.f / cc.tz, tz2 = tz * tz, tz3 = tz2 * tz;
-        const float dtx = cc.xmul * -v.focal_x * tz2 * dJ02;
-        const float dty = cc.ymul * -v.focal_y * tz2 * dJ12;
-        const float dtz = -v.focal_x * tz2 * dJ00 - v.focal_y * tz2 * dJ11 + (2 * v.focal_x * cc.tx) * tz3 * dJ02 +
-                          (2 * v.focal_y * cc.ty) * tz3 * dJ12;
-        float dm3x = vm[0] * dtx + vm[1] * dty + vm[2] * dtz;     // assignment (backward.cu:273)
-        float dm3y = vm[4] * dtx + vm[5] * dty + vm[6] * dtz;
-        float dm3z = vm[8] * dtx + vm[9] * dty + vm[10] * dtz;
-
-        // ---- preprocessCUDA backward (backward.cu:346-396): projection Jacobian
-        const float* pj = cam.pm;
-        const float4 m_hom = gs_xf4x4(p, pj);
-        const float m_w = 1.0f / (m_hom.w + 0.0000001f);
-        const float mul1 = (pj[0] * p.x + pj[4] * p.y + pj[8] * p.z + pj[12]) * m_w * m_w;
-        const float mul2 = (pj[1] * p.x + pj[5] * p.y + pj[9] * p.z + pj[13]) * m_w * m_w;
-        dm3x += (pj[0] * m_w - pj[3] * mul1) * dm2x + (pj[1] * m_w - pj[3] * mul2) * dm2y;
-        dm3y += (pj[4] * m_w - pj[7] * mul1) * dm2x + (pj[5] * m_w - pj[7] * mul2) * dm2y;
-        dm3z += (pj[8] * m_w - pj[11] * mul1) * dm2x + (pj[9] * m_w - pj[11] * mul2) * dm2y;
-
-        // ---- SH backward (backward.cu:20-139)
-        float bs[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) bs[k] = 0.f;
-        float dRGB0 = 0.f, dRGB1 = 0.f, dRGB2 = 0.f;
-        if (shs) {
-            const float3 d0 = make_float3(p.x - cam.campos[0], p.y - cam.campos[1], p.z - cam.campos[2]);
-            const float len = sqrtf(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
-            const float x = d0.x / len, y = d0.y / len, z = d0.z / len;
-            dRGB0 = dcol0 * ((clamped & 1u) ? 0.f : 1.f);
-            dRGB1 = dcol1 * ((clamped & 2u) ? 0.f : 1.f);
-            dRGB2 = dcol2 * ((clamped & 4u) ? 0.f : 1.f);
-            gs_sh_basis(v.D, x, y, z, bs);
-            const int D = v.D;
-            float ddx = 0.f, ddy = 0.f, ddz = 0.f;          // dL_ddir
-            if (D > 0) {
-                // all active coefficients in flight before use (scalar loads: rows need not be 16-byte aligned)
-                const float* sh = shs + (size_t)i * v.M * 3;
-                float cf[48];
-                const int na3 = (D + 1) * (D + 1) * 3;
-#pragma unroll
-                for (int k = 0; k < 48; k++) cf[k] = k < na3 ? __ldg(sh + k) : 0.f;
-                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                const float dR[3] = {dRGB0, dRGB1, dRGB2};
-                float ax[3], ay[3], az[3];
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-#define SHK(k) cf[3 * (k) + ch]
-                    float vx = -GS_C1 * SHK(3), vy = -GS_C1 * SHK(1), vz = GS_C1 * SHK(2);
-                    if (D > 1) {
-                        vx += GS_C2_0 * y * SHK(4) + GS_C2_2 * 2.f * -x * SHK(6) + GS_C2_3 * z * SHK(7) + GS_C2_4 * 2.f * x * SHK(8);
-                        vy += GS_C2_0 * x * SHK(4) + GS_C2_1 * z * SHK(5) + GS_C2_2 * 2.f * -y * SHK(6) + GS_C2_4 * 2.f * -y * SHK(8);
-                        vz += GS_C2_1 * y * SHK(5) + GS_C2_2 * 2.f * 2.f * z * SHK(6) + GS_C2_3 * x * SHK(7);
-                        if (D > 2) {
-                            vx += (GS_C3_0 * SHK(9) * 3.f * 2.f * xy + GS_C3_1 * SHK(10) * yz + GS_C3_2 * SHK(11) * -2.f * xy +
-                                   GS_C3_3 * SHK(12) * -3.f * 2.f * xz + GS_C3_4 * SHK(13) * (-3.f * xx + 4.f * zz - yy) +
-                                   GS_C3_5 * SHK(14) * 2.f * xz + GS_C3_6 * SHK(15) * 3.f * (xx - yy));
-                            vy += (GS_C3_0 * SHK(9) * 3.f * (xx - yy) + GS_C3_1 * SHK(10) * xz + GS_C3_2 * SHK(11) * (-3.f * yy + 4.f * zz - xx) +
-                                   GS_C3_3 * SHK(12) * -3.f * 2.f * yz + GS_C3_4 * SHK(13) * -2.f * xy +
-                                   GS_C3_5 * SHK(14) * -2.f * yz + GS_C3_6 * SHK(15) * -3.f * 2.f * xy);
-                            vz += (GS_C3_1 * SHK(10) * xy + GS_C3_2 * SHK(11) * 4.f * 2.f * yz + GS_C3_3 * SHK(12) * 3.f * (2.f * zz - xx - yy) +
-                                   GS_C3_4 * SHK(13) * 4.f * 2.f * xz + GS_C3_5 * SHK(14) * (xx - yy));
-                        }
-                    }
-#undef SHK
-                    ax[ch] = vx; ay[ch] = vy; az[ch] = vz;
-                }
-                ddx = ax[0] * dR[0] + ax[1] * dR[1] + ax[2] * dR[2];
-                ddy = ay[0] * dR[0] + ay[1] * dR[1] + ay[2] * dR[2];
-                ddz = az[0] * dR[0] + az[1] * dR[1] + az[2] * dR[2];
-            }
-            // dnormvdv (auxiliary.h:107-117)
-            const float sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
-            const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-            dm3x += ((+sum2 - d0.x * d0.x) * ddx - d0.y * d0.x * ddy - d0.z * d0.x * ddz) * inv32;
-            dm3y += (-d0.x * d0.y * ddx + (sum2 - d0.y * d0.y) * ddy - d0.z * d0.y * ddz) * inv32;
-            dm3z += (-d0.x * d0.z * ddx - d0.y * d0.z * ddy + (sum2 - d0.z * d0.z) * ddz) * inv32;
-        }
-
-        // ---- cov3D backward (backward.cu:278-341)
-        float dsx = 0.f, dsy = 0.f, dsz = 0.f;
-        float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (scales) {
-            float R[3][3], M[3][3];
-            gs_quat_R(q, R);
-            const float sv[3] = {v.scale_modifier * sc.x, v.scale_modifier * sc.y, v.scale_modifier * sc.z};
-#pragma unroll
-            for (int r_ = 0; r_ < 3; r_++)
-#pragma unroll
-                for (int c_ = 0; c_ < 3; c_++) M[r_][c_] = sv[r_] * R[c_][r_];
-            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
-                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
-                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-            float dM[3][3];
-#pragma unroll
-            for (int r_ = 0; r_ < 3; r_++)
-#pragma unroll
-                for (int c_ = 0; c_ < 3; c_++)
-                    dM[r_][c_] = 2.0f * (M[r_][0] * dS[0][c_] + M[r_][1] * dS[1][c_] + M[r_][2] * dS[2][c_]);
-            dsx = R[0][0] * dM[0][0] + R[1][0] * dM[0][1] + R[2][0] * dM[0][2];
-            dsy = R[0][1] * dM[1][0] + R[1][1] * dM[1][1] + R[2][1] * dM[1][2];
-            dsz = R[0][2] * dM[2][0] + R[1][2] * dM[2][1] + R[2][2] * dM[2][2];
-            float Q[3][3];
-#pragma unroll
-            for (int r_ = 0; r_ < 3; r_++)
-#pragma unroll
-                for (int c_ = 0; c_ < 3; c_++) Q[r_][c_] = dM[r_][c_] * sv[r_];
-            const float r = q.x, x = q.y, y = q.z, z = q.w;
-            drot.x = 2 * z * (Q[0][1] - Q[1][0]) + 2 * y * (Q[2][0] - Q[0][2]) + 2 * x * (Q[1][2] - Q[2][1]);
-            drot.y = 2 * y * (Q[1][0] + Q[0][1]) + 2 * z * (Q[2][0] + Q[0][2]) + 2 * r * (Q[1][2] - Q[2][1]) - 4 * x * (Q[2][2] + Q[1][1]);
-            drot.z = 2 * x * (Q[1][0] + Q[0][1]) + 2 * r * (Q[2][0] - Q[0][2]) + 2 * z * (Q[1][2] + Q[2][1]) - 4 * y * (Q[2][2] + Q[0][0]);
-            drot.w = 2 * r * (Q[0][1] - Q[1][0]) + 2 * x * (Q[2][0] + Q[0][2]) + 2 * y * (Q[1][2] + Q[2][1]) - 4 * z * (Q[1][1] + Q[0][0]);
-        }
-
-        float4* o = reinterpret_cast<float4*>(gout + (size_t)c * kRow);
-        o[0] = make_float4(dm3x, dm3y, dm3z, dm2x);
-        o[1] = make_float4(dm2y, dop, dsx, dsy);
-        o[2] = make_float4(dsz, drot.x, drot.y, drot.z);
-        o[3] = make_float4(drot.w, dRGB0, dRGB1, dRGB2);
-        o[4] = make_float4(bs[0], bs[1], bs[2], bs[3]);
-        o[5] = make_float4(bs[4], bs[5], bs[6], bs[7]);
-        o[6] = make_float4(bs[8], bs[9], bs[10], bs[11]);
-        o[7] = make_float4(bs[12], bs[13], bs[14], bs[15]);
-        o[8] = make_float4(dcol0, dcol1, dcol2, dcov[0]);
-        o[9] = make_float4(dcov[1], dcov[2], dcov[3], dcov[4]);
-        o[10] = make_float4(dcov[5], 0.f, 0.f, 0.f);
+            for (int k = 0; k < 48; k++) cf[k] = k < na3 ? __ldg(sh + k) : 0.f;
+        };
+        grad_row(v, cam, i, a0, a1, a2, clamped, means3D, shs != nullptr, scales, rotations, cov3D_precomp, fill,
+                 reinterpret_cast<float4*>(gout + (size_t)c * kRow));
     }
 }
 
-// one CTA = 256 consecutive rows; s_slot[row] = CTA-local index of the row's staged gradient, or -1
-template <int NF>
+// Store phase shared by k_grad_write and k_grad_dense.  One CTA of NT threads = NT consecutive rows; s_slot[row] =
+// CTA-local index of the row's staged gradient (RS floats apart in s_row), or -1 for an invisible row (zeros).
+template <int NF, int NT, int RS>
 __device__ __forceinline__ void cta_store_rows(float* __restrict__ dst, const float* s_row, const int* s_slot, int off,
                                                long long row0, long long P) {
     const long long base = row0 * NF, lim = P * NF;
 #pragma unroll
     for (int k = 0; k < NF; k++) {
-        const int e = threadIdx.x + kT * k;
+        const int e = threadIdx.x + NT * k;
         const int row = e / NF, comp = e - row * NF;
         const int cl = s_slot[row];
-        if (base + e < lim) dst[base + e] = cl < 0 ? 0.f : s_row[cl * kRow + off + comp];
+        if (base + e < lim) dst[base + e] = cl < 0 ? 0.f : s_row[cl * RS + off + comp];
     }
 }
 
-// zeroes rows [row0, row0 + kT) of a dense [P, nf] tensor (nf floats per row); kT * nf is a multiple of 4
+// zeroes rows [row0, row0 + NT) of a dense [P, nf] tensor (nf floats per row); NT * nf is a multiple of 4
+template <int NT>
 __device__ __forceinline__ void cta_zero_run(float* __restrict__ base, long long row0, int nf) {
     if (!base || nf <= 0) return;
     float* p = base + row0 * nf;
-    const int total = kT * nf;
+    const int total = NT * nf;
     if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int f = threadIdx.x; f < (total >> 2); f += kT) reinterpret_cast<float4*>(p)[f] = z4;
+        for (int f = threadIdx.x; f < (total >> 2); f += NT) reinterpret_cast<float4*>(p)[f] = z4;
     } else {
-        for (int f = threadIdx.x; f < total; f += kT) p[f] = 0.f;
+        for (int f = threadIdx.x; f < total; f += NT) p[f] = 0.f;
+    }
+}
+
+// `cl` = s_slot[threadIdx.x]; `count` = number of visible rows of the CTA
+template <int NT, int RS>
+__device__ __forceinline__ void cta_write_block(const int P, const int M, const long long row0, const float* s_row,
+                                                const int* s_slot, const int cl, const int count, const GsGradPtrs& g) {
+    const int tid = threadIdx.x;
+    const long long i = row0 + tid;
+    if (count == 0 && row0 + NT <= P) {
+        // no visible row in this CTA (the common case when only a few per cent of the Gaussians are on screen):
+        // the NT rows of every output are one contiguous run -> straight 128-bit zero stores, no index maths
+        const int M3z = g.dsh ? M * 3 : 0;
+        cta_zero_run<NT>(g.dmeans3D, row0, 3); cta_zero_run<NT>(g.dmeans2D, row0, 3); cta_zero_run<NT>(g.dscales, row0, 3);
+        cta_zero_run<NT>(g.dcolors, row0, 3);  cta_zero_run<NT>(g.dcov3D, row0, 6);   cta_zero_run<NT>(g.dopacity, row0, 1);
+        cta_zero_run<NT>(g.drots, row0, 4);    cta_zero_run<NT>(g.dsh, row0, M3z);
+        return;
+    }
+    if (g.dmeans3D) cta_store_rows<3, NT, RS>(g.dmeans3D, s_row, s_slot, 0, row0, P);
+    if (g.dmeans2D) {
+        const long long base = row0 * 3, lim = (long long)P * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int e = tid + NT * k;
+            const int row = e / 3, comp = e - row * 3;
+            const int c2 = s_slot[row];
+            if (base + e < lim) g.dmeans2D[base + e] = (c2 < 0 || comp == 2) ? 0.f : s_row[c2 * RS + 3 + comp];
+        }
+    }
+    if (g.dscales) cta_store_rows<3, NT, RS>(g.dscales, s_row, s_slot, 6, row0, P);
+    if (g.dcolors) cta_store_rows<3, NT, RS>(g.dcolors, s_row, s_slot, 32, row0, P);
+    if (g.dcov3D) cta_store_rows<6, NT, RS>(g.dcov3D, s_row, s_slot, 35, row0, P);
+    if (i < P) {
+        if (g.dopacity) g.dopacity[i] = cl < 0 ? 0.f : s_row[cl * RS + 5];
+        if (g.drots) {
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cl >= 0) { const float* q = s_row + cl * RS + 9; r = make_float4(q[0], q[1], q[2], q[3]); }
+            if ((reinterpret_cast<uintptr_t>(g.drots) & 15) == 0) reinterpret_cast<float4*>(g.drots)[i] = r;
+            else { float* d = g.drots + 4 * i; d[0] = r.x; d[1] = r.y; d[2] = r.z; d[3] = r.w; }
+        }
+    }
+    if (g.dsh && M > 0) {
+        const int M3 = M * 3;
+        const long long rows = min((long long)NT, (long long)P - row0);
+        float* dst = g.dsh + row0 * M3;
+        const int total = (int)rows * M3;
+        if (M3 == 48 && (reinterpret_cast<uintptr_t>(g.dsh) & 15) == 0) {   // M = 16: 12 float4 per row
+            const int total4 = total >> 2;
+            for (int f = tid; f < total4; f += NT) {
+                const int row = f / 12, j = f - row * 12;
+                const int c2 = s_slot[row];
+                float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c2 >= 0) {
+                    const float* sb = s_row + c2 * RS + 16;
+                    const float* sr = s_row + c2 * RS + 13;
+                    float o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = 4 * j + u;
+                        const int k = e / 3, ch = e - 3 * k;
+                        o[u] = sb[k] * sr[ch];
+                    }
+                    o4 = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                reinterpret_cast<float4*>(dst)[f] = o4;
+            }
+        } else {
+            for (int e = tid; e < total; e += NT) {
+                const int row = e / M3, rem = e - row * M3;
+                const int k = rem / 3, ch = rem - 3 * k;
+                const int c2 = s_slot[row];
+                dst[e] = (c2 < 0 || k >= 16) ? 0.f : s_row[c2 * RS + 16 + k] * s_row[c2 * RS + 13 + ch];
+            }
+        }
     }
 }
 
 __global__ void __launch_bounds__(kT)
 k_grad_write(const int P, const int M, const int* __restrict__ radii, const float4* __restrict__ acc,
-             const float* __restrict__ gout, const GsGradPtrs g) {
+             const float* __restrict__ gout, const GsGradPtrs g, const GsDevStatus* __restrict__ status,
+             const bool dense_elsewhere) {
+    if (dense_elsewhere && gs_dense_regime(status, P)) return;
     extern __shared__ __align__(16) float s_row[];       // kT * kRow floats: staged compact rows of this CTA
     __shared__ int s_slot[kT];
     __shared__ int s_count;
@@ -271,72 +370,84 @@ k_grad_write(const int P, const int M, const int* __restrict__ radii, const floa
         for (int k = 0; k < kRow / 4; k++) dstr[k] = __ldg(src + k);
     }
     __syncthreads();
-    if (s_count == 0 && row0 + kT <= P) {
-        // no visible row in this CTA (the common case when only a few per cent of the Gaussians are on screen):
-        // the 256 rows of every output are one contiguous run -> straight 128-bit zero stores, no index maths
-        const int M3z = g.dsh ? M * 3 : 0;
-        cta_zero_run(g.dmeans3D, row0, 3); cta_zero_run(g.dmeans2D, row0, 3); cta_zero_run(g.dscales, row0, 3);
-        cta_zero_run(g.dcolors, row0, 3);  cta_zero_run(g.dcov3D, row0, 6);   cta_zero_run(g.dopacity, row0, 1);
-        cta_zero_run(g.drots, row0, 4);    cta_zero_run(g.dsh, row0, M3z);
-        return;
+    cta_write_block<kT, kRow>(P, M, row0, s_row, s_slot, cl, s_count, g);
+}
+
+// ---- dense regime (more than half of the Gaussians visible -- LucidDreamer's own workload: every Gaussian comes from a
+// pixel of a training view, luciddreamer.py:370-374): ONE kernel over all P rows replaces k_grad_vis + k_grad_write.
+// The compact 176-byte rows never go through HBM (they live in shared memory between the two phases), every global
+// access is row-contiguous, and the SH rows -- 192 B each, the bulk of the input -- arrive by TMA: every thread issues
+// one cp.async.bulk for its own row into a padded shared-memory slot (52 floats apart: conflict-free 128-bit reads) and
+// the CTA waits on one mbarrier while the other operands are loaded and the projection maths runs.
+constexpr int kDT = 128;               // rows per CTA
+constexpr int kDRS = 52;               // shared-memory row stride in floats (48 SH coefficients / 44 gradient floats)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kDT, 4)
+k_grad_dense(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
+             const float* __restrict__ scales, const float* __restrict__ rotations, const int* __restrict__ radii,
+             const float4* __restrict__ rec, float4* __restrict__ acc, const GsDevStatus* __restrict__ status,
+             const GsGradPtrs g) {
+    if (!gs_dense_regime(status, v.P)) return;
+    __shared__ __align__(16) float s_rows[kDT * kDRS];    // SH rows in, gradient rows out (same slot, same thread)
+    __shared__ int s_slot[kDT];
+    __shared__ int s_count;
+    __shared__ GsCam cam;
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kDT;
+    const long long i = row0 + tid;
+    const bool vis = i < v.P && radii[i] > 0;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        s_count = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (g.dmeans3D) cta_store_rows<3>(g.dmeans3D, s_row, s_slot, 0, row0, P);
-    if (g.dmeans2D) {
-        const long long base = row0 * 3, lim = (long long)P * 3;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int e = tid + kT * k;
-            const int row = e / 3, comp = e - row * 3;
-            const int c2 = s_slot[row];
-            if (base + e < lim) g.dmeans2D[base + e] = (c2 < 0 || comp == 2) ? 0.f : s_row[c2 * kRow + 3 + comp];
-        }
+    gs_load_cam(v, &cam);                                  // contains the __syncthreads that publishes the barrier
+    const int nv = __syncthreads_count(vis);
+    if (tid == 0) {
+        s_count = nv;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nv * 192) : "memory");
     }
-    if (g.dscales) cta_store_rows<3>(g.dscales, s_row, s_slot, 6, row0, P);
-    if (g.dcolors) cta_store_rows<3>(g.dcolors, s_row, s_slot, 32, row0, P);
-    if (g.dcov3D) cta_store_rows<6>(g.dcov3D, s_row, s_slot, 35, row0, P);
-    if (i < P) {
-        if (g.dopacity) g.dopacity[i] = cl < 0 ? 0.f : s_row[cl * kRow + 5];
-        if (g.drots) {
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cl >= 0) { const float* q = s_row + cl * kRow + 9; r = make_float4(q[0], q[1], q[2], q[3]); }
-            if ((reinterpret_cast<uintptr_t>(g.drots) & 15) == 0) reinterpret_cast<float4*>(g.drots)[i] = r;
-            else { float* d = g.drots + 4 * i; d[0] = r.x; d[1] = r.y; d[2] = r.z; d[3] = r.w; }
-        }
+    float* my = s_rows + tid * kDRS;
+    if (vis) {
+        // TMA: this Gaussian's 48 SH coefficients -> my shared-memory slot, completion counted on the CTA's mbarrier
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(my)), "l"(shs + (size_t)i * 48), "r"(192), "r"(bar) : "memory");
     }
-    if (g.dsh && M > 0) {
-        const int M3 = M * 3;
-        const long long rows = min((long long)kT, (long long)P - row0);
-        float* dst = g.dsh + row0 * M3;
-        const int total = (int)rows * M3;
-        if (M3 == 48 && (reinterpret_cast<uintptr_t>(g.dsh) & 15) == 0) {   // M = 16: 12 float4 per row
-            const int total4 = total >> 2;
-            for (int f = tid; f < total4; f += kT) {
-                const int row = f / 12, j = f - row * 12;
-                const int c2 = s_slot[row];
-                float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c2 >= 0) {
-                    const float* sb = s_row + c2 * kRow + 16;
-                    const float* sr = s_row + c2 * kRow + 13;
-                    float o[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int e = 4 * j + u;
-                        const int k = e / 3, ch = e - 3 * k;
-                        o[u] = sb[k] * sr[ch];
-                    }
-                    o4 = make_float4(o[0], o[1], o[2], o[3]);
-                }
-                reinterpret_cast<float4*>(dst)[f] = o4;
+    s_slot[tid] = vis ? tid : -1;
+    if (vis) {
+        float4* aa = acc + (size_t)3 * i;
+        const float4 a0 = aa[0], a1 = aa[1], a2 = aa[2];
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, 0.f, 0.f, a2.w);   // re-arm, keep the compact slot
+        const uint32_t clamped = __float_as_uint(__ldg(reinterpret_cast<const float*>(rec + (size_t)GS_REC_V4 * i + 2) + 2));
+        auto fill = [&](float* cf, int na3) {
+            // the SH rows of the CTA have landed when the mbarrier's phase 0 completes
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{.reg .pred p;\n\t"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;}" : "=r"(done) : "r"(bar), "r"(0) : "memory");
             }
-        } else {
-            for (int e = tid; e < total; e += kT) {
-                const int row = e / M3, rem = e - row * M3;
-                const int k = rem / 3, ch = rem - 3 * k;
-                const int c2 = s_slot[row];
-                dst[e] = (c2 < 0 || k >= 16) ? 0.f : s_row[c2 * kRow + 16 + k] * s_row[c2 * kRow + 13 + ch];
+            const float4* s4 = reinterpret_cast<const float4*>(my);
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                const float4 t = s4[k];
+                cf[4 * k] = t.x; cf[4 * k + 1] = t.y; cf[4 * k + 2] = t.z; cf[4 * k + 3] = t.w;
             }
-        }
+            (void)na3;
+        };
+        float4 o[11];
+        grad_row(v, cam, (size_t)i, a0, a1, a2, clamped, means3D, true, scales, rotations, nullptr, fill, o);
+        float4* d4 = reinterpret_cast<float4*>(my);        // my SH row is consumed: the gradient row takes its place
+#pragma unroll
+        for (int k = 0; k < 11; k++) d4[k] = o[k];
     }
+    __syncthreads();
+    cta_write_block<kDT, kDRS>(v.P, v.M, row0, s_rows, s_slot, vis ? tid : -1, s_count, g);
 }
 
 // Fused "final gradient -> peer reduce" for the shared-model data-parallel step: instead of writing
@@ -477,17 +588,26 @@ void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* a
 
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
-                        const uint32_t* vis_list, const GsDevStatus* status, float* gout, cudaStream_t s) {
+                        const uint32_t* vis_list, const GsDevStatus* status, float* gout, bool dense_elsewhere,
+                        cudaStream_t s) {
     const int need = (v.P + kVisT - 1) / kVisT;
     const int grid = need < num_sms * 8 ? need : num_sms * 8;
-    k_grad_vis<<<grid, kVisT, 0, s>>>(v, means3D, shs, scales, rotations, cov3D_precomp, rec, acc, vis_list, status, gout);
+    k_grad_vis<<<grid, kVisT, 0, s>>>(v, means3D, shs, scales, rotations, cov3D_precomp, rec, acc, vis_list, status, gout,
+                                      dense_elsewhere);
+}
+// the dense-regime twin of (k_grad_vis, k_grad_write): returns at once on the device unless most Gaussians are visible
+void gs_launch_grad_dense(const GsView& v, const float* means3D, const float* shs, const float* scales,
+                          const float* rotations, const int* radii, const float4* rec, float4* acc,
+                          const GsDevStatus* status, GsGradPtrs g, cudaStream_t s) {
+    const int grid = (v.P + kDT - 1) / kDT;
+    k_grad_dense<<<grid, kDT, 0, s>>>(v, means3D, shs, scales, rotations, radii, rec, acc, status, g);
 }
 void gs_grad_write_init() {
     cudaFuncSetAttribute(k_grad_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kRow * (int)sizeof(float));
     cudaFuncSetAttribute(k_grad_reduce_peers, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kRow * (int)sizeof(float));
 }
 void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
-                          cudaStream_t s) {
+                          const GsDevStatus* status, bool dense_elsewhere, cudaStream_t s) {
     const int grid = (P + kT - 1) / kT;
-    k_grad_write<<<grid, kT, kT * kRow * sizeof(float), s>>>(P, M, radii, acc, gout, g);
+    k_grad_write<<<grid, kT, kT * kRow * sizeof(float), s>>>(P, M, radii, acc, gout, g, status, dense_elsewhere);
 }

@@ -69,15 +69,18 @@ void fill_frame(Frame& fr, const c10::optional<at::Tensor>& bg, const at::Tensor
 
 #define GS_OK_OR_THROW(call) TORCH_CHECK((call) == 0, "gsraster: ", gs_last_error())
 
-// -> (num_rendered, color, depth, radii, geom, binning, img, pair_capacity, num_visible, num_pairs)
-std::tuple<int64_t, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, int64_t, int64_t, int64_t>
+// -> (num_rendered, color, depth, radii, geom, binning, img, pair_capacity, num_visible, num_pairs, ticket)
+// static_cap >= 0: sync-free forward (gsraster.h: gs_forward_counts_peek) -- the render is enqueued with exactly that pair
+// capacity and the host never waits; num_rendered / num_visible / num_pairs come back as -1 and the caller checks the
+// ticket later.  This is also the only mode that can be captured into a CUDA graph.
+std::tuple<int64_t, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, int64_t, int64_t, int64_t, int64_t>
 forward(int64_t ctx_ptr, const c10::optional<at::Tensor>& bg, const at::Tensor& means3D,
         const c10::optional<at::Tensor>& colors, const c10::optional<at::Tensor>& opacity,
         const c10::optional<at::Tensor>& scales, const c10::optional<at::Tensor>& rotations, double scale_modifier,
         const c10::optional<at::Tensor>& cov3D, const c10::optional<at::Tensor>& viewmatrix,
         const c10::optional<at::Tensor>& projmatrix, double tan_fovx, double tan_fovy, int64_t H, int64_t W,
         const c10::optional<at::Tensor>& sh, int64_t degree, const c10::optional<at::Tensor>& campos, bool prefiltered,
-        bool debug, int64_t pair_hint) {
+        bool debug, int64_t pair_hint, int64_t static_cap) {
     Frame fr;
     fill_frame(fr, bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D, viewmatrix, projmatrix, tan_fovx,
                tan_fovy, H, W, sh, degree, campos, prefiltered, debug);
@@ -98,6 +101,13 @@ forward(int64_t ctx_ptr, const c10::optional<at::Tensor>& bg, const at::Tensor& 
     GsCounts n{};
     at::Tensor binning;
     int64_t cap = 0;
+    if (static_cap >= 0) {
+        cap = round_cap((double)static_cap);
+        binning = at::empty({(int64_t)gs_binning_bytes(cap)}, u8);
+        GS_OK_OR_THROW(gs_forward_render(ctx, &fr.f, rad, geom.data_ptr(), binning.data_ptr(), cap, img.data_ptr(),
+                                         color.data_ptr<float>(), depth.data_ptr<float>(), 0, s));
+        return {-1, color, depth, radii, geom, binning, img, cap, -1, -1, (int64_t)ticket};
+    }
     if (pair_hint < 0) {
         // first frame on this device: learn the pair count (one event wait), then render
         GS_OK_OR_THROW(gs_forward_counts(ctx, ticket, &n));
@@ -120,7 +130,7 @@ forward(int64_t ctx_ptr, const c10::optional<at::Tensor>& bg, const at::Tensor& 
                                              color.data_ptr<float>(), depth.data_ptr<float>(), 1, s));
         }
     }
-    return {n.num_rendered, color, depth, radii, geom, binning, img, cap, n.num_visible, n.num_pairs};
+    return {n.num_rendered, color, depth, radii, geom, binning, img, cap, n.num_visible, n.num_pairs, (int64_t)ticket};
 }
 
 // -> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
@@ -176,6 +186,7 @@ backward(int64_t ctx_ptr, const c10::optional<at::Tensor>& bg, const at::Tensor&
 // ---- the autograd node itself in C++ (RAST/depth_diff_gaussian_rasterization_min/__init__.py:44-156): same inputs,
 // outputs (color, radii, depth), gradient order and None/zero conventions as the Python _RasterizeGaussians
 int64_t g_last_pairs[64] = {0};
+int64_t g_last_ticket[64] = {0};
 
 struct RasterizeFn : public torch::autograd::Function<RasterizeFn> {
     static torch::autograd::variable_list forward(torch::autograd::AutogradContext* ctx, at::Tensor means3D,
@@ -184,12 +195,13 @@ struct RasterizeFn : public torch::autograd::Function<RasterizeFn> {
                                                   at::Tensor viewmatrix, at::Tensor projmatrix, at::Tensor campos,
                                                   int64_t ctx_ptr, double scale_modifier, double tan_fovx, double tan_fovy,
                                                   int64_t H, int64_t W, int64_t degree, bool prefiltered, bool debug,
-                                                  int64_t pair_hint) {
+                                                  int64_t pair_hint, int64_t static_cap) {
         auto r = ::forward(ctx_ptr, bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D, viewmatrix,
-                           projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered, debug, pair_hint);
+                           projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered, debug, pair_hint,
+                           static_cap);
         at::Tensor color = std::get<1>(r), depth = std::get<2>(r), radii = std::get<3>(r);
         const int dev = means3D.device().index();
-        if (dev >= 0 && dev < 64) g_last_pairs[dev] = std::get<9>(r);
+        if (dev >= 0 && dev < 64) { g_last_pairs[dev] = std::get<9>(r); g_last_ticket[dev] = std::get<10>(r); }
         ctx->save_for_backward({radii, std::get<4>(r), std::get<5>(r), std::get<6>(r), means3D, sh, colors, opacity, scales,
                                 rotations, cov3D, bg, viewmatrix, projmatrix, campos});
         ctx->saved_data["ctx_ptr"] = ctx_ptr;
@@ -229,7 +241,7 @@ struct RasterizeFn : public torch::autograd::Function<RasterizeFn> {
         return {std::get<3>(g), std::get<0>(g), has(sh) ? std::get<5>(g) : none, std::get<1>(g), std::get<2>(g),
                 has(scales) ? std::get<6>(g) : none, has(rotations) ? std::get<7>(g) : none, std::get<4>(g),
                 none, none, none, none,                                        // bg, viewmatrix, projmatrix, campos
-                none, none, none, none, none, none, none, none, none, none};   // the ten non-tensor arguments
+                none, none, none, none, none, none, none, none, none, none, none};   // the eleven non-tensor arguments
     }
 };
 
@@ -239,14 +251,16 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> rasterize(at::Tensor means3D, at:
                                                          at::Tensor viewmatrix, at::Tensor projmatrix, at::Tensor campos,
                                                          int64_t ctx_ptr, double scale_modifier, double tan_fovx,
                                                          double tan_fovy, int64_t H, int64_t W, int64_t degree,
-                                                         bool prefiltered, bool debug, int64_t pair_hint) {
+                                                         bool prefiltered, bool debug, int64_t pair_hint,
+                                                         int64_t static_cap) {
     auto out = RasterizeFn::apply(means3D, means2D, sh, colors, opacity, scales, rotations, cov3D, bg, viewmatrix,
                                   projmatrix, campos, ctx_ptr, scale_modifier, tan_fovx, tan_fovy, H, W, degree, prefiltered,
-                                  debug, pair_hint);
+                                  debug, pair_hint, static_cap);
     return {out[0], out[1], out[2]};
 }
 
 int64_t last_pairs(int64_t dev) { return dev >= 0 && dev < 64 ? g_last_pairs[dev] : 0; }
+int64_t last_ticket(int64_t dev) { return dev >= 0 && dev < 64 ? g_last_ticket[dev] : -1; }
 
 }  // namespace
 
@@ -256,4 +270,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("backward", &backward);
     m.def("rasterize", &rasterize);
     m.def("last_pairs", &last_pairs);
+    m.def("last_ticket", &last_ticket);
 }

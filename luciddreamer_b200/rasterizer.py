@@ -40,6 +40,107 @@ def _note_pairs(idx: int, pairs: int) -> None:
     _last_pairs[idx] = int(pairs)
 
 
+# ---- sync-free ("static capacity") mode ------------------------------------------------------------------------------
+# The reference blocks the host once per forward (cudaMemcpy D2H of num_rendered, rasterizer_impl.cu:282); the default
+# path here waits once too (an event, for the pair count that sizes the binning buffer).  With a STATIC pair capacity
+# the forward is pure stream work: nothing waits, the call can be captured into a CUDA graph (graphs.GraphedStep), and
+# the host runs ahead of the GPU.  The price is a deferred check: a frame with more (tile, Gaussian) pairs than the
+# capacity renders NOTHING (device-side guard) and the error surfaces at the next rasterizer call / check_static().
+_static: dict = {}        # device index -> {"cap": int, "pending": deque[(ticket, cap)], "graph": [(ticket, cap)]}
+_last_counts: dict = {}   # device index -> dict(num_rendered, num_pairs, num_visible) of the last CHECKED static forward
+
+
+def set_static_capacity(pairs: Optional[int], device=None) -> None:
+    """pairs = N: every forward on `device` renders with room for exactly N (tile, Gaussian) pairs and never waits for
+    the GPU; pairs = None: back to the default (one event wait per forward, buffer sized from the frame's own count)."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if pairs is None:
+        if idx in _static:
+            _static[idx]["cap"] = None            # forwards already issued stay on the list until they are checked
+        return
+    st = _static.get(idx)
+    if st is None:
+        from collections import deque
+        st = _static[idx] = dict(cap=None, pending=deque(), graph=[])
+    st["cap"] = _round_cap(int(pairs))
+
+
+class static_capacity:
+    """`with static_capacity(N): ...` -- see set_static_capacity; restores the previous mode and checks on exit."""
+
+    def __init__(self, pairs: int, device=None):
+        self.pairs, self.device = pairs, device
+
+    def __enter__(self):
+        idx = torch.cuda.current_device() if self.device is None else torch.device(self.device).index
+        self.idx = idx
+        self.prev = (_static.get(idx) or {}).get("cap")
+        set_static_capacity(self.pairs, idx)
+        return self
+
+    def __exit__(self, *a):
+        set_static_capacity(self.prev, self.idx)
+        return False
+
+
+def _static_cap(idx: int) -> int:
+    st = _static.get(idx)
+    return -1 if st is None or st["cap"] is None else st["cap"]
+
+
+def _check_ticket(idx: int, ticket: int, cap: int, wait: bool) -> bool:
+    """True when the ticket has been checked (and was fine); False when the device has not written it yet."""
+    L = N.lib()
+    counts = N.GsCounts()
+    rc = L.gs_forward_counts_peek(_ctx(idx), int(ticket), C.byref(counts))
+    if rc == N.GS_ENOTREADY and wait and not (int(ticket) & 0x40000000):
+        rc = L.gs_forward_counts(_ctx(idx), int(ticket), C.byref(counts))
+    if rc == N.GS_ENOTREADY:
+        return False
+    N.check(rc)
+    _last_counts[idx] = dict(num_rendered=int(counts.num_rendered), num_pairs=int(counts.num_pairs),
+                             num_visible=int(counts.num_visible))
+    _note_pairs(idx, counts.num_pairs)
+    if counts.num_pairs > cap:
+        raise RuntimeError(
+            f"luciddreamer_b200: a forward rendered with static pair capacity {cap} had {int(counts.num_pairs)} (tile, "
+            "Gaussian) pairs; its outputs (and everything computed from them) are invalid. Raise the capacity "
+            "(set_static_capacity / GraphedStep(pair_capacity=...)) or use the default synchronising mode.")
+    return True
+
+
+def _poll_static(idx: int, wait: bool = False) -> None:
+    st = _static.get(idx)
+    if st is None:
+        return
+    pend = st["pending"]
+    while pend:
+        ticket, cap = pend[0]
+        if not _check_ticket(idx, ticket, cap, wait or len(pend) > 48):   # 64 status slots per context: never lap them
+            break
+        pend.popleft()
+
+
+def _note_static(idx: int, ticket: int, cap: int) -> None:
+    st = _static[idx]
+    if int(ticket) & 0x40000000:          # captured into a CUDA graph: the slot is rewritten by every replay
+        st["graph"].append((int(ticket), cap))
+    else:
+        st["pending"].append((int(ticket), cap))
+
+
+def check_static(device=None, synchronize: bool = True) -> dict:
+    """Checks every static-capacity forward issued so far on `device` (eager ones and the most recent replay of every
+    captured one); raises RuntimeError if one of them overflowed its capacity.  Returns the counts of the last one."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if synchronize:
+        torch.cuda.synchronize(idx)
+    _poll_static(idx, wait=True)
+    for ticket, cap in (_static.get(idx) or {}).get("graph", []):
+        _check_ticket(idx, ticket, cap, False)
+    return dict(_last_counts.get(idx, {}))
+
+
 def _ctx(dev_index: int) -> C.c_void_p:
     c = _contexts.get(dev_index)
     if c is None:
@@ -154,6 +255,7 @@ def _forward_impl(prep: _Prepared):
     f, dev, P = prep.frame, prep.device, prep.P
     H, W = f.H, f.W
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    _poll_static(idx)
     with _guard(idx):
         ctx = _ctx(idx)
         stream = _raw_stream(idx)
@@ -169,6 +271,15 @@ def _forward_impl(prep: _Prepared):
                                         C.byref(ticket)))
         counts = N.GsCounts()
         hint = _cap_hint.get(idx)
+        scap = _static_cap(idx)
+        if scap >= 0:
+            # sync-free: exactly the caller's capacity, no wait; the ticket is checked at a later call
+            cap = scap
+            binning = torch.empty((L.gs_binning_bytes(cap),), **u8)
+            N.check(L.gs_forward_render(ctx, C.byref(f), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), cap,
+                                        img.data_ptr(), color.data_ptr(), depth.data_ptr(), 0, stream))
+            _note_static(idx, ticket.value, cap)
+            return -1, color, depth, radii, geom, binning, img, (cap, P)
         if hint is None:
             # first frame on this device: learn the pair count (one event wait), then render
             N.check(L.gs_forward_counts(ctx, ticket, C.byref(counts)))
@@ -352,11 +463,19 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
         rs = raster_settings
         idx = means3D.device.index
         hint = _cap_hint.get(idx)
+        scap = -1
+        if _static:
+            _poll_static(idx)
+            scap = _static_cap(idx)
         color, radii, depth = fast.rasterize(
             means3D, _t(means2D), _t(sh), _t(colors_precomp), _t(opacities), _t(scales), _t(rotations), _t(cov3Ds_precomp),
             rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, _ctx(idx).value, rs.scale_modifier, rs.tanfovx, rs.tanfovy,
-            rs.image_height, rs.image_width, rs.sh_degree, bool(rs.prefiltered), bool(rs.debug), -1 if hint is None else hint)
-        _note_pairs(idx, fast.last_pairs(idx))
+            rs.image_height, rs.image_width, rs.sh_degree, bool(rs.prefiltered), bool(rs.debug), -1 if hint is None else hint,
+            scap)
+        if scap >= 0:
+            _note_static(idx, fast.last_ticket(idx), scap)
+        else:
+            _note_pairs(idx, fast.last_pairs(idx))
         return color, radii, depth
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                      cov3Ds_precomp, raster_settings)
@@ -377,11 +496,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raise RuntimeError("luciddreamer_b200: tensors must live on a CUDA device (no CPU fallback)")
             idx = means3D.device.index
             hint = _cap_hint.get(idx)
-            (num_rendered, color, depth, radii, geom, binning, img, cap, nvis, npairs) = fast.forward(
+            _poll_static(idx)
+            scap = _static_cap(idx)
+            (num_rendered, color, depth, radii, geom, binning, img, cap, nvis, npairs, ticket) = fast.forward(
                 _ctx(idx).value, rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
                 cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
-                rs.sh_degree, rs.campos, bool(rs.prefiltered), bool(rs.debug), -1 if hint is None else hint)
-            _note_pairs(idx, npairs)
+                rs.sh_degree, rs.campos, bool(rs.prefiltered), bool(rs.debug), -1 if hint is None else hint, scap)
+            if scap >= 0:
+                _note_static(idx, ticket, scap)
+            else:
+                _note_pairs(idx, npairs)
             ctx.num_rendered = num_rendered
             ctx.pair_capacity = (cap, nvis)
             ctx.prep = None

@@ -62,7 +62,10 @@ def refmods():
     yield types.SimpleNamespace(render=gaussian_renderer.render, GaussianModel=GaussianModel, GSParams=arguments.GSParams,
                                 BasicPointCloud=BasicPointCloud, refrast=refrast, ours=ours_rast)
     sys.path[:] = saved_path
-    for name in [m for m in sys.modules if m not in saved_mods]:
+    # drop only what this fixture put there: torch imports modules lazily (optimizer.step() pulls in torch._dynamo /
+    # torch._inductor), and deleting those would make a later import re-run their TORCH_LIBRARY registrations
+    ours = ("utils", "scene", "gaussian_renderer", "arguments", "refrast", "plyfile")
+    for name in [m for m in sys.modules if m not in saved_mods and m.split(".")[0] in ours]:
         del sys.modules[name]
 
 
