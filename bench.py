@@ -339,19 +339,25 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss, graphed
             ev_up[b].record(copy_s)
 
     graphs = None
+    dbg = os.environ.get("GS_E2E_SKIP", "")          # diagnostics only: "u" skips the uploads, "c" the camera copy, "l" the loss copy
 
     def run(n, base):
-        upload(base)
+        if "u" not in dbg:
+            upload(base)
         for k in range(base, base + n):
             b = k & 1
-            d_cam.copy_(h_cam, non_blocking=True)                 # 140 bytes, main stream; the operator reads it in place
-            main.wait_event(ev_up[b])
+            if "c" not in dbg:
+                d_cam.copy_(h_cam, non_blocking=True)             # 140 bytes, main stream; the operator reads it in place
+            if "u" not in dbg:
+                main.wait_event(ev_up[b])
             if graphs is not None:
                 loss = graphs[b].replay()
-                h_loss[k].copy_(loss.reshape(()), non_blocking=True)
-                ev_free[b].record(main)
-                if k + 1 < base + n:
-                    upload(k + 1)
+                if "l" not in dbg:
+                    h_loss[k].copy_(loss.reshape(()), non_blocking=True)
+                if "u" not in dbg:
+                    ev_free[b].record(main)
+                    if k + 1 < base + n:
+                        upload(k + 1)
                 continue
             color = impl.forward()
             if fused_loss:
@@ -646,6 +652,127 @@ def shared_model_leg(scene, cam, cot, dev, D, steps, warmup, world):
     return out
 
 
+def _maxrank(ms, world):
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def config4_leg(dev, rank, world, impl="ours", D=3, n_views=64, reps=3):
+    """BASELINE config 4 at its stated size: 1 M Gaussians, 64 views of the rotate360 path at 1920x1080, forward only,
+    views sharded round-robin over the ranks (strong scaling: 64 views in total whatever N is).  Ours: the batched C entry
+    point gs_forward_views with 1 and with 2 views in flight per GPU; reference arm (N = 1): its per-view loop."""
+    from luciddreamer_b200 import multiview as MV
+    from luciddreamer_b200 import rasterizer as R
+    W, H, P = 1920, 1080, 1_000_000
+    scene = syn.make_scene(P, 1004)
+    poses = syn.rotate360_poses(720)[::11][:n_views]          # every floor(720/64)-th frame (SURVEY.md 8d)
+    cams = [syn.make_camera(W, H, c2w=m) for m in poses]
+    out = {"P": P, "W": W, "H": H, "views": n_views, "views_per_rank": len(MV.shard_views(n_views, rank, world)), "reps": reps}
+
+    def timed(fn):
+        fn()                                                  # warm-up (learns the binning capacity)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return _maxrank(e0.elapsed_time(e1), world) / reps
+
+    if impl == "reference":
+        ref = RefCuda(scene, cams[0], dev, D)
+        ref.set_cameras(cams)
+        ref.order = np.arange(4096) % len(cams)
+
+        def loop():
+            ref.k = 0
+            for _ in range(n_views):
+                ref.forward()
+        ms = timed(loop)
+        out.update(ms_per_batch=ms, value=n_views * W * H / ms / 1e3, unit="Mrays/s", what="reference per-view loop")
+        return out
+    params = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    bg = torch.zeros(3, device=dev)
+    sl = [R.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, c.viewmatrix.to(dev), c.projmatrix.to(dev), D,
+                                          c.campos.to(dev), False, False) for c in cams]
+    for ns in (1, 2):
+        ms = timed(lambda: MV.render_views_batched(params, sl, rank, world, n_streams=ns))
+        out[f"in_flight_{ns}"] = {"ms_per_batch": ms, "value": n_views * W * H / ms / 1e3, "unit": "Mrays/s"}
+    best = min((1, 2), key=lambda ns: out[f"in_flight_{ns}"]["ms_per_batch"])
+    out.update(ms_per_batch=out[f"in_flight_{best}"]["ms_per_batch"], value=out[f"in_flight_{best}"]["value"], unit="Mrays/s",
+               views_in_flight=best, scaling="strong")
+    return out
+
+
+def config5_leg(dev, rank, world, D=3, steps=5, warmup=2):
+    """BASELINE config 5 at its stated size: 2 M Gaussians, 8 views of the llff path at 1920x1080, ONE shared-model
+    optimisation step = forward+backward of every view (8 / N per rank) + the sum of the per-Gaussian gradients over
+    all views of all ranks (472 MB bucket).  nccl: dense buckets + one all-reduce; fused: the final backward kernel of every
+    view adds its visible rows straight into every rank's symmetric bucket (multimem.red / peer stores)."""
+    from luciddreamer_b200 import multiview as MV
+    from luciddreamer_b200 import rasterizer as R
+    W, H, P, NV = 1920, 1080, 2_000_000, 8
+    scene = syn.make_scene(P, 1005)
+    cams = [syn.make_camera(W, H, c2w=m) for m in syn.llff_poses(400)[::50][:NV]]    # every 50th frame (SURVEY.md 8d)
+    params = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    bg = torch.zeros(3, device=dev)
+    sl = [R.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, c.viewmatrix.to(dev), c.projmatrix.to(dev), D,
+                                          c.campos.to(dev), False, False) for c in cams]
+    mine = MV.shard_views(NV, rank, world)
+    cots = [syn.make_cotangent(H, W, 1005 + v).to(dev) if v in mine else None for v in range(NV)]
+    M = params["shs"].shape[1]
+    out = {"P": P, "W": W, "H": H, "views": NV, "views_per_rank": len(mine), "bucket_bytes": P * (3 + 3 * M + 1 + 3 + 4) * 4}
+
+    def timed(step):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return _maxrank(e0.elapsed_time(e1), world) / steps
+
+    dense = MV.GradBucket(P, M, dev)
+
+    def step_nccl():
+        MV.multi_view_step(params, sl, cots, dense, rank, world)
+        MV.allreduce_bucket(dense)
+    ms = timed(step_nccl)
+    out["nccl_allreduce" if world > 1 else "single_gpu"] = {"ms_per_step": ms, "value": NV * W * H / ms / 1e3, "unit": "Mrays/s"}
+    out.update(ms_per_step=ms, value=NV * W * H / ms / 1e3, unit="Mrays/s", scaling="strong")
+    if world > 1:
+        try:
+            symm = MV.SymmGradBucket(P, M, dev)
+
+            def step_fused():
+                symm.begin_step()
+                MV.multi_view_step(params, sl, cots, symm, rank, world)
+                symm.end_step()
+            ms_f = timed(step_fused)
+            torch.cuda.synchronize()
+            err = float(((symm.flat - dense.flat).norm() / dense.flat.norm().clamp_min(1e-30)).item())
+            out["fused_peer_reduce"] = {"ms_per_step": ms_f, "value": NV * W * H / ms_f / 1e3, "unit": "Mrays/s",
+                                        "multicast": bool(symm.peers["mc"]), "rel_err_vs_nccl": err}
+            if ms_f < ms:
+                out.update(ms_per_step=ms_f, value=NV * W * H / ms_f / 1e3)
+        except Exception as ex:
+            out["fused_peer_reduce"] = {"unavailable": str(ex)[:200]}
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------- main
 
 def main():
@@ -661,6 +788,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared-model", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e through the eager loop only (no CUDA-graph step)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 4 / config 5 legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     os.environ.setdefault("OMP_PROC_BIND", "close")      # cpu_baseline: pinned OpenMP threads (read when libgomp starts)
@@ -757,6 +885,10 @@ def main():
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import make_traffic
+                if tj.get("sources_sha") != make_traffic.sources_sha():
+                    raise ValueError("profiles/traffic.json was captured from other kernel sources")   # -> traffic: null
                 traffic = tj.get(args.scene, {}).get(dom)
                 warp_inst = tj.get(args.scene + "_warp_inst", {}).get(dom)
             except Exception:
@@ -783,6 +915,21 @@ def main():
         if world > 1 and not args.no_shared_model:
             line["shared_model_step"] = shared_model_leg(scene, cam, cot, dev, D, args.steps, args.warmup, world)
 
+    if not args.no_configs and args.scene == "shell" and not args.P:
+        # BASELINE configs 4 and 5 at their stated sizes (every rank takes part; strong scaling over the view list)
+        cfgs = {}
+        del impl
+        torch.cuda.empty_cache()
+        for name, fn in (("config4_rotate360_64views_fwd", lambda: config4_leg(dev, rank, world, impl=args.impl)),
+                         ("config5_llff_8views_shared_model", lambda: config5_leg(dev, rank, world))):
+            if args.impl == "reference" and name.startswith("config5"):
+                continue                                  # the reference has no multi-view / multi-GPU step
+            try:
+                cfgs[name] = fn()
+            except Exception as ex:
+                cfgs[name] = {"error": str(ex)[:300]}
+            torch.cuda.empty_cache()
+        line["baseline_configs"] = cfgs
     if rank == 0 and world == 1 and args.impl == "ours" and not args.no_next_rows:
         nr = {}
         for name, fn in (("photometric_loss", lambda: loss_leg(H, W, dev)), ("optimizer_step", lambda: adam_leg(scene, dev)),

@@ -31,7 +31,9 @@ class GsGrads(C.Structure):
                 ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dscales", C.c_void_p),
                 ("dL_drotations", C.c_void_p), ("dL_dcov3D", C.c_void_p),
                 ("peer_world", C.c_int32), ("peer_pad", C.c_int32), ("peer_buckets", C.POINTER(C.c_void_p)),
-                ("peer_multicast", C.c_void_p), ("peer_seg_off", C.POINTER(C.c_int64))]
+                ("peer_multicast", C.c_void_p), ("peer_seg_off", C.POINTER(C.c_int64)),
+                ("peer_signals", C.POINTER(C.c_void_p)), ("peer_rank", C.c_int32), ("peer_epoch_begin", C.c_uint32),
+                ("peer_epoch_end", C.c_uint32), ("peer_pad2", C.c_int32)]
 
 
 class GsAdamGroup(C.Structure):

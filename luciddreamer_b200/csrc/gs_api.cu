@@ -155,6 +155,7 @@ int gs_context_create(int device, GsContext** out) {
     g_gs_num_sms = c->num_sms;
     gs_tile_sort_init();
     gs_grad_write_init();
+    gs_preprocess_init();
     if (const char* e = getenv("GS_BLEND_VARIANT")) g_gs_blend_variant = atoi(e);
     cudaError_t e = cudaHostAlloc((void**)&c->slots, sizeof(GsDevStatus) * (kSlots + kGraphSlots),
                                 cudaHostAllocMapped | cudaHostAllocPortable);
@@ -237,7 +238,7 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
         GS_TIMED(ctx, 0, s, gs_launch_project(v, f->means3D, f->opacities, f->scales, f->rotations, f->cov3D_precomp,
                                               radii, gl.rec, gl.vis_list, il.status, s));
         if ((rc = debug_sync(f, s, "project"))) return rc;
-        GS_TIMED(ctx, 8, s, gs_launch_count_tiles(v, ctx->num_sms, radii, gl.rec, gl.vis_list, il.tile_cnt, il.status, s));
+        GS_TIMED(ctx, 8, s, gs_launch_count_tiles(v, ctx->num_sms, radii, gl.rec, gl.vis_list, gl.hitmask, il.tile_cnt, il.status, s));
         if ((rc = debug_sync(f, s, "count_tiles"))) return rc;
     }
     GsDevStatus* dev_slot = nullptr;
@@ -307,8 +308,8 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
     GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
     GsBinLayout bl = gs_bin_layout(binning_buffer, pair_capacity > 0 ? pair_capacity : 1);
     GS_TIMED(ctx, 2, s, gs_launch_shade_emit(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs, f->colors_precomp, radii,
-                                             gl.rec, gl.acc, gl.vis_list, il.tile_off, il.tile_cnt, il.status, bl.keys,
-                                             pair_capacity, rerender != 0, s));
+                                             gl.rec, gl.acc, gl.vis_list, gl.hitmask, il.tile_off, il.tile_cnt, il.status,
+                                             bl.keys, pair_capacity, rerender != 0, s));
     if ((rc = debug_sync(f, s, "emit"))) return rc;
     {
         const bool prof = ctx && ctx->profile;
@@ -419,8 +420,12 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
     // When most Gaussians are visible (decided on the device from num_visible) ONE dense kernel does the whole
     // per-Gaussian backward and the compact pair below returns at once; otherwise the other way round.  The dense
     // kernel covers the reference's own input mode (SH degree <= 3 stored as 16 coefficients, scales + rotations).
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool dense_ok = grads->peer_world <= 0 && f->shs && f->M == 16 && !f->cov3D_precomp && f->scales && f->rotations &&
-                          !getenv("GS_NO_DENSE");
+                          !grads->dL_dcolors && !grads->dL_dcov3D && g.dmeans3D && g.dmeans2D && g.dsh && g.dopacity &&
+                          g.dscales && g.drots && al16(f->means3D) && al16(f->scales) && al16(g.dmeans3D) &&
+                          al16(g.dmeans2D) && al16(g.dsh) && al16(g.dopacity) && al16(g.dscales) && al16(g.drots) &&
+                          !getenv("GS_NO_DENSE");          // bulk copies need 16-byte aligned bases (gsraster.h)
     GS_TIMED(ctx, 7, s, gs_launch_grad_vis(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs,
                                            f->cov3D_precomp ? nullptr : f->scales,
                                            f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec, gl.acc,
@@ -432,14 +437,16 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
         if (grads->peer_world > GS_MAX_PEERS || !grads->peer_buckets) return fail(GS_EINVAL, "bad peer arguments");
         GS_TIMED(ctx, 9, s, gs_launch_grad_reduce_peers(f->P, v.M, radii, gl.acc, gout, grads->dL_dmeans2D,
                                                         (float* const*)grads->peer_buckets, grads->peer_world,
-                                                        (float*)grads->peer_multicast, (const long long*)grads->peer_seg_off, s));
+                                                        (float*)grads->peer_multicast, (const long long*)grads->peer_seg_off,
+                                                        (uint32_t* const*)grads->peer_signals, grads->peer_rank,
+                                                        grads->peer_epoch_begin, grads->peer_epoch_end, s));
         return debug_sync(f, s, "grad_reduce_peers");
     }
     GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, il.status, dense_ok, s));
     if ((rc = debug_sync(f, s, "grad_write"))) return rc;
     if (dense_ok) {
-        GS_TIMED(ctx, 10, s, gs_launch_grad_dense(v, f->means3D, f->shs, f->scales, f->rotations, radii, gl.rec, gl.acc,
-                                                  il.status, g, s));
+        GS_TIMED(ctx, 10, s, gs_launch_grad_dense(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs, f->scales, f->rotations,
+                                                  radii, gl.acc, il.status, g, s));
         if ((rc = debug_sync(f, s, "grad_dense"))) return rc;
     }
     // outputs the fused kernel does not produce in this input mode are defined as zeros (reference: torch::zeros)

@@ -310,8 +310,8 @@ k_blend_fwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
                 float tmin = fminf(tT[0].x, tT[0].y);
                 if (NH == 2) tmin = fminf(tmin, fminf(tT[NH - 1].x, tT[NH - 1].y));
                 // a pixel about to terminate (forward.cu:348-352; dead pixels keep T >= 1e-4 and never trigger), an
-                // alpha in the band or an ineligible splat: the whole warp takes the reference's sequence
-                if (__any_sync(0xffffffffu, band || tmin < 0.0001f) || r.generic) {
+                // alpha in the band or an ineligible splat: this thread takes the reference's sequence for its pixels
+                if (band || tmin < 0.0001f || r.generic) {
                     fwd_generic<NH>(P, r, dx, dy, p, a, band, pos1, rec);
                     continue;
                 }
@@ -374,7 +374,6 @@ __device__ __forceinline__ void warp_reduce9(float* v, const int lane) {
 
 template <int NH> struct BwdPix {
     float2 T[NH];
-    float2 nam[NH];                   // -1/255 for a pixel with contributors, -inf otherwise (same role as in FwdPix)
     float2 tb[NH];                    // -T_final * (bg . dL_dpixel)
     float2 AR[NH];                    // sum_ch accum_rec_ch * dL_dpixel_ch, already advanced past the last contributing splat
     float2 g0[NH], g1[NH], g2[NH];    // dL_dpixel
@@ -464,7 +463,7 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
     const size_t HW = (size_t)v.H * v.W;
     const float bgc0 = __ldg(v.bg), bgc1 = __ldg(v.bg + 1), bgc2 = __ldg(v.bg + 2);
     BwdPix<NH> Q;
-    int wmax = 0, wmin = 0x7fffffff;
+    int wmax = 0;
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
         const uint32_t py = pyb + 2 * q;
@@ -473,7 +472,6 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
         const float T_final = in ? final_Ts[pix_id] : 0.f;
         GS_Q(Q.T, q) = T_final;
         Q.last[q] = in ? (int)n_contrib[pix_id] : 0;
-        GS_Q(Q.nam, q) = Q.last[q] > 0 ? -kAlphaMin : kNegInf;
         const float g0 = in ? dL_dpix[pix_id] : 0.f, g1 = in ? dL_dpix[HW + pix_id] : 0.f, g2 = in ? dL_dpix[2 * HW + pix_id] : 0.f;
         GS_Q(Q.g0, q) = g0; GS_Q(Q.g1, q) = g1; GS_Q(Q.g2, q) = g2;
         float bd = 0.f;
@@ -481,17 +479,12 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
         GS_Q(Q.tb, q) = -T_final * bd;
         GS_Q(Q.AR, q) = 0.f;
         wmax = max(wmax, Q.last[q]);
-        if (Q.last[q] > 0) wmin = min(wmin, Q.last[q]);
     }
     const float ddelx_dx = 0.5 * v.W, ddely_dy = 0.5 * v.H;
 
-    // max of n_contrib over the warp's strip / over the tile: nothing behind it contributes.  wmin: the smallest
-    // n_contrib among the strip's pixels that have contributors -- in front of it every such pixel takes part.
+    // max of n_contrib over the warp's strip / over the tile: nothing behind it contributes
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-        wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
-    }
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     if (lane == 0) sMax[wid] = wmax;
     __syncthreads();
     int maxc = 0;
@@ -526,25 +519,22 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
                 float2 dy[NH], p[NH], g[NH], a[NH], d[NH];
 #pragma unroll
                 for (int h = 0; h < NH; h++) dy[h] = add2(bc(r.a.y), npy[h]);
-                const bool band = eval_alpha<NH>(r, dx, dy, Q.nam, p, g, a, d);
+                float2 nam[NH];
+#pragma unroll
+                for (int h = 0; h < NH; h++) nam[h] = bc(-kAlphaMin);
+                const bool band = eval_alpha<NH>(r, dx, dy, nam, p, g, a, d);
                 float vv[9];
                 bool any;
-                if (__any_sync(0xffffffffu, band) || r.generic) {
+                if (band || r.generic) {
 #pragma unroll
                     for (int q = 0; q < 9; q++) vv[q] = 0.f;
                     any = bwd_generic<NH>(Q, r, dx, dy, p, g, a, band, pos, rec, vv);
                 } else {
-                    // fast path: alpha = a (no clamp), contributes <=> pos < last && d >= 0 (d is -inf for a pixel
-                    // without contributors); a skipped pixel runs with alpha = 0, which makes every update a no-op
-                    // (T / 1 = T, AR + 0, zero weights).  In front of wmin the position test is true for every pixel.
+                    // fast path: alpha = a (no clamp), contributes <=> pos < last && d >= 0; a skipped pixel runs with
+                    // alpha = 0, which makes every update a no-op (T / 1 = T, AR + 0, zero weights)
                     float2 ae[NH];
-                    if (pos < wmin) {
 #pragma unroll
-                        for (int q = 0; q < NQ; q++) GS_Q(ae, q) = GS_Q(d, q) >= 0.f ? GS_Q(a, q) : 0.f;
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < NQ; q++) GS_Q(ae, q) = (pos < Q.last[q] && GS_Q(d, q) >= 0.f) ? GS_Q(a, q) : 0.f;
-                    }
+                    for (int q = 0; q < NQ; q++) GS_Q(ae, q) = (pos < Q.last[q] && GS_Q(d, q) >= 0.f) ? GS_Q(a, q) : 0.f;
                     uint32_t anyb = __float_as_uint(ae[0].x) | __float_as_uint(ae[0].y);
                     if (NH == 2) anyb |= __float_as_uint(ae[NH - 1].x) | __float_as_uint(ae[NH - 1].y);
                     any = anyb != 0u;

@@ -9,7 +9,7 @@
 //                          forward; consumed and re-zeroed by the backward)
 //                          a0 = (dmean2D.x, dmean2D.y, dconic.a, dconic.b)
 //                          a1 = (dconic.c, dopacity, dcolor.r, dcolor.g)
-//                          a2 = (dcolor.b, 0, 0, compact slot)
+//                          a2 = (dcolor.b, SH clamp bits, 0, compact slot)
 //  image buffer  final_T[N] f32 | n_contrib[N] u32 | tile_off[G+1] u32 | tile_cnt[G] u32 | status
 //  binning       keys[C] u64 = (depth_bits << 32 | gaussian_idx)  |  list[C] u32 (per tile, depth sorted)
 #pragma once
@@ -62,6 +62,7 @@ struct GsGeomLayout {
     float4* rec;          // [P][3]
     float4* acc;          // [P][3]
     uint32_t* vis_list;   // [P] compact list of visible Gaussian indices (first num_visible entries valid)
+    uint32_t* hitmask;    // [P] per compact slot: which tiles of a small rect the splat reaches (histogram -> emission)
     size_t bytes;
 };
 __host__ inline GsGeomLayout gs_geom_layout(void* base, int P) {
@@ -71,6 +72,7 @@ __host__ inline GsGeomLayout gs_geom_layout(void* base, int P) {
     L.rec = (float4*)(p + off); off = gs_align_up(off + (size_t)P * 48, 256);
     L.acc = (float4*)(p + off); off = gs_align_up(off + (size_t)P * 48, 256);
     L.vis_list = (uint32_t*)(p + off); off = gs_align_up(off + (size_t)P * 4, 256);
+    L.hitmask = (uint32_t*)(p + off); off = gs_align_up(off + (size_t)P * 4, 256);
     L.bytes = off;
     return L;
 }
@@ -289,13 +291,14 @@ void gs_launch_project(const GsView& v, const float* means3D, const float* opaci
                        const float* rotations, const float* cov3D_precomp, int* radii, float4* rec,
                        uint32_t* vis_list, GsDevStatus* status, cudaStream_t s);
 void gs_launch_count_tiles(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
-                           uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s);
+                           uint32_t* hitmask, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s);
+void gs_preprocess_init();
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status,
                          GsDevStatus* host_slot, cudaStream_t s);
 void gs_launch_shade_emit(const GsView& v, int num_sms, const float* means3D, const float* shs,
                           const float* colors_precomp, const int* radii, float4* rec, float4* acc,
-                          const uint32_t* vis_list, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
-                          unsigned long long* keys, long long capacity, bool shaded, cudaStream_t s);
+                          const uint32_t* vis_list, const uint32_t* hitmask, const uint32_t* tile_off, uint32_t* tile_cur,
+                          GsDevStatus* status, unsigned long long* keys, long long capacity, bool shaded, cudaStream_t s);
 void gs_tile_sort_init();
 void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
                          uint32_t* big_list, unsigned long long* keys, uint32_t* list, long long capacity,
@@ -318,14 +321,15 @@ void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, cons
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
                         const uint32_t* vis_list, const GsDevStatus* status, float* gout, bool dense_elsewhere,
                         cudaStream_t s);
-void gs_launch_grad_dense(const GsView& v, const float* means3D, const float* shs, const float* scales,
-                          const float* rotations, const int* radii, const float4* rec, float4* acc,
-                          const GsDevStatus* status, GsGradPtrs g, cudaStream_t s);
+void gs_launch_grad_dense(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
+                          const float* rotations, const int* radii, float4* acc, const GsDevStatus* status, GsGradPtrs g,
+                          cudaStream_t s);
 void gs_grad_write_init();
 void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
                           const GsDevStatus* status, bool dense_elsewhere, cudaStream_t s);
 void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* acc, const float* gout, float* dmeans2D,
                                  float* const* peers, int world, float* mc, const long long* seg_off,
+                                 uint32_t* const* signals, int rank, uint32_t epoch_begin, uint32_t epoch_end,
                                  cudaStream_t s);
 void gs_launch_l1_loss_grad(const float* color, const uint8_t* target, int H, int W, float weight, float* dL_dcolor,
                             float* loss, int num_sms, cudaStream_t s);

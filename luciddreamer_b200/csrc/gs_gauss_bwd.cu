@@ -25,27 +25,16 @@ constexpr int kVisT = 64;              // small CTAs: P_vis is often only a few 
 // One Gaussian's gradients from the 9 sums of the tile pass (a0, a1, a2 = its accumulator row): computeCov2DCUDA
 // (backward.cu:144-274), preprocessCUDA bwd (:346-396), SH bwd (:20-139), cov3D bwd (:278-341).  `fill_cf(cf, n)` loads
 // the first n SH coefficients of the Gaussian (global or shared memory).  Writes the 44-float row (11 float4) to o.
+// `scales` true: sc / q hold the scale and the quaternion (cov3D is derived); false: c6 holds cov3D_precomp.
 template <typename FillCf>
-__device__ __forceinline__ void grad_row(const GsView& v, const GsCam& cam, const size_t i, const float4 a0, const float4 a1,
-                                         const float4 a2, const uint32_t clamped, const float* __restrict__ means3D,
-                                         const bool has_sh, const float* __restrict__ scales,
-                                         const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
-                                         FillCf fill_cf, float4* o) {
+__device__ __forceinline__ void grad_row_core(const GsView& v, const GsCam& cam, const float4 a0, const float4 a1,
+                                              const float4 a2, const uint32_t clamped, const float3 p, const bool has_sh,
+                                              const bool scales, const float3 sc, const float4 q, float* c6,
+                                              FillCf fill_cf, float4* o) {
     const float dm2x = a0.x, dm2y = a0.y, dop = a1.y;
     const float dcx = a0.z, dcy = a0.w, dcz = a1.x;     // dL_dconic (a, b, c)
     const float dcol0 = a1.z, dcol1 = a1.w, dcol2 = a2.x;
-    const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
-    float c6[6];
-    float3 sc = make_float3(0.f, 0.f, 0.f);
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cov3D_precomp) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * i + k];
-    } else {
-        sc = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
-        q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
-        gs_cov3d(sc, v.scale_modifier, q, c6);
-    }
+    if (scales) gs_cov3d(sc, v.scale_modifier, q, c6);
     // ---- computeCov2DCUDA (backward.cu:144-274)
     GsCov2D cc;
     gs_cov2d(p, v, cam.vm, c6, cc);
@@ -203,6 +192,27 @@ __device__ __forceinline__ void grad_row(const GsView& v, const GsCam& cam, cons
     o[10] = make_float4(dcov[5], 0.f, 0.f, 0.f);
 }
 
+// operands from global memory (compact-list kernel)
+template <typename FillCf>
+__device__ __forceinline__ void grad_row(const GsView& v, const GsCam& cam, const size_t i, const float4 a0, const float4 a1,
+                                         const float4 a2, const uint32_t clamped, const float* __restrict__ means3D,
+                                         const bool has_sh, const float* __restrict__ scales,
+                                         const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
+                                         FillCf fill_cf, float4* o) {
+    const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    float c6[6];
+    float3 sc = make_float3(0.f, 0.f, 0.f);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * i + k];
+    } else {
+        sc = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
+        q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
+    }
+    grad_row_core(v, cam, a0, a1, a2, clamped, p, has_sh, cov3D_precomp == nullptr, sc, q, c6, fill_cf, o);
+}
+
 // more than half of the Gaussians visible: the dense kernel (k_grad_dense) does the whole per-Gaussian backward
 __device__ __forceinline__ bool gs_dense_regime(const GsDevStatus* status, int P) {
     return 2ull * status->num_visible > (unsigned long long)P;
@@ -223,8 +233,8 @@ k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __res
         float4* aa = acc + (size_t)3 * i;
         const float4 a0 = aa[0], a1 = aa[1], a2 = aa[2];
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, 0.f, 0.f, a2.w);   // re-arm, keep the compact slot
-        const uint32_t clamped = __float_as_uint(__ldg(reinterpret_cast<const float*>(rec + (size_t)GS_REC_V4 * i + 2) + 2));
+        aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, a2.y, 0.f, a2.w);  // re-arm; keep the clamp bits + compact slot
+        const uint32_t clamped = __float_as_uint(a2.y);
         const float* sh = shs ? shs + (size_t)i * v.M * 3 : nullptr;
         // scalar loads: rows need not be 16-byte aligned
         auto fill = [&](float* cf, int na3) {
@@ -374,80 +384,176 @@ k_grad_write(const int P, const int M, const int* __restrict__ radii, const floa
 }
 
 // ---- dense regime (more than half of the Gaussians visible -- LucidDreamer's own workload: every Gaussian comes from a
-// pixel of a training view, luciddreamer.py:370-374): ONE kernel over all P rows replaces k_grad_vis + k_grad_write.
-// The compact 176-byte rows never go through HBM (they live in shared memory between the two phases), every global
-// access is row-contiguous, and the SH rows -- 192 B each, the bulk of the input -- arrive by TMA: every thread issues
-// one cp.async.bulk for its own row into a padded shared-memory slot (52 floats apart: conflict-free 128-bit reads) and
-// the CTA waits on one mbarrier while the other operands are loaded and the projection maths runs.
-constexpr int kDT = 128;               // rows per CTA
-constexpr int kDRS = 52;               // shared-memory row stride in floats (48 SH coefficients / 44 gradient floats)
+// pixel of a training view, luciddreamer.py:370-374): ONE persistent kernel over all P rows replaces k_grad_vis +
+// k_grad_write, built as a TMA pipeline.  A CTA owns blocks of 128 CONSECUTIVE Gaussians; everything such a block reads
+// (SH rows 24 KB, accumulator rows 6 KB, means, scales, rotations) and writes (the six dense gradient tensors) is one
+// contiguous run per tensor, so
+//   in :  5 cp.async.bulk loads per block into one of two shared-memory stages, completion on the stage's mbarrier;
+//         the loads of block k+1 are in flight while block k is computed (double buffering);
+//   out:  every thread leaves its row's gradients in shared memory (the dL_dsh row = basis x dRGB takes the place of
+//         the consumed SH row) and 6 cp.async.bulk stores per block write them out -- no index arithmetic, no
+//         uncoalesced access, and the compact 176-byte rows of the sparse path never exist.
+constexpr int kDT = 128;               // rows per block = threads per CTA
+struct DenseStage {                    // byte offsets inside one stage
+    static constexpr int sh = 0, acc = 24576, means = 30720, scales = 32256, rot = 33792, dm2 = 35840, dop = 37376,
+                         bytes = 37888;
+};
+constexpr int kDenseSmem = 2 * DenseStage::bytes;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
 
-__global__ void __launch_bounds__(kDT, 4)
+__global__ void __launch_bounds__(kDT, 3)
 k_grad_dense(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
              const float* __restrict__ scales, const float* __restrict__ rotations, const int* __restrict__ radii,
-             const float4* __restrict__ rec, float4* __restrict__ acc, const GsDevStatus* __restrict__ status,
-             const GsGradPtrs g) {
+             float4* __restrict__ acc, const GsDevStatus* __restrict__ status, const GsGradPtrs g) {
     if (!gs_dense_regime(status, v.P)) return;
-    __shared__ __align__(16) float s_rows[kDT * kDRS];    // SH rows in, gradient rows out (same slot, same thread)
-    __shared__ int s_slot[kDT];
-    __shared__ int s_count;
+    extern __shared__ __align__(128) unsigned char s_dense[];
     __shared__ GsCam cam;
-    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x;
-    const long long row0 = (long long)blockIdx.x * kDT;
-    const long long i = row0 + tid;
-    const bool vis = i < v.P && radii[i] > 0;
-    const uint32_t bar = smem_u32(&s_bar);
+    const int nfull = v.P / kDT;                           // full blocks take the TMA pipeline
     if (tid == 0) {
-        s_count = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[1])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    gs_load_cam(v, &cam);                                  // contains the __syncthreads that publishes the barrier
-    const int nv = __syncthreads_count(vis);
-    if (tid == 0) {
-        s_count = nv;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nv * 192) : "memory");
-    }
-    float* my = s_rows + tid * kDRS;
-    if (vis) {
-        // TMA: this Gaussian's 48 SH coefficients -> my shared-memory slot, completion counted on the CTA's mbarrier
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(my)), "l"(shs + (size_t)i * 48), "r"(192), "r"(bar) : "memory");
-    }
-    s_slot[tid] = vis ? tid : -1;
-    if (vis) {
-        float4* aa = acc + (size_t)3 * i;
-        const float4 a0 = aa[0], a1 = aa[1], a2 = aa[2];
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, 0.f, 0.f, a2.w);   // re-arm, keep the compact slot
-        const uint32_t clamped = __float_as_uint(__ldg(reinterpret_cast<const float*>(rec + (size_t)GS_REC_V4 * i + 2) + 2));
-        auto fill = [&](float* cf, int na3) {
-            // the SH rows of the CTA have landed when the mbarrier's phase 0 completes
+    gs_load_cam(v, &cam);                                  // contains the __syncthreads that publishes the barriers
+
+    auto issue_loads = [&](int blk, int st) {              // one thread
+        const size_t row0 = (size_t)blk * kDT;
+        const uint32_t base = smem_u32(s_dense + st * DenseStage::bytes), bar = smem_u32(&s_bar[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(DenseStage::dm2) : "memory");
+        tma_load(base + DenseStage::sh, shs + row0 * 48, 24576, bar);
+        tma_load(base + DenseStage::acc, acc + row0 * 3, 6144, bar);
+        tma_load(base + DenseStage::means, means3D + row0 * 3, 1536, bar);
+        tma_load(base + DenseStage::scales, scales + row0 * 3, 1536, bar);
+        tma_load(base + DenseStage::rot, rotations + row0 * 4, 2048, bar);
+    };
+
+    int it = 0;
+    if (tid == 0 && (int)blockIdx.x < nfull) issue_loads(blockIdx.x, 0);
+    for (int blk = blockIdx.x; blk < nfull; blk += gridDim.x, it++) {
+        const int st = it & 1;
+        unsigned char* S = s_dense + st * DenseStage::bytes;
+        const size_t row0 = (size_t)blk * kDT, i = row0 + tid;
+        if (tid == 0) {
+            // the other stage is free once the bulk stores issued from it (previous iteration) have read it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (blk + (int)gridDim.x < nfull) issue_loads(blk + gridDim.x, st ^ 1);
+        }
+        const bool vis = radii[i] > 0;
+        {
             uint32_t done = 0;
+            const uint32_t bar = smem_u32(&s_bar[st]), parity = (it >> 1) & 1;
             while (!done) {
                 asm volatile("{.reg .pred p;\n\t"
                              "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                             "selp.u32 %0, 1, 0, p;}" : "=r"(done) : "r"(bar), "r"(0) : "memory");
+                             "selp.u32 %0, 1, 0, p;}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
             }
-            const float4* s4 = reinterpret_cast<const float4*>(my);
-#pragma unroll
-            for (int k = 0; k < 12; k++) {
-                const float4 t = s4[k];
-                cf[4 * k] = t.x; cf[4 * k + 1] = t.y; cf[4 * k + 2] = t.z; cf[4 * k + 3] = t.w;
-            }
-            (void)na3;
-        };
+        }
+        float* s_sh = reinterpret_cast<float*>(S + DenseStage::sh) + tid * 48;
+        float* s_m = reinterpret_cast<float*>(S + DenseStage::means) + tid * 3;
+        float* s_s = reinterpret_cast<float*>(S + DenseStage::scales) + tid * 3;
+        float4* s_r = reinterpret_cast<float4*>(S + DenseStage::rot) + tid;
+        float* s_dm2 = reinterpret_cast<float*>(S + DenseStage::dm2) + tid * 3;
+        float* s_dop = reinterpret_cast<float*>(S + DenseStage::dop) + tid;
         float4 o[11];
-        grad_row(v, cam, (size_t)i, a0, a1, a2, clamped, means3D, true, scales, rotations, nullptr, fill, o);
-        float4* d4 = reinterpret_cast<float4*>(my);        // my SH row is consumed: the gradient row takes its place
+        if (vis) {
+            const float4* sa = reinterpret_cast<const float4*>(S + DenseStage::acc) + tid * 3;
+            const float4 a0 = sa[0], a1 = sa[1], a2 = sa[2];
+            float4* aa = acc + i * 3;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, a2.y, 0.f, a2.w);  // re-arm; keep the clamp bits + compact slot
+            const float3 p = make_float3(s_m[0], s_m[1], s_m[2]);
+            const float3 sc = make_float3(s_s[0], s_s[1], s_s[2]);
+            const float4 q = *s_r;
+            auto fill = [&](float* cf, int) {
+                const float4* s4 = reinterpret_cast<const float4*>(s_sh);
 #pragma unroll
-        for (int k = 0; k < 11; k++) d4[k] = o[k];
+                for (int k = 0; k < 12; k++) {
+                    const float4 t = s4[k];
+                    cf[4 * k] = t.x; cf[4 * k + 1] = t.y; cf[4 * k + 2] = t.z; cf[4 * k + 3] = t.w;
+                }
+            };
+            float c6[6];
+            grad_row_core(v, cam, a0, a1, a2, __float_as_uint(a2.y), p, true, true, sc, q, c6, fill, o);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 11; k++) o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // every thread writes only slots it alone read: its SH row, mean, scale, rotation (dm2 / dop have their own)
+        s_m[0] = o[0].x; s_m[1] = o[0].y; s_m[2] = o[0].z;                       // dL_dmeans3D
+        s_dm2[0] = o[0].w; s_dm2[1] = o[1].x; s_dm2[2] = 0.f;                    // dL_dmeans2D
+        *s_dop = o[1].y;                                                         // dL_dopacity
+        s_s[0] = o[1].z; s_s[1] = o[1].w; s_s[2] = o[2].x;                       // dL_dscales
+        *s_r = make_float4(o[2].y, o[2].z, o[2].w, o[3].x);                      // dL_drotations
+        {
+            const float bs[16] = {o[4].x, o[4].y, o[4].z, o[4].w, o[5].x, o[5].y, o[5].z, o[5].w,
+                                  o[6].x, o[6].y, o[6].z, o[6].w, o[7].x, o[7].y, o[7].z, o[7].w};
+            const float dR[3] = {o[3].y, o[3].z, o[3].w};
+            float4* d4 = reinterpret_cast<float4*>(s_sh);                        // dL_dsh row = basis x dRGB
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                float w[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int e = 4 * j + u; w[u] = bs[e / 3] * dR[e % 3]; }
+                d4[j] = make_float4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic writes -> visible to the TMA
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t base = smem_u32(S);
+            tma_store(g.dsh + row0 * 48, base + DenseStage::sh, 24576);
+            tma_store(g.dmeans3D + row0 * 3, base + DenseStage::means, 1536);
+            tma_store(g.dmeans2D + row0 * 3, base + DenseStage::dm2, 1536);
+            tma_store(g.dopacity + row0, base + DenseStage::dop, 512);
+            tma_store(g.dscales + row0 * 3, base + DenseStage::scales, 1536);
+            tma_store(g.drots + row0 * 4, base + DenseStage::rot, 2048);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     }
-    __syncthreads();
-    cta_write_block<kDT, kDRS>(v.P, v.M, row0, s_rows, s_slot, vis ? tid : -1, s_count, g);
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA exits
+
+    // the last, partial block (P % 128 rows): plain loads and stores, one CTA
+    if (blockIdx.x == 0 && nfull * kDT < v.P) {
+        const size_t i = (size_t)nfull * kDT + tid;
+        if (i < (size_t)v.P) {
+            float4 o[11];
+            if (radii[i] > 0) {
+                float4* aa = acc + i * 3;
+                const float4 a0 = aa[0], a1 = aa[1], a2 = aa[2];
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, a2.y, 0.f, a2.w);
+                const float* sh = shs + i * 48;
+                auto fill = [&](float* cf, int) {
+#pragma unroll
+                    for (int k = 0; k < 48; k++) cf[k] = __ldg(sh + k);
+                };
+                grad_row(v, cam, i, a0, a1, a2, __float_as_uint(a2.y), means3D, true, scales, rotations, nullptr, fill, o);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 11; k++) o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            g.dmeans3D[3 * i] = o[0].x; g.dmeans3D[3 * i + 1] = o[0].y; g.dmeans3D[3 * i + 2] = o[0].z;
+            g.dmeans2D[3 * i] = o[0].w; g.dmeans2D[3 * i + 1] = o[1].x; g.dmeans2D[3 * i + 2] = 0.f;
+            g.dopacity[i] = o[1].y;
+            g.dscales[3 * i] = o[1].z; g.dscales[3 * i + 1] = o[1].w; g.dscales[3 * i + 2] = o[2].x;
+            g.drots[4 * i] = o[2].y; g.drots[4 * i + 1] = o[2].z; g.drots[4 * i + 2] = o[2].w; g.drots[4 * i + 3] = o[3].x;
+            const float bs[16] = {o[4].x, o[4].y, o[4].z, o[4].w, o[5].x, o[5].y, o[5].z, o[5].w,
+                                  o[6].x, o[6].y, o[6].z, o[6].w, o[7].x, o[7].y, o[7].z, o[7].w};
+            const float dR[3] = {o[3].y, o[3].z, o[3].w};
+#pragma unroll
+            for (int e = 0; e < 48; e++) g.dsh[i * 48 + e] = bs[e / 3] * dR[e % 3];
+        }
+    }
 }
 
 // Fused "final gradient -> peer reduce" for the shared-model data-parallel step: instead of writing
@@ -458,6 +564,12 @@ k_grad_dense(const GsView v, const float* __restrict__ means3D, const float* __r
 // 2 x 59 x P all-reduce; rows of invisible Gaussians are never touched.  dL_dmeans2D stays local (it feeds the
 // per-view densification statistic, scene/gaussian_model.py:405-407).
 struct GsPeerArgs {
+    // Cross-rank barriers folded into the kernel (no separate barrier launches): sig[r] = rank r's signal words
+    // (peer-mapped uint32 array): [0, 16) "bucket of rank j is zeroed" epochs, [16, 32) "rank j's adds are done" epochs,
+    // [32] the local block ticket.  epoch_begin / epoch_end = 0: no barrier on that side of this launch.
+    uint32_t* sig[GS_MAX_PEERS];
+    int rank;
+    uint32_t epoch_begin, epoch_end;
     float* peers[GS_MAX_PEERS];       // bucket base of every rank (peer-mapped), [0, world)
     float* mc;                        // multicast address of the bucket, or nullptr
     int world;
@@ -483,6 +595,18 @@ __device__ __forceinline__ void peer_add4(const GsPeerArgs& pa, long long off, f
         for (int r = 0; r < pa.world; r++) atomicAdd(reinterpret_cast<float4*>(pa.peers[r] + off), v);
     }
 }
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void peer_reduce_rows(const GsPeerArgs& pa, const float* s_row, const int* s_rowidx, int nv, int M,
+                                                 long long row0);
 
 __global__ void __launch_bounds__(kT)
 k_grad_reduce_peers(const int P, const int M, const int* __restrict__ radii, const float4* __restrict__ acc,
@@ -526,6 +650,36 @@ k_grad_reduce_peers(const int P, const int M, const int* __restrict__ radii, con
         }
     }
     const int nv = s_count;
+    // ---- barrier in: nobody adds into a bucket before every rank has zeroed its own (signalled by its block 0)
+    if (pa.epoch_begin) {
+        if (blockIdx.x == 0 && tid < pa.world) st_release_sys(pa.sig[tid] + pa.rank, pa.epoch_begin);
+        if (nv > 0) {
+            if (tid < pa.world) while ((int)(ld_acquire_sys(pa.sig[pa.rank] + tid) - pa.epoch_begin) < 0) {}
+            __syncthreads();
+        }
+    }
+    if (nv > 0) peer_reduce_rows(pa, s_row, s_rowidx, nv, M, row0);
+    // ---- barrier out: the kernel does not end before every rank's adds have landed (last block of each rank signals)
+    if (pa.epoch_end) {
+        if (nv > 0) __threadfence_system();                  // my reductions are performed before the ticket below
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t* mine = pa.sig[pa.rank];
+            const unsigned t = atomicAdd(mine + 32, 1u);
+            if (t == gridDim.x - 1) {
+                mine[32] = 0u;                               // re-armed for the next launch
+                __threadfence_system();
+                for (int r = 0; r < pa.world; r++) st_release_sys(pa.sig[r] + 16 + pa.rank, pa.epoch_end);
+                for (int r = 0; r < pa.world; r++)
+                    while ((int)(ld_acquire_sys(mine + 16 + r) - pa.epoch_end) < 0) {}
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void peer_reduce_rows(const GsPeerArgs& pa, const float* s_row, const int* s_rowidx, int nv, int M,
+                                                 long long row0) {
+    const int tid = threadIdx.x;
     const int M3 = M * 3;
     if (M3 == 48 && ((pa.off_sh | pa.off_rot) & 3) == 0) {
         // M = 16: 20 reductions per visible Gaussian -- 3 (mean) + 12 x 128-bit (SH) + 1 (opacity) + 3 (scale)
@@ -577,9 +731,14 @@ k_grad_reduce_peers(const int P, const int M, const int* __restrict__ radii, con
 
 void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* acc, const float* gout, float* dmeans2D,
                                  float* const* peers, int world, float* mc, const long long* seg_off,
+                                 uint32_t* const* signals, int rank, uint32_t epoch_begin, uint32_t epoch_end,
                                  cudaStream_t s) {
     GsPeerArgs pa;
     for (int r = 0; r < GS_MAX_PEERS; r++) pa.peers[r] = r < world ? peers[r] : nullptr;
+    for (int r = 0; r < GS_MAX_PEERS; r++) pa.sig[r] = (signals && r < world) ? signals[r] : nullptr;
+    pa.rank = rank;
+    pa.epoch_begin = signals ? epoch_begin : 0u;
+    pa.epoch_end = signals ? epoch_end : 0u;
     pa.mc = mc; pa.world = world;
     pa.off_m3 = seg_off[0]; pa.off_sh = seg_off[1]; pa.off_op = seg_off[2]; pa.off_sc = seg_off[3]; pa.off_rot = seg_off[4];
     const int grid = (P + kT - 1) / kT;
@@ -596,15 +755,17 @@ void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, cons
                                       dense_elsewhere);
 }
 // the dense-regime twin of (k_grad_vis, k_grad_write): returns at once on the device unless most Gaussians are visible
-void gs_launch_grad_dense(const GsView& v, const float* means3D, const float* shs, const float* scales,
-                          const float* rotations, const int* radii, const float4* rec, float4* acc,
-                          const GsDevStatus* status, GsGradPtrs g, cudaStream_t s) {
-    const int grid = (v.P + kDT - 1) / kDT;
-    k_grad_dense<<<grid, kDT, 0, s>>>(v, means3D, shs, scales, rotations, radii, rec, acc, status, g);
+void gs_launch_grad_dense(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
+                          const float* rotations, const int* radii, float4* acc, const GsDevStatus* status, GsGradPtrs g,
+                          cudaStream_t s) {
+    const int need = (v.P + kDT - 1) / kDT;
+    const int grid = need < num_sms * 3 ? need : num_sms * 3;      // persistent: 3 CTAs (2 x 37 KB stages each) per SM
+    k_grad_dense<<<grid, kDT, kDenseSmem, s>>>(v, means3D, shs, scales, rotations, radii, acc, status, g);
 }
 void gs_grad_write_init() {
     cudaFuncSetAttribute(k_grad_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kRow * (int)sizeof(float));
     cudaFuncSetAttribute(k_grad_reduce_peers, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kRow * (int)sizeof(float));
+    cudaFuncSetAttribute(k_grad_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem);
 }
 void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
                           const GsDevStatus* status, bool dense_elsewhere, cudaStream_t s) {

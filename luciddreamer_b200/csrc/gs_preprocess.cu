@@ -17,13 +17,22 @@
 // Histogram and emission spread the (Gaussian, tile) candidates of a CTA's 256 Gaussians evenly over its threads
 // (block scan of the rect areas + binary search), so a splat covering thousands of tiles costs the same per thread
 // as one covering four.
+#include <cstdlib>
+
 #include "gs_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kChunk = 64;            // Gaussians per CTA round in the vis-list kernels: small chunks keep all SMs busy
-                                      // when only a few 10^4 Gaussians are visible (the candidate walk uses all threads)
+constexpr int kChunkMax = 256;        // Gaussians per CTA round in the vis-list kernels: 256 when many are visible (every
+constexpr int kChunkMin = 64;         // thread owns one), 64 when only a few 10^4 are (small chunks keep all SMs busy; the
+                                      // candidate walk uses all threads either way).  Chosen on the device from num_visible.
+constexpr int kBitRect = 32;          // rects of up to 32 tiles: the histogram pass hands its hit decisions to the emission
+                                      // pass as a bit mask (one word per visible Gaussian), so the exact test runs once
+
+__device__ __forceinline__ int vis_chunk(uint32_t nvis) {
+    return nvis >= (uint32_t)gridDim.x * (uint32_t)kChunkMax ? kChunkMax : kChunkMin;
+}
 
 // Exact tile culling (parity-safe): a (tile, splat) pair is binned only if the splat can
 // reach alpha >= 1/255 somewhere in the tile (gs_box_hit).  Pairs that are dropped are skipped by every pixel of
@@ -36,37 +45,39 @@ __device__ __noinline__ bool gs_tile_hit(float mx, float my, float A, float B, f
 }
 
 struct CandShared {                   // per-CTA candidate table (one entry per Gaussian of the chunk)
-    float mx[kChunk], my[kChunk], A[kChunk], B[kChunk], C[kChunk], thr[kChunk];
-    int rx[kChunk], ry[kChunk], rw[kChunk];
-    uint32_t p0[kChunk], p1[kChunk];
-    uint32_t cum[kChunk + 1];
-    uint32_t warp_tot[kChunk / 32];
+    float mx[kChunkMax], my[kChunkMax], A[kChunkMax], B[kChunkMax], C[kChunkMax], thr[kChunkMax];
+    int rx[kChunkMax], ry[kChunkMax], rw[kChunkMax];
+    uint32_t p0[kChunkMax], p1[kChunkMax];
+    uint32_t bits[kChunkMax];         // hit bits of rects with <= kBitRect tiles (bit r = tile r of the rect, row-major)
+    uint32_t cum[kChunkMax + 1];
+    uint32_t warp_tot[kChunkMax / 32];
 };
 
-// Exclusive scan of the chunk's `area`s (threads 0..kChunk-1 hold one each) into s.cum[0..kChunk]; returns the total.
+// Exclusive scan of the chunk's `area`s (threads 0..CH-1 hold one each) into s.cum[0..CH]; returns the total.
 // All threads of the CTA must call.
-__device__ __forceinline__ uint32_t cta_scan_areas(CandShared& s, uint32_t area) {
+__device__ __forceinline__ uint32_t cta_scan_areas(CandShared& s, uint32_t area, const int CH) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t x = area;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31 && wid < kChunk / 32) s.warp_tot[wid] = x;
+    if (lane == 31) s.warp_tot[wid] = x;                 // threads >= CH carry area 0
     __syncthreads();
     uint32_t wbase = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kChunk / 32; w++) { const uint32_t t = s.warp_tot[w]; if (w < wid) wbase += t; total += t; }
-    if (tid < kChunk) s.cum[tid] = wbase + x - area;
-    if (tid == 0) s.cum[kChunk] = total;
+    for (int w = 0; w < kThreads / 32; w++) { const uint32_t t = s.warp_tot[w]; if (w < wid) wbase += t; total += t; }
+    if (tid < CH) s.cum[tid] = wbase + x - area;
+    if (tid == 0) s.cum[CH] = total;
     __syncthreads();
     return total;
 }
 
-// Visits every (Gaussian, tile) candidate of the chunk that passes the culling test: f(tile, p0, p1).
+// Visits every (Gaussian, tile) candidate of the chunk: f(c, r, tx, ty) with c the chunk-local Gaussian, r the index of
+// the tile inside its rect (row-major).  The candidates are spread evenly over the threads of the CTA.
 template <typename F>
-__device__ __forceinline__ void cta_for_each_hit(const CandShared& s, uint32_t total, int gx, F f) {
+__device__ __forceinline__ void cta_for_each_candidate(const CandShared& s, uint32_t total, const int CH, F f) {
     uint32_t q = threadIdx.x;
     if (q >= total) return;
-    int lo = 0, hi = kChunk;                             // largest c with cum[c] <= q (binary search once ...)
+    int lo = 0, hi = CH;                                 // largest c with cum[c] <= q (binary search once ...)
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (s.cum[mid] <= q) lo = mid; else hi = mid;
@@ -77,8 +88,7 @@ __device__ __forceinline__ void cta_for_each_hit(const CandShared& s, uint32_t t
         const int r = (int)(q - s.cum[c]);
         const int w = s.rw[c];
         const int yy = r / w, xx = r - yy * w;
-        const int tx = s.rx[c] + xx, ty = s.ry[c] + yy;
-        if (gs_tile_hit(s.mx[c], s.my[c], s.A[c], s.B[c], s.C[c], s.thr[c], tx, ty)) f((uint32_t)(ty * gx + tx), s.p0[c], s.p1[c]);
+        f(c, r, s.rx[c] + xx, s.ry[c] + yy);
     }
 }
 
@@ -174,14 +184,16 @@ __device__ __forceinline__ void sh_to_rgb(const float* __restrict__ sh, float x,
 
 __global__ void __launch_bounds__(kThreads)
 k_count_tiles(const GsView v, const int* __restrict__ radii, const float4* __restrict__ rec,
-              const uint32_t* __restrict__ vis_list, uint32_t* __restrict__ tile_cnt,
+              const uint32_t* __restrict__ vis_list, uint32_t* __restrict__ hitmask, uint32_t* __restrict__ tile_cnt,
               GsDevStatus* __restrict__ status) {
     __shared__ CandShared S;
     const uint32_t nvis = (uint32_t)status->num_visible;
-    for (uint32_t chunk = blockIdx.x * kChunk; chunk < nvis; chunk += gridDim.x * kChunk) {
+    const int CH = vis_chunk(nvis);
+    unsigned long long rendered = 0;                      // thread 0: sum of the rect areas this CTA has seen
+    for (uint32_t chunk = blockIdx.x * CH; chunk < nvis; chunk += gridDim.x * CH) {
         const uint32_t c = chunk + threadIdx.x;
         uint32_t area = 0;
-        if (threadIdx.x < kChunk && c < nvis) {
+        if (threadIdx.x < CH && c < nvis) {
             const uint32_t i = vis_list[c];
             const float4* rr = rec + (size_t)GS_REC_V4 * i;
             const float4 q0 = __ldg(rr), q1 = __ldg(rr + 1);   // k_project: (x,y,A,B), (C, opacity, depth, thr)
@@ -189,13 +201,21 @@ k_count_tiles(const GsView v, const int* __restrict__ radii, const float4* __res
             area = (uint32_t)((rect.z - rect.x) * (rect.w - rect.y));
             const int t = threadIdx.x;
             S.mx[t] = q0.x; S.my[t] = q0.y; S.A[t] = q0.z; S.B[t] = q0.w; S.C[t] = q1.x; S.thr[t] = q1.w;
-            S.rx[t] = rect.x; S.ry[t] = rect.y; S.rw[t] = rect.z - rect.x; S.p0[t] = 0; S.p1[t] = 0;
+            S.rx[t] = rect.x; S.ry[t] = rect.y; S.rw[t] = rect.z - rect.x; S.p0[t] = area; S.bits[t] = 0u;
         }
-        const uint32_t total = cta_scan_areas(S, area);
-        cta_for_each_hit(S, total, v.gx, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&tile_cnt[tile], 1u); });
-        if (threadIdx.x == 0 && total) atomicAdd(&status->num_rendered, (unsigned long long)total);
+        const uint32_t total = cta_scan_areas(S, area, CH);
+        cta_for_each_candidate(S, total, CH, [&](int cc, int r, int tx, int ty) {
+            if (gs_tile_hit(S.mx[cc], S.my[cc], S.A[cc], S.B[cc], S.C[cc], S.thr[cc], tx, ty)) {
+                atomicAdd(&tile_cnt[ty * v.gx + tx], 1u);
+                if (S.p0[cc] <= kBitRect) atomicOr(&S.bits[cc], 1u << r);
+            }
+        });
+        __syncthreads();
+        if (threadIdx.x < CH && c < nvis && area <= kBitRect) hitmask[c] = S.bits[threadIdx.x];
+        if (threadIdx.x == 0) rendered += total;         // num_rendered keeps the reference's meaning (rasterizer_impl.cu:278-282)
         __syncthreads();
     }
+    if (threadIdx.x == 0 && rendered) atomicAdd(&status->num_rendered, rendered);
 }
 
 // Exclusive scan of the G tile counts (single CTA: G is ~8k at 1080p, one round).  Every thread owns 8 consecutive
@@ -268,12 +288,40 @@ k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_
 
 // After the scan (off the host's critical path): SH -> RGB for the visible Gaussians, final record + zeroed
 // accumulator, and emission of the (tile, Gaussian) pairs into the tile buckets.
+// SH rows (192 B at M = 16, the bulk of this kernel's input) arrive by TMA when they can: every thread issues one
+// cp.async.bulk for its own Gaussian's row into a padded shared-memory slot (52 floats apart: conflict-free 128-bit
+// reads), one mbarrier per CTA counts the bytes, and the rest of the per-Gaussian loads (record, mean, radius) are in
+// flight meanwhile.  Rows of other widths / alignments take the direct 128-bit or scalar loads.
+constexpr int kShRow = 52;            // shared-memory row stride in floats
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// colour from a Gaussian's SH row staged in shared memory (generic 128-bit loads; only the active coefficients)
+template <int D>
+__device__ __forceinline__ void sh_smem_to_rgb(const float* row, float x, float y, float z, float& cr, float& cg, float& cb) {
+    constexpr int NA = (D + 1) * (D + 1);
+    constexpr int NV = (NA * 3 + 3) / 4;
+    float c[NV * 4];
+    const float4* s4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        const float4 t = s4[k];
+        c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
+    }
+    float bs[16];
+    gs_sh_basis(D, x, y, z, bs);
+    cr = bs[0] * c[0]; cg = bs[0] * c[1]; cb = bs[0] * c[2];
+#pragma unroll
+    for (int k = 1; k < NA; k++) { cr = cr + bs[k] * c[3 * k]; cg = cg + bs[k] * c[3 * k + 1]; cb = cb + bs[k] * c[3 * k + 2]; }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_shade_emit(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
              const float* __restrict__ colors_precomp, const int* __restrict__ radii, float4* __restrict__ rec,
-             float4* __restrict__ acc, const uint32_t* __restrict__ vis_list, const uint32_t* __restrict__ tile_off,
-             uint32_t* __restrict__ tile_cur, GsDevStatus* __restrict__ status, unsigned long long* __restrict__ keys,
-             long long capacity, const bool shaded) {
+             float4* __restrict__ acc, const uint32_t* __restrict__ vis_list, const uint32_t* __restrict__ hitmask,
+             const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ tile_cur, GsDevStatus* __restrict__ status,
+             unsigned long long* __restrict__ keys, long long capacity, const bool shaded, const bool use_tma) {
+    extern __shared__ __align__(16) float s_sh[];                    // kChunkMax x kShRow floats when use_tma
     const bool overflow = (long long)status->num_pairs > capacity;   // device-side guard: nothing is binned then,
     if (blockIdx.x == 0 && threadIdx.x == 0) {                       // the host re-renders with a larger buffer
         if (overflow) status->overflow = 1u;
@@ -281,20 +329,46 @@ k_shade_emit(const GsView v, const float* __restrict__ means3D, const float* __r
     }
     __shared__ CandShared S;
     __shared__ float s_campos[3];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t bar = smem_addr(&s_bar);
     if (threadIdx.x < 3) s_campos[threadIdx.x] = __ldg(v.campos + threadIdx.x);
-    __syncthreads();
     const uint32_t nvis = (uint32_t)status->num_visible;
+    const int CH = vis_chunk(nvis);
+    // TMA staging pays when the rows are (nearly) consecutive and every thread has one: the many-visible regime
+    const bool tma = use_tma && !shaded && CH == kChunkMax;
+    if (tma && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const bool aligned = ((v.M * 3) & 3) == 0;
-    for (uint32_t chunk = blockIdx.x * kChunk; chunk < nvis; chunk += gridDim.x * kChunk) {
+    uint32_t parity = 0;
+    for (uint32_t chunk = blockIdx.x * CH; chunk < nvis; chunk += gridDim.x * CH) {
         const uint32_t c = chunk + threadIdx.x;
+        const bool active = threadIdx.x < CH && c < nvis;
+        uint32_t i = 0;
+        float* my_sh = s_sh + threadIdx.x * kShRow;
+        if (tma) {
+            if (threadIdx.x == 0) {
+                const uint32_t nact = min((uint32_t)CH, nvis - chunk);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nact * 192u) : "memory");
+            }
+            if (active) {
+                i = vis_list[c];
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_addr(my_sh)), "l"(shs + (size_t)i * 48), "r"(192), "r"(bar) : "memory");
+            }
+        } else if (active) {
+            i = vis_list[c];
+        }
         uint32_t area = 0;
-        if (threadIdx.x < kChunk && c < nvis) {
-            const uint32_t i = vis_list[c];
+        if (active) {
             float4* rr = rec + (size_t)GS_REC_V4 * i;
             const float4 q0 = rr[0];
             float4 q1 = rr[1];
             float depth, thr;
             const float4 q2old = rr[2];
+            const int radius = radii[i];
             // first render of this frame: q1 = (C, opacity, depth, thr) from k_project.  A re-render after a capacity
             // overflow (`shaded`, set by the host) finds the final record layout already in place.
             if (!shaded) {
@@ -310,7 +384,20 @@ k_shade_emit(const GsView v, const float* __restrict__ means3D, const float* __r
                     d.x = d.x / len; d.y = d.y / len; d.z = d.z / len;
                     const float* sh = shs + (size_t)i * v.M * 3;
                     float cr, cg, cb;
-                    if (aligned) {
+                    if (tma) {
+                        uint32_t done = 0;               // the CTA's SH rows have landed when this phase completes
+                        while (!done) {
+                            asm volatile("{.reg .pred p;\n\t"
+                                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                         "selp.u32 %0, 1, 0, p;}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                        }
+                        switch (v.D) {
+                            case 0: sh_smem_to_rgb<0>(my_sh, d.x, d.y, d.z, cr, cg, cb); break;
+                            case 1: sh_smem_to_rgb<1>(my_sh, d.x, d.y, d.z, cr, cg, cb); break;
+                            case 2: sh_smem_to_rgb<2>(my_sh, d.x, d.y, d.z, cr, cg, cb); break;
+                            default: sh_smem_to_rgb<3>(my_sh, d.x, d.y, d.z, cr, cg, cb); break;
+                        }
+                    } else if (aligned) {
                         switch (v.D) {
                             case 0: sh_to_rgb<0>(sh, d.x, d.y, d.z, cr, cg, cb); break;
                             case 1: sh_to_rgb<1>(sh, d.x, d.y, d.z, cr, cg, cb); break;
@@ -334,22 +421,35 @@ k_shade_emit(const GsView v, const float* __restrict__ means3D, const float* __r
                 float4* aa = acc + (size_t)3 * i;
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 aa[0] = z4; aa[1] = z4;
-                aa[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));   // a2.w = compact slot
+                aa[2] = make_float4(0.f, __uint_as_float(clamped), 0.f, __uint_as_float(c));   // a2.y = SH clamp bits
+                                                                                                 // a2.w = compact slot
             } else {
                 depth = q2old.y; thr = q2old.w;
             }
-            const int4 rect = gs_rect(q0.x, q0.y, radii[i], v.gx, v.gy);   // same recomputation as rasterizer_impl.cu:91
-            area = overflow ? 0u : (uint32_t)((rect.z - rect.x) * (rect.w - rect.y));
+            const int4 rect = gs_rect(q0.x, q0.y, radius, v.gx, v.gy);   // same recomputation as rasterizer_impl.cu:91
+            const int rw = rect.z - rect.x;
+            area = overflow ? 0u : (uint32_t)(rw * (rect.w - rect.y));
             const int t = threadIdx.x;
             S.mx[t] = q0.x; S.my[t] = q0.y; S.A[t] = q0.z; S.B[t] = q0.w; S.C[t] = q1.x; S.thr[t] = thr;
-            S.rx[t] = rect.x; S.ry[t] = rect.y; S.rw[t] = rect.z - rect.x;
+            S.rx[t] = rect.x; S.ry[t] = rect.y; S.rw[t] = rw;
             S.p0[t] = __float_as_uint(depth); S.p1[t] = i;
+            // rects of up to kBitRect tiles: the histogram pass left its decisions (same tiles, same order); larger ones
+            // repeat the test (same machine code on the same operands: gs_tile_hit)
+            S.bits[t] = (area != 0u && area <= kBitRect) ? hitmask[c] : 0u;
         }
-        const uint32_t total = cta_scan_areas(S, area);
-        cta_for_each_hit(S, total, v.gx, [&](uint32_t tile, uint32_t d, uint32_t idx) {
-            const uint32_t pos = tile_off[tile] + atomicAdd(&tile_cur[tile], 1u);
-            keys[pos] = ((unsigned long long)d << 32) | idx;
+        const uint32_t total = cta_scan_areas(S, area, CH);
+        cta_for_each_candidate(S, total, CH, [&](int cc, int r, int tx, int ty) {
+            const uint32_t b = S.bits[cc];
+            const bool big = (S.cum[cc + 1] - S.cum[cc]) > (uint32_t)kBitRect;
+            const bool hit = big ? gs_tile_hit(S.mx[cc], S.my[cc], S.A[cc], S.B[cc], S.C[cc], S.thr[cc], tx, ty)
+                                 : ((b >> r) & 1u) != 0u;
+            if (hit) {
+                const uint32_t tile = (uint32_t)(ty * v.gx + tx);
+                const uint32_t pos = tile_off[tile] + atomicAdd(&tile_cur[tile], 1u);
+                keys[pos] = ((unsigned long long)S.p0[cc] << 32) | S.p1[cc];
+            }
         });
+        parity ^= 1u;
         __syncthreads();
     }
 }
@@ -373,23 +473,30 @@ void gs_launch_project(const GsView& v, const float* means3D, const float* opaci
                                        status);
 }
 void gs_launch_count_tiles(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
-                           uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s) {
-    const int need = (v.P + kChunk - 1) / kChunk;
+                           uint32_t* hitmask, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s) {
+    const int need = (v.P + kChunkMin - 1) / kChunkMin;
     const int grid = need < num_sms * 8 ? need : num_sms * 8;
-    k_count_tiles<<<grid, kThreads, 0, s>>>(v, radii, rec, vis_list, tile_cnt, status);
+    k_count_tiles<<<grid, kThreads, 0, s>>>(v, radii, rec, vis_list, hitmask, tile_cnt, status);
 }
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status, GsDevStatus* host_slot,
                          cudaStream_t s) {
     k_tile_scan<<<1, kScanT, 0, s>>>(G, tile_cnt, tile_off, status, host_slot);
 }
+void gs_preprocess_init() {
+    cudaFuncSetAttribute(k_shade_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kChunkMax * kShRow * (int)sizeof(float));
+}
 void gs_launch_shade_emit(const GsView& v, int num_sms, const float* means3D, const float* shs,
                           const float* colors_precomp, const int* radii, float4* rec, float4* acc,
-                          const uint32_t* vis_list, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
-                          unsigned long long* keys, long long capacity, bool shaded, cudaStream_t s) {
-    const int need = (v.P + kChunk - 1) / kChunk;
-    const int grid = need < num_sms * 8 ? need : num_sms * 8;
-    k_shade_emit<<<grid, kThreads, 0, s>>>(v, means3D, shs, colors_precomp, radii, rec, acc, vis_list, tile_off,
-                                           tile_cur, status, keys, capacity, shaded);
+                          const uint32_t* vis_list, const uint32_t* hitmask, const uint32_t* tile_off, uint32_t* tile_cur,
+                          GsDevStatus* status, unsigned long long* keys, long long capacity, bool shaded, cudaStream_t s) {
+    const int need = (v.P + kChunkMin - 1) / kChunkMin;
+    // TMA staging of the SH rows: 16 stored coefficients (192-byte rows, 16-byte aligned like the base pointer)
+    const bool use_tma = shs && !colors_precomp && v.M == 16 && !getenv("GS_NO_TMA");
+    const size_t smem = use_tma ? (size_t)kChunkMax * kShRow * sizeof(float) : 0;
+    const int per_sm = use_tma ? 4 : 8;                  // 53 KB of shared memory per CTA with the staging buffer
+    const int grid = need < num_sms * per_sm ? need : num_sms * per_sm;
+    k_shade_emit<<<grid, kThreads, smem, s>>>(v, means3D, shs, colors_precomp, radii, rec, acc, vis_list, hitmask, tile_off,
+                                              tile_cur, status, keys, capacity, shaded, use_tma);
 }
 void gs_launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s) {
     k_mark_visible<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, vm, present);

@@ -86,6 +86,77 @@ __device__ __forceinline__ unsigned long long* merge_rank_sort(unsigned long lon
     return A;
 }
 
+// ---- merge-path sort for the long buckets (mid / big kernels).  Runs of kVT keys are sorted in registers by an
+// odd-even transposition network, then sorted runs are merged pairwise: every thread produces kVT consecutive outputs
+// of a merged pair -- ONE binary search along its merge-path diagonal (log2 L probes), then a serial merge (one
+// shared-memory read per output) -- instead of one binary search per key per pass.  ~10 instructions per key and pass.
+constexpr int kVT = 8;
+
+__device__ __forceinline__ void cswap(unsigned long long& a, unsigned long long& b) {
+    const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo; b = hi;
+}
+
+// Shared-memory layout: one padding word after every kVT keys (logical index i lives at i + i / 8).  Every thread works
+// on kVT CONSECUTIVE keys; unpadded, the 64-byte stride between neighbouring threads would put a warp's 64-bit accesses
+// on two bank pairs (16-way conflicts); with the pad the stride is 72 bytes and a half-warp covers all 32 banks.
+__device__ __forceinline__ int ph(const int i) { return i + (i >> 3); }
+__host__ __device__ constexpr int padded_keys(const int n) { return n + n / 8 + 8; }
+
+// Sorts n unique keys that sit at A[ph(0..n)); B is scratch; both hold padded_keys(capacity) words.  Returns the buffer
+// that holds the result (same layout).  All `nthreads` threads call; sync() synchronises them.
+template <typename Sync>
+__device__ __forceinline__ unsigned long long* merge_path_sort(unsigned long long* A, unsigned long long* B, const int n,
+                                                               const int tid, const int nthreads, Sync sync) {
+    const int nseg = (n + kVT - 1) / kVT, npad = nseg * kVT;
+    for (int i = n + tid; i < npad; i += nthreads) A[ph(i)] = ~0ull;    // +inf padding sorts to the very end
+    sync();
+    // phase 1: runs of kVT, in registers
+    for (int sg = tid; sg < nseg; sg += nthreads) {
+        unsigned long long k[kVT];
+        unsigned long long* run = A + ph(sg * kVT);      // kVT consecutive words (the pad comes after them)
+#pragma unroll
+        for (int j = 0; j < kVT; j++) k[j] = run[j];
+#pragma unroll
+        for (int r = 0; r < kVT; r++) {
+#pragma unroll
+            for (int j = r & 1; j + 1 < kVT; j += 2) cswap(k[j], k[j + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < kVT; j++) run[j] = k[j];
+    }
+    sync();
+    // phase 2: pairwise merges of runs of length L (the last run of a level may be shorter or missing)
+    for (int L = kVT; L < npad; L <<= 1) {
+        for (int sg = tid; sg < nseg; sg += nthreads) {
+            const int out0 = sg * kVT;                   // first output position of this thread's segment
+            const int base = out0 & ~(2 * L - 1);        // start of the pair of runs (a multiple of kVT)
+            const int la = min(L, npad - base), lb = max(0, min(L, npad - base - L));
+            const unsigned long long* a = A + ph(base);          // ph(base + i) == ph(base) + ph(i) for base % 8 == 0
+            const unsigned long long* b = A + ph(base + L);
+            const int d = out0 - base;                   // diagonal: outputs [d, d + kVT) of the merged pair
+            int lo = max(0, d - lb), hi = min(d, la);    // merge path: i = #elements taken from a before diagonal d
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (a[ph(mid)] < b[ph(d - 1 - mid)]) lo = mid + 1; else hi = mid;
+            }
+            int i = lo, j = d - lo;
+            unsigned long long ka = i < la ? a[ph(i)] : ~0ull, kb = j < lb ? b[ph(j)] : ~0ull;
+            unsigned long long* out = B + ph(out0);
+#pragma unroll
+            for (int o = 0; o < kVT; o++) {
+                const bool take_a = (j >= lb) || (i < la && ka < kb);
+                out[o] = take_a ? ka : kb;
+                if (take_a) { i++; ka = i < la ? a[ph(i)] : ~0ull; }
+                else { j++; kb = j < lb ? b[ph(j)] : ~0ull; }
+            }
+        }
+        sync();
+        unsigned long long* t = A; A = B; B = t;
+    }
+    return A;
+}
+
 template <typename Ptr, typename Sync>
 __device__ __forceinline__ void bitonic_sort_any_n(Ptr a, const int n, const int tid, const int nthreads, Sync sync) {
     int lg = 0;
@@ -151,7 +222,7 @@ k_tile_sort_mid(const uint32_t* __restrict__ tile_off, const GsDevStatus* __rest
                 const uint32_t* __restrict__ big_list, const unsigned long long* __restrict__ keys,
                 uint32_t* __restrict__ list, long long capacity) {
     if ((long long)status->num_pairs > capacity) return;
-    __shared__ unsigned long long s_mid[2][kMidKeys];
+    __shared__ unsigned long long s_mid[2][padded_keys(kMidKeys)];
     const unsigned nmid = status->n_mid;
     for (unsigned b = blockIdx.x; b < nmid; b += gridDim.x) {
         const uint32_t tile = big_list[b];
@@ -159,10 +230,10 @@ k_tile_sort_mid(const uint32_t* __restrict__ tile_off, const GsDevStatus* __rest
         const int n = (int)(end - beg);
         const unsigned long long* g = keys + beg;
         __syncthreads();
-        for (int t = threadIdx.x; t < n; t += kMidThreads) s_mid[0][t] = g[t];
+        for (int t = threadIdx.x; t < n; t += kMidThreads) s_mid[0][ph(t)] = g[t];
         __syncthreads();
-        const unsigned long long* r = merge_rank_sort(s_mid[0], s_mid[1], n, threadIdx.x, kMidThreads, [] { __syncthreads(); });
-        for (int t = threadIdx.x; t < n; t += kMidThreads) list[beg + t] = (uint32_t)r[t];
+        const unsigned long long* r = merge_path_sort(s_mid[0], s_mid[1], n, threadIdx.x, kMidThreads, [] { __syncthreads(); });
+        for (int t = threadIdx.x; t < n; t += kMidThreads) list[beg + t] = (uint32_t)r[ph(t)];
     }
 }
 
@@ -180,10 +251,10 @@ k_tile_sort_big(int G, const uint32_t* __restrict__ tile_off, const GsDevStatus*
         unsigned long long* g = keys + beg;
         __syncthreads();
         if (n <= kBigKeys) {
-            for (int t = threadIdx.x; t < n; t += kBigThreads) s_big[t] = g[t];
+            for (int t = threadIdx.x; t < n; t += kBigThreads) s_big[ph(t)] = g[t];
             __syncthreads();
-            const unsigned long long* r = merge_rank_sort(s_big, s_big + kBigKeys, n, threadIdx.x, kBigThreads, [] { __syncthreads(); });
-            for (int t = threadIdx.x; t < n; t += kBigThreads) list[beg + t] = (uint32_t)r[t];
+            const unsigned long long* r = merge_path_sort(s_big, s_big + padded_keys(kBigKeys), n, threadIdx.x, kBigThreads, [] { __syncthreads(); });
+            for (int t = threadIdx.x; t < n; t += kBigThreads) list[beg + t] = (uint32_t)r[ph(t)];
         } else {
             bitonic_sort_any_n(g, n, threadIdx.x, kBigThreads, [] { __syncthreads(); });
             for (int t = threadIdx.x; t < n; t += kBigThreads) list[beg + t] = (uint32_t)g[t];
@@ -195,7 +266,7 @@ k_tile_sort_big(int G, const uint32_t* __restrict__ tile_off, const GsDevStatus*
 
 // per device, once (called from gs_context_create with the device current)
 void gs_tile_sort_init() {
-    cudaFuncSetAttribute(k_tile_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBigKeys * 8);
+    cudaFuncSetAttribute(k_tile_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * padded_keys(kBigKeys) * 8);
 }
 
 void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
@@ -208,6 +279,6 @@ void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t*
     k_tile_sort_mid<<<gmid, kMidThreads, 0, s>>>(tile_off, status, big_list, keys, list, capacity);
     if (prof) { cudaEventRecord(prof[1], s); cudaEventRecord(prof[2], s); }
     const int grid = G < num_sms ? G : num_sms;
-    k_tile_sort_big<<<grid, kBigThreads, 2 * kBigKeys * 8, s>>>(G, tile_off, status, big_list, keys, list, capacity);
+    k_tile_sort_big<<<grid, kBigThreads, 2 * padded_keys(kBigKeys) * 8, s>>>(G, tile_off, status, big_list, keys, list, capacity);
     if (prof) cudaEventRecord(prof[3], s);
 }

@@ -63,40 +63,93 @@ class SymmGradBucket(GradBucket):
     This replaces the dense 59-floats-per-Gaussian all-reduce of the shared-model step by traffic proportional to
     the number of VISIBLE Gaussians.  Usage per optimisation step, on every rank:
 
-        bucket.begin_step()                 # zero the local bucket, then a cross-rank barrier
+        bucket.begin_step()                 # switch to the pre-zeroed buffer; the other one is cleared in the background
         view_step(params, settings, cot, bucket=bucket)     # forward + backward, gradients land in all buckets
-        bucket.end_step()                   # cross-rank barrier: bucket.flat now holds the sum over all views
-    """
+        bucket.end_step()                   # bucket.flat now holds the sum over all views of all ranks
 
-    def __init__(self, P: int, M: int, device, group=None, use_multicast: bool = True):
+    Nothing of the exchange sits on the step's critical path except the adds themselves:
+      * two buffers alternate; the one used by the previous step is zeroed on a side stream while this step computes;
+      * the two cross-rank barriers (before the first add: every rank has zeroed; after the last add: every rank's adds
+        have landed) are folded into the final backward kernel -- it signals and waits on peer-mapped signal words
+        (GsGrads.peer_signals) instead of two host-launched barrier kernels.  `device_sync=False` keeps the host barriers
+        (needed when some rank has no view in a step)."""
+
+    def __init__(self, P: int, M: int, device, group=None, use_multicast: bool = True, device_sync: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
         self.P, self.M = int(P), int(M)
         self.width = 3 + 3 * self.M + 1 + 3 + 4
         widths = (3, 3 * self.M, 1, 3, 4)
         seg = [(self.P * w + 63) // 64 * 64 for w in widths]
         self.group = group if group is not None else dist.group.WORLD
-        self.flat = symm_mem.empty(sum(seg), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.flat, self.group)
-        self.flat.zero_()
+        n = sum(seg)
+        self._both = symm_mem.empty(2 * n, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self._both, self.group)
+        self._both.zero_()
+        self._sig = symm_mem.empty(64, dtype=torch.int32, device=device)      # signal words of the folded barriers
+        self._sig_handle = symm_mem.rendezvous(self._sig, self.group)
+        self._sig.zero_()
         offs = [0]
         for x in seg[:-1]:
             offs.append(offs[-1] + x)
         self.seg_off = offs
         shapes = ((self.P, 3), (self.P, self.M, 3), (self.P, 1), (self.P, 3), (self.P, 4))
-        views = [self.flat[o:o + self.P * w].view(*sh) for o, w, sh in zip(offs, widths, shapes)]
-        self.means3D, self.shs, self.opacities, self.scales, self.rotations = views
         mc = 0
         if use_multicast and getattr(self.handle, "has_multicast_support", False):
             mc = int(self.handle.multicast_ptr or 0)
-        self.peers = dict(world=self.handle.world_size, ptrs=[int(p) for p in self.handle.buffer_ptrs], mc=mc,
-                          seg_off=offs)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        self._bufs = []
+        for b in range(2):
+            flat = self._both[b * n:(b + 1) * n]
+            views = [flat[o:o + self.P * w].view(*sh) for o, w, sh in zip(offs, widths, shapes)]
+            peers = dict(world=self.world, ptrs=[int(p) + b * n * 4 for p in self.handle.buffer_ptrs],
+                         mc=(mc + b * n * 4) if mc else 0, seg_off=offs, rank=self.rank,
+                         signals=[int(p) for p in self._sig_handle.buffer_ptrs] if device_sync else None,
+                         epoch_begin=0, epoch_end=0)
+            self._bufs.append((flat, views, peers))
+        self.device_sync = bool(device_sync)
+        self._cur, self._epoch = 0, 0
+        self._side = torch.cuda.Stream(device=device)
+        self._zeroed = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev in self._zeroed:
+            ev.record()
+        self._select(0)
+        torch.cuda.synchronize(device)
+        self.handle.barrier(channel=0)          # every rank's buffers and signal words are zero before the first step
 
-    def begin_step(self):
-        self.flat.zero_()
-        self.handle.barrier(channel=0)
+    def _select(self, b):
+        self._cur = b
+        self.flat, views, self.peers = self._bufs[b]
+        self.means3D, self.shs, self.opacities, self.scales, self.rotations = views
+
+    def begin_step(self, first_and_last: bool = True):
+        """Call before the first view of the step.  `first_and_last`: the step has exactly one view_step on this rank (it
+        then carries both folded barriers); multi_view_step manages the flags itself."""
+        main = torch.cuda.current_stream(self.flat.device)
+        prev = self._cur
+        self._select(prev ^ 1)
+        main.wait_event(self._zeroed[self._cur])              # cleared during the previous step
+        ev = torch.cuda.Event()
+        ev.record(main)                                       # consumers of the previous result enqueued so far
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            self._bufs[prev][0].zero_()
+            self._zeroed[prev].record(self._side)
+        self._epoch += 1
+        if self.device_sync:
+            self.peers["epoch_begin"] = self._epoch if first_and_last else 0
+            self.peers["epoch_end"] = self._epoch if first_and_last else 0
+        else:
+            self.handle.barrier(channel=0)
+
+    def mark(self, first: bool, last: bool):
+        """Which folded barriers the NEXT view_step of this step carries (several views per rank and step)."""
+        if self.device_sync:
+            self.peers["epoch_begin"] = self._epoch if first else 0
+            self.peers["epoch_end"] = self._epoch if last else 0
 
     def end_step(self):
-        self.handle.barrier(channel=1)
+        if not self.device_sync:
+            self.handle.barrier(channel=1)
 
 
 class DensifyStats:
@@ -183,8 +236,12 @@ def multi_view_step(params: dict, settings_list: Sequence, cotangents: Sequence,
     out = {}
     views = shard_views(len(settings_list), rank, world)
     symm = isinstance(bucket, SymmGradBucket)
+    if symm and bucket.device_sync and len(settings_list) < world:
+        raise RuntimeError("SymmGradBucket(device_sync=True) needs at least one view per rank and step")
     tmp = None
     for n, v in enumerate(views):
+        if symm:
+            bucket.mark(first=(n == 0), last=(n == len(views) - 1))
         if symm or n == 0:
             target = bucket
         else:
@@ -200,6 +257,84 @@ def multi_view_step(params: dict, settings_list: Sequence, cotangents: Sequence,
     if not views and not symm:
         bucket.flat.zero_()
     return out
+
+
+def render_views_batched(params: dict, settings_list: Sequence, rank: int = 0, world: int = 1, n_streams: int = 2,
+                         pair_capacity: Optional[int] = None):
+    """Forward-only batch render of this rank's share of `settings_list` (config 4) through the batched C entry point
+    gs_forward_views: up to `n_streams` views IN FLIGHT on the context's internal streams (forked from / joined into
+    the current stream), nothing blocks until every view is enqueued, then ONE host wait collects all counts.  The
+    reference renders view by view and blocks the host once per view (rasterizer_impl.cu:282; luciddreamer.py:250-262).
+    All views must share P and the image size.  Returns ({view: (color, depth)}, {view: counts dict})."""
+    import ctypes as C
+
+    from . import _native as N
+    from . import rasterizer as R
+
+    views = shard_views(len(settings_list), rank, world)
+    if not views:
+        return {}, {}
+    dev = params["means3D"].device
+    if not params["means3D"].is_cuda:
+        raise RuntimeError("luciddreamer_b200: tensors must live on a CUDA device (no CPU fallback)")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    e = torch.empty(0)
+    preps = []
+    for v in views:
+        rs = settings_list[v]
+        preps.append(R._prepare(rs.bg, params["means3D"], e, params["opacities"], params["scales"], params["rotations"],
+                                rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+                                rs.image_width, params["shs"], rs.sh_degree, rs.campos, rs.prefiltered, rs.debug))
+    n, P = len(views), preps[0].P
+    H, W = preps[0].frame.H, preps[0].frame.W
+    if any(p.frame.H != H or p.frame.W != W or p.P != P for p in preps):
+        raise RuntimeError("render_views_batched: all views must share one image size and one Gaussian set")
+    L = N.lib()
+    out, counts = {}, {}
+    with R._guard(idx), torch.no_grad():
+        ctx, stream = R._ctx(idx), R._raw_stream(idx)
+        hint = R._cap_hint.get(idx)
+        if pair_capacity is None and hint is None:
+            # nothing known about this scene yet: learn the pair count from one ordinary (synchronising) render
+            rs = settings_list[views[0]]
+            R.GaussianRasterizer(rs)(params["means3D"], e, params["opacities"], shs=params["shs"], scales=params["scales"],
+                                     rotations=params["rotations"])
+            hint = R._cap_hint.get(idx)
+        cap = R._round_cap(pair_capacity if pair_capacity is not None else hint * 1.5 + 4096)
+        color = torch.empty((n, 3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((n, 1, H, W), dtype=torch.float32, device=dev)
+        for first in range(0, n, 64):                       # a context has 64 status slots
+            m = min(64, n - first)
+            ns = max(1, min(int(n_streams), m, 8))
+            u8 = dict(dtype=torch.uint8, device=dev)
+            scr_t = [(torch.empty((L.gs_geom_bytes(P),), **u8), torch.empty((L.gs_image_bytes(W, H),), **u8),
+                      torch.empty((L.gs_binning_bytes(cap),), **u8), torch.empty((P,), dtype=torch.int32, device=dev))
+                     for _ in range(ns)]
+            scr = (N.GsViewScratch * ns)()
+            for k, (g_, i_, b_, r_) in enumerate(scr_t):
+                scr[k].geom_buffer, scr[k].image_buffer, scr[k].binning_buffer = g_.data_ptr(), i_.data_ptr(), b_.data_ptr()
+                scr[k].pair_capacity, scr[k].radii = cap, r_.data_ptr()
+            frames = (N.GsFrame * m)()
+            res = (N.GsViewResult * m)()
+            for k in range(m):
+                C.memmove(C.byref(frames[k]), C.byref(preps[first + k].frame), C.sizeof(N.GsFrame))
+                res[k].out_color, res[k].out_depth, res[k].radii = color[first + k].data_ptr(), depth[first + k].data_ptr(), None
+            rc = L.gs_forward_views(ctx, frames, m, scr, ns, res, stream)
+            if rc not in (0, -3):                           # GS_ECAPACITY (-3) is handled per view below
+                N.check(rc)
+            for k in range(m):
+                v = views[first + k]
+                c = res[k].counts
+                counts[v] = dict(num_rendered=int(c.num_rendered), num_pairs=int(c.num_pairs), num_visible=int(c.num_visible))
+                R._note_pairs(idx, c.num_pairs)
+                if res[k].status != 0:                      # this view alone needs a larger buffer: ordinary path
+                    rs = settings_list[v]
+                    col, _r, dep = R.GaussianRasterizer(rs)(params["means3D"], e, params["opacities"], shs=params["shs"],
+                                                            scales=params["scales"], rotations=params["rotations"])
+                    color[first + k].copy_(col)
+                    depth[first + k].copy_(dep)
+                out[v] = (color[first + k], depth[first + k])
+    return out, counts
 
 
 def render_views(params: dict, settings_list: Sequence, rank: int = 0, world: int = 1):

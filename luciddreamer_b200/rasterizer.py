@@ -116,8 +116,12 @@ def _poll_static(idx: int, wait: bool = False) -> None:
     pend = st["pending"]
     while pend:
         ticket, cap = pend[0]
-        if not _check_ticket(idx, ticket, cap, wait or len(pend) > 48):   # 64 status slots per context: never lap them
-            break
+        try:
+            if not _check_ticket(idx, ticket, cap, wait or len(pend) > 48):   # 64 status slots per context: never lap them
+                break
+        except RuntimeError:
+            pend.popleft()                # an overflow is reported once
+            raise
         pend.popleft()
 
 
@@ -387,6 +391,13 @@ def _backward_peers(prep: _Prepared, radii, geom, binning, img, cap, grad_color,
         g.peer_buckets = C.cast(ptrs, C.POINTER(C.c_void_p))
         g.peer_multicast = int(peers.get("mc") or 0) or None
         g.peer_seg_off = C.cast(seg, C.POINTER(C.c_int64))
+        sig = None
+        if peers.get("signals"):          # cross-rank barriers folded into the kernel (multiview.SymmGradBucket)
+            sig = (C.c_void_p * world)(*[int(p) for p in peers["signals"]])
+            g.peer_signals = C.cast(sig, C.POINTER(C.c_void_p))
+            g.peer_rank = int(peers["rank"])
+            g.peer_epoch_begin = int(peers.get("epoch_begin", 0))
+            g.peer_epoch_end = int(peers.get("epoch_end", 0))
         gc = _dev_f32(grad_color, dev)
         if gc is None or gc.numel() != 3 * f.H * f.W:
             raise RuntimeError(f"dL_dout_color must hold 3 x {f.H} x {f.W} values")

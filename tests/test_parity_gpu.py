@@ -668,3 +668,122 @@ def test_visibility_and_radii_on_adversarial_population(seed):
     flips = np.nonzero((mine > 0) != (ref > 0))[0]
     assert len(flips) <= 2, (len(flips), mine[flips][:8], ref[flips][:8])
     assert (f.radii > 0).sum() > 1000 and (f.radii == 0).sum() > 1000
+
+
+def _view_settings(case, inp, d, poses):
+    from luciddreamer_b200 import GaussianRasterizationSettings
+    from luciddreamer_b200 import synthetic as syn
+    out = []
+    for m in poses:
+        cam = syn.make_camera(case.W, case.H, c2w=m)
+        out.append(GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, inp["bg"].to(d),
+                                                 case.scale_modifier, cam.viewmatrix.to(d), cam.projmatrix.to(d), case.D,
+                                                 cam.campos.to(d), False, False))
+    return out
+
+
+@pytest.mark.parametrize("n_streams", [1, 3])
+def test_batched_forward_views_match_the_per_view_loop(n_streams):
+    """gs_forward_views (config 4's shape: one Gaussian set, many cameras, several views in flight) renders exactly what
+    the per-view operator renders, incl. a view that overflows the shared binning capacity and is redone on its own."""
+    from luciddreamer_b200 import GaussianRasterizer, multiview as MV, rasterizer as R
+    from luciddreamer_b200 import synthetic as syn
+    d = dev()
+    case = cases.BY_NAME["rot40_5k_128x72"]
+    inp = cases.build_inputs(case)
+    params = {k: inp[k].to(d) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    sl = _view_settings(case, inp, d, syn.rotate360_poses(7))
+    e = torch.empty(0)
+    ref = [GaussianRasterizer(rs)(params["means3D"], e, params["opacities"], shs=params["shs"], scales=params["scales"],
+                                  rotations=params["rotations"]) for rs in sl]
+    torch.cuda.synchronize()
+    out, counts = MV.render_views_batched(params, sl, n_streams=n_streams)
+    torch.cuda.synchronize()
+    assert sorted(out) == list(range(7))
+    for v in range(7):
+        assert torch.equal(out[v][0], ref[v][0]) and torch.equal(out[v][1], ref[v][2])
+        assert counts[v]["num_visible"] == int((ref[v][1] > 0).sum())
+    # capacity sized for the smallest view: the others take the per-view path, results unchanged
+    small = min(c["num_pairs"] for c in counts.values())
+    out2, _ = MV.render_views_batched(params, sl, n_streams=n_streams, pair_capacity=small)
+    torch.cuda.synchronize()
+    for v in range(7):
+        assert torch.equal(out2[v][0], ref[v][0])
+    # sharding: rank 1 of 2 renders views 1, 3, 5
+    out3, _ = MV.render_views_batched(params, sl, rank=1, world=2, n_streams=n_streams)
+    assert sorted(out3) == [1, 3, 5] and torch.equal(out3[3][0], ref[3][0])
+
+
+def _training_step_fixture(name="micro_1k_64"):
+    from luciddreamer_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    d = dev()
+    case = cases.BY_NAME[name]
+    inp = cases.build_inputs(case)
+    cam = inp["cam"]
+    d_cam = torch.cat([cam.viewmatrix.reshape(-1), cam.projmatrix.reshape(-1), cam.campos.reshape(-1)]).to(d)
+    rs = GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, inp["bg"].to(d),
+                                       case.scale_modifier, d_cam[0:16].view(4, 4), d_cam[16:32].view(4, 4), case.D,
+                                       d_cam[32:35], False, False)
+    rast = GaussianRasterizer(rs)
+    leaves = {k: inp[k].to(d).requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    m2 = torch.zeros(case.P, 3, device=d, requires_grad=True)
+    cot = inp["cot"].to(d)
+    out = {}
+
+    def step():
+        out.clear()                      # no reference to the previous step's autograd graph (graphs.GraphedStep)
+        for t in list(leaves.values()) + [m2]:
+            t.grad = None
+        color, radii, depth = rast(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+                                   rotations=leaves["rotations"])
+        torch.autograd.backward(color, grad_tensors=cot)
+        out["color"] = color.detach()
+        return out["color"]
+
+    def grads():
+        return [leaves[k].grad.clone() for k in leaves] + [m2.grad.clone()]
+    return case, inp, d_cam, step, grads, out
+
+
+def test_static_capacity_forward_is_sync_free_and_checked():
+    """rasterizer.static_capacity: same results as the default path, no host wait inside the forward, and a frame
+    that exceeds the capacity raises at the next check instead of returning garbage silently."""
+    from luciddreamer_b200 import rasterizer as R
+    case, inp, d_cam, step, grads, out = _training_step_fixture()
+    step(); torch.cuda.synchronize()
+    ref_color, ref_grads, pairs = out["color"].clone(), grads(), R._last_pairs[0]
+    with R.static_capacity(pairs + 1000):
+        step()
+        torch.cuda.synchronize()
+        assert torch.equal(out["color"], ref_color)
+        for a, b in zip(grads(), ref_grads):
+            assert float((a - b).norm()) <= 1e-5 * max(float(b.norm()), 1e-20)
+    c = R.check_static()
+    assert c["num_pairs"] == pairs and c["num_visible"] == int((torch.from_numpy(util.load_golden(case.name)["radii"]) > 0).sum())
+    with R.static_capacity(max(64, pairs // 3)):
+        step()                           # too small: renders nothing, every kernel of the backward stays in bounds
+    with pytest.raises(RuntimeError, match="static pair capacity"):
+        R.check_static()
+    step(); torch.cuda.synchronize()     # reported once; the default path afterwards is unaffected
+    assert torch.equal(out["color"], ref_color)
+
+
+def test_cuda_graph_step_replays_match_eager_with_a_new_camera():
+    """graphs.GraphedStep: forward + backward captured once, replayed with the camera rewritten in place."""
+    from luciddreamer_b200 import synthetic as syn
+    from luciddreamer_b200.graphs import GraphedStep
+    case, inp, d_cam, step, grads, out = _training_step_fixture("rot40_5k_128x72")
+    step(); torch.cuda.synchronize()
+    ref_color, ref_grads = out["color"].clone(), grads()
+    g = GraphedStep(step, warmup=2)
+    g.replay()
+    c = g.check()
+    assert torch.equal(g.outputs, ref_color) and c["num_pairs"] <= g.pair_capacity
+    for a, b in zip(grads(), ref_grads):
+        assert float((a - b).norm()) <= 1e-5 * max(float(b.norm()), 1e-20)
+    cam2 = syn.make_camera(case.W, case.H, c2w=syn.rotate360_poses(16)[1])
+    d_cam.copy_(torch.cat([cam2.viewmatrix.reshape(-1), cam2.projmatrix.reshape(-1), cam2.campos.reshape(-1)]).to(d_cam.device))
+    g.replay(); g.check()
+    graphed = g.outputs.clone()
+    step(); torch.cuda.synchronize()
+    assert torch.equal(graphed, out["color"]) and not torch.equal(graphed, ref_color)

@@ -54,7 +54,7 @@ def timeit(fn, n=30):
 
 
 step(); torch.cuda.synchronize()
-ref_color, ref_grads = out["color"].clone(), grads()
+ref_color, ref_grads = out["color"].detach().clone(), grads()   # detach: a clone with a grad_fn would keep the graph alive
 pairs = R._last_pairs[0]
 print("pairs", pairs)
 print("eager sync   : gpu %.3f ms/step, wall %.3f, host-enqueue %.3f" % timeit(step))
@@ -75,7 +75,7 @@ try:
     print("ERROR: overflow not detected"); sys.exit(1)
 except RuntimeError as ex:
     print("overflow detected:", str(ex)[:90])
-R._static[0]["pending"].clear()
+pass
 step(); torch.cuda.synchronize()                  # the device survived the overflow (guards in every kernel)
 assert torch.equal(out["color"], ref_color)
 
@@ -91,7 +91,7 @@ g.check()
 cam2 = syn.make_camera(W, H, c2w=syn.rotate360_poses(64)[5])
 d_cam.copy_(torch.cat([cam2.viewmatrix.reshape(-1), cam2.projmatrix.reshape(-1), cam2.campos.reshape(-1)]).to(dev))
 g.replay(); c2 = g.check()
-gc = g.outputs[0].clone()
+gc = g.outputs[0].detach().clone()
 step(); torch.cuda.synchronize()
 assert torch.equal(gc, out["color"]), "graph replay with a new camera differs from eager"
 print("new camera through the graph ok:", c2)
