@@ -137,8 +137,8 @@ def make_workload(args, rank):
     if args.W and args.H:
         W, H = args.W, args.H
     scale_mult = 4.0 if args.scene == "stress" else 1.0
-    if args.scene == "frustum":          # LucidDreamer-shaped population (synthetic.make_frustum_scene)
-        scene = syn.make_frustum_scene(P, 1000 + CFG_ID, W, H)
+    if args.scene == "frustum":          # LucidDreamer-shaped population (synthetic.make_frustum_scene), raster memory order
+        scene = syn.make_frustum_scene(P, 1000 + CFG_ID, W, H, raster=not args.shuffled)
     else:
         scene = syn.make_scene(P, 1000 + CFG_ID, scale_mult=scale_mult)
     cam = syn.make_camera(W, H, c2w=view_pose(rank))
@@ -331,6 +331,8 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss, graphed
     if fused_loss:
         from luciddreamer_b200 import losses
 
+    dbg = os.environ.get("GS_E2E_SKIP", "")          # diagnostics only: "u" skips the uploads, "c" the camera copy, "l" the loss copy
+
     def upload(k):
         b = k & 1
         with torch.cuda.stream(copy_s):
@@ -339,7 +341,6 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss, graphed
             ev_up[b].record(copy_s)
 
     graphs = None
-    dbg = os.environ.get("GS_E2E_SKIP", "")          # diagnostics only: "u" skips the uploads, "c" the camera copy, "l" the loss copy
 
     def run(n, base):
         if "u" not in dbg:
@@ -378,15 +379,39 @@ def time_e2e(impl, cam, target_u8_cpu, steps, warmup, world, fused_loss, graphed
         d_tgt[b].copy_(h_tgt)
     if graphed:
         from luciddreamer_b200.graphs import GraphedStep
+        # ONE host->device copy per step: the step's camera (35 floats) and target image travel together in one pinned
+        # staging buffer [256 B header | H*W*3 B image] on the copy stream -- a separate 140-byte copy on the compute stream
+        # would queue behind the next step's image upload in the same copy engine
+        nimg = h_tgt.numel()
+        h_in = torch.empty(256 + nimg, dtype=torch.uint8).pin_memory()
+        h_in[:140].copy_(h_cam.view(torch.uint8))
+        h_in[256:].copy_(h_tgt.reshape(-1))
+        d_in = [torch.empty(256 + nimg, dtype=torch.uint8, device=dev) for _ in range(2)]
+        for b in range(2):
+            d_in[b].copy_(h_in)
+        h2d = 256 + nimg
+
+        def upload(k):                               # noqa: F811 (replaces the two-copy version above)
+            b = k & 1
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(ev_free[b])
+                d_in[b].copy_(h_in, non_blocking=True)
+                ev_up[b].record(copy_s)
 
         def make_fn(b):
+            tgt = d_in[b][256:].view(H, W, 3)
+
             def fn():
                 color = impl.forward()
-                loss, cot = losses.l1_loss_with_grad(color, d_tgt[b])
+                loss, cot = losses.l1_loss_with_grad(color, tgt)
                 impl.backward(color, cot)
                 return loss
             return fn
-        graphs = [GraphedStep(make_fn(b), warmup=2) for b in range(2)]
+        graphs = []
+        for b in range(2):
+            impl.bind_camera(d_in[b][:140].view(torch.float32))   # graph b reads the camera of staging buffer b
+            graphs.append(GraphedStep(make_fn(b), warmup=2))
+        dbg = dbg + "c"                              # no separate camera copy in this mode
     for b in range(2):
         ev_free[b].record(main)
     run(warmup, 0)
@@ -536,6 +561,8 @@ SHAPED = [
     ("frustum_1M_512_randcam", dict(scene="frustum", P=1_000_000, W=512, H=512, seed=2001, cams=16)),
     ("frustum_2M_512_randcam", dict(scene="frustum", P=2_000_000, W=512, H=512, seed=2002, cams=16)),
     ("frustum_1M_1080p", dict(scene="frustum", P=1_000_000, W=1920, H=1080, seed=2003, cams=0)),
+    # the same population in RANDOM memory order (the frustum rows above are in LucidDreamer's raster order)
+    ("frustum_1M_512_shuffled", dict(scene="frustum", P=1_000_000, W=512, H=512, seed=2001, cams=0, shuffled=True)),
 ]
 
 
@@ -549,8 +576,8 @@ def shaped_legs(impl_cls, dev, D=3, steps=10, warmup=3, only=None):
             continue
         try:
             W, H = s["W"], s["H"]
-            scene = (syn.make_frustum_scene(s["P"], s["seed"], W, H) if s["scene"] == "frustum"
-                     else syn.make_scene(s["P"], s["seed"]))
+            scene = (syn.make_frustum_scene(s["P"], s["seed"], W, H, raster=not s.get("shuffled", False))
+                     if s["scene"] == "frustum" else syn.make_scene(s["P"], s["seed"]))
             cam = syn.make_camera(W, H)
             cot = syn.make_cotangent(H, W, s["seed"]).to(dev)
             impl = impl_cls(scene, cam, dev, D)
@@ -789,6 +816,8 @@ def main():
     ap.add_argument("--no-shared-model", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e through the eager loop only (no CUDA-graph step)")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 4 / config 5 legs")
+    ap.add_argument("--shuffled", action="store_true", help="frustum scene: Gaussians in random memory order (default: "
+                    "LucidDreamer's raster order)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     os.environ.setdefault("OMP_PROC_BIND", "close")      # cpu_baseline: pinned OpenMP threads (read when libgomp starts)
@@ -866,8 +895,9 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "loss": loss,
                     "mode": ("cuda_graph" if (e2e_eager and "value" in e2e_eager) else "eager"), "eager": e2e_eager,
-                    "protocol": "per step: H2D camera (35 floats) + uint8 target image [H,W,3] from pinned memory (copy "
-                                "stream, double buffered), forward, on-device L1 loss + gradient, backward, D2H scalar loss"},
+                    "protocol": "per step: H2D of the step's camera (35 floats) + uint8 target image [H,W,3] from pinned memory "
+                                "(copy stream, double buffered; cuda_graph mode: both in ONE staged copy), forward, on-device L1 "
+                                "loss + gradient, backward, D2H scalar loss"},
             "clocks": clocks, "scene_stats": {"P_vis": st["P_vis"], "pairs": st["pairs"]}}
     if args.impl == "reference":
         line["impl"] = "reference"
@@ -962,7 +992,8 @@ def config_dict(wl, args, world):
     return {"workload": f"BASELINE config {CFG_ID}: {wl['P']} Gaussians, {wl['W']}x{wl['H']}, SH degree {wl['D']}, "
                         f"forward+backward, one view per GPU per step",
             "scene": (f"{args.scene} (SURVEY.md 8d shell, seed {1000 + CFG_ID}, scale x{wl['scale_mult']})" if args.scene != "frustum"
-                      else f"frustum (LucidDreamer-shaped, synthetic.make_frustum_scene, seed {1000 + CFG_ID})"),
+                      else f"frustum (LucidDreamer-shaped, synthetic.make_frustum_scene, seed {1000 + CFG_ID}, "
+                           f"{'random' if args.shuffled else 'raster'} memory order)"),
             "random_cameras": len(wl["cams"]) if wl.get("cams") else 0,
             "views_per_step": world, "parallelism": f"view-parallel x{world}",
             "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 25 MB cotangent per step)"}

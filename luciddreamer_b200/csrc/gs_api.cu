@@ -96,6 +96,7 @@ struct GsContext {
     bool pev_used[kNumKernels];
     GsDevStatus* slots;            // pinned, mapped: kSlots recycled slots, then kGraphSlots persistent ones
     std::atomic<int> next_graph_slot;
+    std::atomic<long long> last_visible;   // num_visible of the most recent forward whose counts were read (-1: none yet)
     cudaEvent_t events[kSlots];
     unsigned slot_gen[kSlots];     // generation of the ticket that currently owns the slot
     std::atomic<unsigned> next;
@@ -145,6 +146,7 @@ int gs_context_create(int device, GsContext** out) {
     c->device = device;
     c->next = 0;
     c->next_graph_slot = 0;
+    c->last_visible = -1;
     c->profile = 0;
     c->vstreams_ready = false;
     for (int i = 0; i < kSlots; i++) c->slot_gen[i] = 0;
@@ -249,7 +251,7 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     return GS_OK;
 }
 
-static int read_slot(const volatile GsDevStatus* h, int slot, GsCounts* out, bool must_be_ready) {
+static int read_slot(GsContext* ctx, const volatile GsDevStatus* h, int slot, GsCounts* out, bool must_be_ready) {
     if (h->overflow != 0xC0FFEEu) {
         if (must_be_ready) return fail(GS_ECUDA, "status slot %d was not written by the device", slot);
         return GS_ENOTREADY;
@@ -257,6 +259,7 @@ static int read_slot(const volatile GsDevStatus* h, int slot, GsCounts* out, boo
     out->num_rendered = (int64_t)h->num_rendered;
     out->num_pairs = (int64_t)h->num_pairs;
     out->num_visible = (int64_t)h->num_visible;
+    ctx->last_visible = out->num_visible;
     return GS_OK;
 }
 
@@ -271,7 +274,7 @@ int gs_forward_counts(GsContext* ctx, int32_t ticket, GsCounts* out) {
     GS_CUDA(cudaEventSynchronize(ctx->events[slot]));
     if (ctx->slot_gen[slot] != gen)
         return fail(GS_EINVAL, "ticket expired: more than %d forwards were enqueued on this context since", kSlots);
-    return read_slot(ctx->slots + slot, slot, out, true);
+    return read_slot(ctx, ctx->slots + slot, slot, out, true);
 }
 
 int gs_forward_counts_peek(GsContext* ctx, int32_t ticket, GsCounts* out) {
@@ -279,13 +282,13 @@ int gs_forward_counts_peek(GsContext* ctx, int32_t ticket, GsCounts* out) {
     if (ticket & kGraphTicket) {
         const int gsl = ticket & (kGraphTicket - 1);
         if (gsl >= kGraphSlots) return fail(GS_EINVAL, "bad graph ticket");
-        return read_slot(ctx->slots + kSlots + gsl, kSlots + gsl, out, false);
+        return read_slot(ctx, ctx->slots + kSlots + gsl, kSlots + gsl, out, false);
     }
     const int slot = ticket & (kSlots - 1);
     const unsigned gen = (unsigned)ticket >> 6;
     if (ctx->slot_gen[slot] != gen)
         return fail(GS_EINVAL, "ticket expired: more than %d forwards were enqueued on this context since", kSlots);
-    return read_slot(ctx->slots + slot, slot, out, false);
+    return read_slot(ctx, ctx->slots + slot, slot, out, false);
 }
 
 int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, void* geom_buffer, void* binning_buffer,
@@ -309,7 +312,8 @@ int gs_forward_render(GsContext* ctx, const GsFrame* f, const int32_t* radii, vo
     GsBinLayout bl = gs_bin_layout(binning_buffer, pair_capacity > 0 ? pair_capacity : 1);
     GS_TIMED(ctx, 2, s, gs_launch_shade_emit(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs, f->colors_precomp, radii,
                                              gl.rec, gl.acc, gl.vis_list, gl.hitmask, il.tile_off, il.tile_cnt, il.status,
-                                             bl.keys, pair_capacity, rerender != 0, s));
+                                             bl.keys, pair_capacity, rerender != 0,
+                                             ctx && 2 * ctx->last_visible.load() > (long long)f->P, s));
     if ((rc = debug_sync(f, s, "emit"))) return rc;
     {
         const bool prof = ctx && ctx->profile;
@@ -407,7 +411,6 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
     if (!grads) return fail(GS_EINVAL, "grads is NULL");
     if (f->P == 0) return GS_OK;
     if (!radii || !geom_buffer || !image_buffer || !grad_scratch) return fail(GS_EINVAL, "radii / scratch is NULL");
-    (void)grad_scratch_bytes;   // sized by the caller with gs_backward_scratch_bytes(num_visible)
     cudaStream_t s = (cudaStream_t)stream;
     const GsView v = make_view(f);
     GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
@@ -444,7 +447,9 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
     }
     GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, il.status, dense_ok, s));
     if ((rc = debug_sync(f, s, "grad_write"))) return rc;
-    if (dense_ok) {
+    // a scratch buffer sized from the true visible count (synchronising hosts) can prove the sparse regime: no launch
+    const long long nvis_bound = (long long)(grad_scratch_bytes / (GS_GOUT_FLOATS * sizeof(float)));
+    if (dense_ok && 2 * nvis_bound > (long long)f->P) {
         GS_TIMED(ctx, 10, s, gs_launch_grad_dense(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs, f->scales, f->rotations,
                                                   radii, gl.acc, il.status, g, s));
         if ((rc = debug_sync(f, s, "grad_dense"))) return rc;

@@ -433,7 +433,7 @@ __device__ __forceinline__ bool bwd_generic(BwdPix<NH>& Q, const SRec& r, const 
 }
 
 template <int NH>
-__global__ void __launch_bounds__(Geo<NH>::NT, NH == 2 ? 10 : 6)
+__global__ void __launch_bounds__(Geo<NH>::NT, NH == 2 ? 10 : 7)
 k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ list,
             const float4* __restrict__ rec, const float* __restrict__ final_Ts,
             const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix, float4* __restrict__ acc,

@@ -298,7 +298,8 @@ void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevSta
 void gs_launch_shade_emit(const GsView& v, int num_sms, const float* means3D, const float* shs,
                           const float* colors_precomp, const int* radii, float4* rec, float4* acc,
                           const uint32_t* vis_list, const uint32_t* hitmask, const uint32_t* tile_off, uint32_t* tile_cur,
-                          GsDevStatus* status, unsigned long long* keys, long long capacity, bool shaded, cudaStream_t s);
+                          GsDevStatus* status, unsigned long long* keys, long long capacity, bool shaded, bool dense_hint,
+                          cudaStream_t s);
 void gs_tile_sort_init();
 void gs_launch_tile_sort(int G, int num_sms, const uint32_t* tile_off, uint32_t* tile_cur, GsDevStatus* status,
                          uint32_t* big_list, unsigned long long* keys, uint32_t* list, long long capacity,

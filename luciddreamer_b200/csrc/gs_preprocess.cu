@@ -71,25 +71,47 @@ __device__ __forceinline__ uint32_t cta_scan_areas(CandShared& s, uint32_t area,
     return total;
 }
 
-// Visits every (Gaussian, tile) candidate of the chunk: f(c, r, tx, ty) with c the chunk-local Gaussian, r the index of
-// the tile inside its rect (row-major).  The candidates are spread evenly over the threads of the CTA.
+// Visits every (Gaussian, tile) candidate of the chunk: f(valid, c, r, tx, ty) with c the chunk-local Gaussian, r the
+// index of the tile inside its rect (row-major).  The candidates are spread evenly over the threads of the CTA; every
+// thread runs the same number of rounds (lanes without a candidate in the last round get valid = false), so f may
+// use warp-wide primitives.
 template <typename F>
 __device__ __forceinline__ void cta_for_each_candidate(const CandShared& s, uint32_t total, const int CH, F f) {
+    if (total == 0) return;
     uint32_t q = threadIdx.x;
-    if (q >= total) return;
-    int lo = 0, hi = CH;                                 // largest c with cum[c] <= q (binary search once ...)
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s.cum[mid] <= q) lo = mid; else hi = mid;
+    int c = 0;
+    if (q < total) {
+        int lo = 0, hi = CH;                             // largest c with cum[c] <= q (binary search once ...)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s.cum[mid] <= q) lo = mid; else hi = mid;
+        }
+        c = lo;
     }
-    int c = lo;
-    for (; q < total; q += kThreads) {
-        while (s.cum[c + 1] <= q) c++;                   // ... then the slot only ever advances
-        const int r = (int)(q - s.cum[c]);
-        const int w = s.rw[c];
-        const int yy = r / w, xx = r - yy * w;
-        f(c, r, s.rx[c] + xx, s.ry[c] + yy);
+    for (uint32_t base = 0; base < total; base += kThreads, q += kThreads) {
+        const bool valid = q < total;
+        int r = 0, tx = 0, ty = 0;
+        if (valid) {
+            while (s.cum[c + 1] <= q) c++;               // ... then the slot only ever advances
+            r = (int)(q - s.cum[c]);
+            const int w = s.rw[c];
+            const int yy = r / w, xx = r - yy * w;
+            tx = s.rx[c] + xx; ty = s.ry[c] + yy;
+        }
+        f(valid, c, r, tx, ty);
     }
+}
+
+// Lanes of a warp that hit the SAME tile share one atomic: returns the lane's rank among them and, in `count`, how many
+// they are; `leader` is true for the lane that issues the atomic.  Gaussians that are neighbours in memory are usually
+// neighbours on screen (LucidDreamer's point clouds are in raster order, luciddreamer.py:363-372), so a warp's 32
+// candidates mostly fall into one or two tiles.
+__device__ __forceinline__ int tile_peers(const bool hit, const uint32_t tile, int& count, bool& leader, unsigned& peers) {
+    const int lane = threadIdx.x & 31;
+    peers = __match_any_sync(0xffffffffu, hit ? tile : (0x80000000u | (uint32_t)lane));
+    count = __popc(peers);
+    leader = hit && lane == __ffs(peers) - 1;
+    return __popc(peers & ((1u << lane) - 1u));
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -204,11 +226,13 @@ k_count_tiles(const GsView v, const int* __restrict__ radii, const float4* __res
             S.rx[t] = rect.x; S.ry[t] = rect.y; S.rw[t] = rect.z - rect.x; S.p0[t] = area; S.bits[t] = 0u;
         }
         const uint32_t total = cta_scan_areas(S, area, CH);
-        cta_for_each_candidate(S, total, CH, [&](int cc, int r, int tx, int ty) {
-            if (gs_tile_hit(S.mx[cc], S.my[cc], S.A[cc], S.B[cc], S.C[cc], S.thr[cc], tx, ty)) {
-                atomicAdd(&tile_cnt[ty * v.gx + tx], 1u);
-                if (S.p0[cc] <= kBitRect) atomicOr(&S.bits[cc], 1u << r);
-            }
+        cta_for_each_candidate(S, total, CH, [&](bool valid, int cc, int r, int tx, int ty) {
+            const bool hit = valid && gs_tile_hit(S.mx[cc], S.my[cc], S.A[cc], S.B[cc], S.C[cc], S.thr[cc], tx, ty);
+            const uint32_t tile = (uint32_t)(ty * v.gx + tx);
+            int n; bool leader; unsigned peers;
+            tile_peers(hit, tile, n, leader, peers);
+            if (leader) atomicAdd(&tile_cnt[tile], (uint32_t)n);
+            if (hit && S.p0[cc] <= kBitRect) atomicOr(&S.bits[cc], 1u << r);
         });
         __syncthreads();
         if (threadIdx.x < CH && c < nvis && area <= kBitRect) hitmask[c] = S.bits[threadIdx.x];
@@ -328,10 +352,10 @@ k_shade_emit(const GsView v, const float* __restrict__ means3D, const float* __r
         else { status->n_big = 0u; status->n_mid = 0u; }
     }
     __shared__ CandShared S;
-    __shared__ float s_campos[3];
+    __shared__ __align__(16) float s_campos[4];         // own 16-byte slot: the compiler reads it with one 128-bit load
     __shared__ __align__(8) unsigned long long s_bar;
     const uint32_t bar = smem_addr(&s_bar);
-    if (threadIdx.x < 3) s_campos[threadIdx.x] = __ldg(v.campos + threadIdx.x);
+    if (threadIdx.x < 4) s_campos[threadIdx.x] = threadIdx.x < 3 ? __ldg(v.campos + threadIdx.x) : 0.f;
     const uint32_t nvis = (uint32_t)status->num_visible;
     const int CH = vis_chunk(nvis);
     // TMA staging pays when the rows are (nearly) consecutive and every thread has one: the many-visible regime
@@ -438,16 +462,20 @@ k_shade_emit(const GsView v, const float* __restrict__ means3D, const float* __r
             S.bits[t] = (area != 0u && area <= kBitRect) ? hitmask[c] : 0u;
         }
         const uint32_t total = cta_scan_areas(S, area, CH);
-        cta_for_each_candidate(S, total, CH, [&](int cc, int r, int tx, int ty) {
-            const uint32_t b = S.bits[cc];
-            const bool big = (S.cum[cc + 1] - S.cum[cc]) > (uint32_t)kBitRect;
-            const bool hit = big ? gs_tile_hit(S.mx[cc], S.my[cc], S.A[cc], S.B[cc], S.C[cc], S.thr[cc], tx, ty)
-                                 : ((b >> r) & 1u) != 0u;
-            if (hit) {
-                const uint32_t tile = (uint32_t)(ty * v.gx + tx);
-                const uint32_t pos = tile_off[tile] + atomicAdd(&tile_cur[tile], 1u);
-                keys[pos] = ((unsigned long long)S.p0[cc] << 32) | S.p1[cc];
+        cta_for_each_candidate(S, total, CH, [&](bool valid, int cc, int r, int tx, int ty) {
+            bool hit = false;
+            if (valid) {
+                const bool big = (S.cum[cc + 1] - S.cum[cc]) > (uint32_t)kBitRect;
+                hit = big ? gs_tile_hit(S.mx[cc], S.my[cc], S.A[cc], S.B[cc], S.C[cc], S.thr[cc], tx, ty)
+                          : ((S.bits[cc] >> r) & 1u) != 0u;
             }
+            const uint32_t tile = (uint32_t)(ty * v.gx + tx);
+            int n; bool leader; unsigned peers;
+            const int rank = tile_peers(hit, tile, n, leader, peers);
+            uint32_t basepos = 0;
+            if (leader) basepos = tile_off[tile] + atomicAdd(&tile_cur[tile], (uint32_t)n);   // one atomic per (warp, tile)
+            basepos = __shfl_sync(0xffffffffu, basepos, __ffs(peers) - 1);
+            if (hit) keys[basepos + rank] = ((unsigned long long)S.p0[cc] << 32) | S.p1[cc];
         });
         parity ^= 1u;
         __syncthreads();
@@ -488,10 +516,13 @@ void gs_preprocess_init() {
 void gs_launch_shade_emit(const GsView& v, int num_sms, const float* means3D, const float* shs,
                           const float* colors_precomp, const int* radii, float4* rec, float4* acc,
                           const uint32_t* vis_list, const uint32_t* hitmask, const uint32_t* tile_off, uint32_t* tile_cur,
-                          GsDevStatus* status, unsigned long long* keys, long long capacity, bool shaded, cudaStream_t s) {
+                          GsDevStatus* status, unsigned long long* keys, long long capacity, bool shaded, bool dense_hint,
+                          cudaStream_t s) {
     const int need = (v.P + kChunkMin - 1) / kChunkMin;
-    // TMA staging of the SH rows: 16 stored coefficients (192-byte rows, 16-byte aligned like the base pointer)
-    const bool use_tma = shs && !colors_precomp && v.M == 16 && !getenv("GS_NO_TMA");
+    // TMA staging of the SH rows: 16 stored coefficients (192-byte rows, 16-byte aligned like the base pointer).  The
+    // kernel uses it only when most Gaussians are visible; `dense_hint` (the previous frame on this context) decides
+    // whether the launch reserves the 53 KB staging buffer at all -- either way the result is the same.
+    const bool use_tma = dense_hint && shs && !colors_precomp && v.M == 16 && !getenv("GS_NO_TMA");
     const size_t smem = use_tma ? (size_t)kChunkMax * kShRow * sizeof(float) : 0;
     const int per_sm = use_tma ? 4 : 8;                  // 53 KB of shared memory per CTA with the staging buffer
     const int grid = need < num_sms * per_sm ? need : num_sms * per_sm;

@@ -132,7 +132,7 @@ def make_scene(P: int, seed: int, M: int = 16, scale_mult: float = 1.0, opacity_
 
 
 def make_frustum_scene(P: int, seed: int, W: int, H: int, M: int = 16, sigma_px: float = 1.0, fovx: float = REF_FOVX,
-                       margin: float = 0.95) -> Dict[str, torch.Tensor]:
+                       margin: float = 0.95, raster: bool = False) -> Dict[str, torch.Tensor]:
     """LucidDreamer-shaped population: what the reference's optimisation loop actually renders (luciddreamer.py:
     283-327).  Its Gaussians come from depth maps re-projected through the training cameras (luciddreamer.py:370-374,
     492; one point per pixel and view), so nearly ALL of them are inside the frustum of a training view, about one
@@ -155,7 +155,18 @@ def make_frustum_scene(P: int, seed: int, W: int, H: int, M: int = 16, sigma_px:
     opac = torch.sigmoid(torch.randn(P, 1, generator=g) * 2.0).contiguous()
     shs = torch.randn(P, M, 3, generator=g) * 0.05
     shs[:, 0, :] = (torch.rand(P, 3, generator=g) - 0.5) / 0.28209479177387814
-    return {"means3D": means, "scales": scales, "rotations": rots, "opacities": opac, "shs": shs.contiguous()}
+    out = {"means3D": means, "scales": scales, "rotations": rots, "opacities": opac, "shs": shs.contiguous()}
+    if raster:
+        # LucidDreamer's own memory order: the point cloud is the concatenation, view after view, of one point per
+        # pixel in row-major pixel order (luciddreamer.py:363-372: meshgrid(x, y, indexing='xy') ... reshape(3, -1), then
+        # np.concatenate per view :492-495).  Same Gaussians as above, permuted: consecutive blocks of W*H points play the
+        # views, each sorted by (pixel row, pixel column) of the identity camera.
+        px = ((uv[:, 0] * 0.5 + 0.5) * W).clamp(0, W - 1).floor().long()
+        py = ((uv[:, 1] * 0.5 + 0.5) * H).clamp(0, H - 1).floor().long()
+        layer = torch.arange(P) // (W * H)
+        perm = torch.argsort(layer * (W * H) + py * W + px, stable=True)
+        out = {k: v[perm].contiguous() for k, v in out.items()}
+    return out
 
 
 def jitter_poses(n: int, seed: int, max_deg: float = 3.0, max_shift: float = 0.05) -> np.ndarray:

@@ -18,13 +18,16 @@ ref = MV.GradBucket(P, 16, dev)
 MV.view_step(sc, rs, cot, bucket=ref)
 MV.allreduce_bucket(ref)
 torch.cuda.synchronize()
-for mc in (False, True):
-    b = MV.SymmGradBucket(P, 16, dev, use_multicast=mc)
+for mc, ds in ((False, True), (True, True), (True, False)):
+    b = MV.SymmGradBucket(P, 16, dev, use_multicast=mc, device_sync=ds)
     if mc and not b.peers["mc"]:
         if rank == 0: print("multicast not supported here; skipped")
         continue
-    for it in range(3):
+    for it in range(5):        # both buffers of the double-buffered bucket get used, cleared and reused
         b.begin_step(); MV.view_step(sc, rs, cot, bucket=b); b.end_step()
+        torch.cuda.synchronize()
+        e_it = ((b.flat - ref.flat).norm() / ref.flat.norm()).item()
+        assert e_it < 1e-5, (it, e_it)
     torch.cuda.synchronize()
     err = (b.flat - ref.flat).norm() / ref.flat.norm()
     nz = (ref.flat != 0).sum().item()
@@ -40,6 +43,6 @@ for mc in (False, True):
         MV.view_step(sc, rs, cot, bucket=ref); MV.allreduce_bucket(ref)
     e1.record(); torch.cuda.synchronize()
     t_nccl = e0.elapsed_time(e1) / 10
-    print(f"rank {rank}: multicast={bool(b.peers['mc'])} rel err vs NCCL all-reduce {err.item():.2e} (nonzeros {nz}); "
+    print(f"rank {rank}: multicast={bool(b.peers['mc'])} device_sync={ds} rel err vs NCCL all-reduce {err.item():.2e} (nonzeros {nz}); "
           f"step fused {t_fused:.3f} ms vs dense all-reduce {t_nccl:.3f} ms")
 dist.destroy_process_group()

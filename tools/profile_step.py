@@ -11,9 +11,10 @@ ap.add_argument("--H", type=int, default=1080); ap.add_argument("--D", type=int,
 ap.add_argument("--seed", type=int, default=1003); ap.add_argument("--scale-mult", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=3); ap.add_argument("--ref", action="store_true")
 ap.add_argument("--scene", default="shell", choices=["shell", "frustum"])
+ap.add_argument("--shuffled", action="store_true", help="frustum scene in random memory order (default: raster order)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-_scene = (syn.make_frustum_scene(a.P, a.seed, a.W, a.H) if a.scene == "frustum"
+_scene = (syn.make_frustum_scene(a.P, a.seed, a.W, a.H, raster=not a.shuffled) if a.scene == "frustum"
           else syn.make_scene(a.P, a.seed, scale_mult=a.scale_mult))
 sc = {k: v.to(dev) for k, v in _scene.items()}
 cam = syn.make_camera(a.W, a.H)
