@@ -170,7 +170,9 @@ class Ours:
         self.rast = R.GaussianRasterizer(self.settings)
         # k_project, k_count_tiles, k_tile_scan, k_shade_emit, k_tile_sort, k_tile_sort_mid, k_tile_sort_big, k_blend_fwd,
         # k_blend_bwd, k_grad_vis, k_grad_write (profiles/r01_launches_ours.csv) -- our kernels only, no torch kernels
-        self.kernels_per_step = 12            # + k_grad_dense (returns at once unless most Gaussians are visible)
+        # k_clear_words, k_project, k_count_tiles, k_tile_scan, k_shade_emit, k_tile_sort, k_tile_sort_mid, k_tile_sort_big,
+        # k_blend_fwd | k_blend_bwd, k_grad_vis, k_grad_write (+ k_grad_dense unless the host can prove the sparse regime)
+        self.kernels_per_step = 12
         self.last = None
         self.rasts, self.order, self.k = None, None, 0
 

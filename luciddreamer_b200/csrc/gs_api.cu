@@ -82,6 +82,15 @@ int debug_sync(const GsFrame* f, cudaStream_t s, const char* what) {
 
 }  // namespace
 
+__global__ void k_clear_words(uint32_t* __restrict__ p, size_t words) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+void gs_launch_clear_words(uint32_t* p, size_t words, cudaStream_t s) {
+    if (!words) return;
+    const int grid = (int)((words + 255) / 256 < 296 ? (words + 255) / 256 : 296);
+    k_clear_words<<<grid, 256, 0, s>>>(p, words);
+}
+
 constexpr int kNumKernels = GS_NUM_KERNELS;
 static const char* const kKernelNames[kNumKernels] = {"k_project", "k_tile_scan", "k_shade_emit", "k_tile_sort",
                                                       "k_tile_sort_big", "k_blend_fwd", "k_blend_bwd", "k_grad_vis",
@@ -234,7 +243,7 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     }
     host_slot->overflow = 0;                             // cleared; kernel writes 0xC0FFEE when done
     // zero tile histogram + status in one memset (they are adjacent)
-    GS_CUDA(cudaMemsetAsync(il.tile_cnt, 0, (size_t)((char*)il.status - (char*)il.tile_cnt) + sizeof(GsDevStatus), s));
+    gs_launch_clear_words(il.tile_cnt, ((size_t)((char*)il.status - (char*)il.tile_cnt) + sizeof(GsDevStatus)) / 4, s);
     if (f->P > 0) {
         GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
         GS_TIMED(ctx, 0, s, gs_launch_project(v, f->means3D, f->opacities, f->scales, f->rotations, f->cov3D_precomp,

@@ -283,6 +283,11 @@ __device__ __forceinline__ bool gs_box_hit(float mx, float my, float A, float B,
     return !(best < thr);
 }
 
+// Zeroes `words` 32-bit words with a KERNEL.  cudaMemsetAsync nodes may be served by a copy engine, where they queue
+// behind whatever large host<->device transfer is in flight on another stream (measured: a CUDA-graph step stalled
+// ~0.2 ms per replay behind the next step's 6 MB image upload); a kernel only depends on its own stream.
+void gs_launch_clear_words(uint32_t* p, size_t words, cudaStream_t s);
+
 // launchers (defined in the .cu files, used by gs_api.cu)
 struct GsGradPtrs {
     float *dmeans3D, *dmeans2D, *dsh, *dcolors, *dopacity, *dscales, *drots, *dcov3D;

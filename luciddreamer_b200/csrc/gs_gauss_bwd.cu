@@ -20,6 +20,11 @@ constexpr int kT = 256;
 // masked), 16-31 SH basis, 32-34 dcolor (raw), 35-40 dcov3D, 41-43 pad
 constexpr int kRow = GS_GOUT_FLOATS;
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_store(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
 constexpr int kVisT = 64;              // small CTAs: P_vis is often only a few 10^4, spread it over all SMs
 
 // One Gaussian's gradients from the 9 sums of the tile pass (a0, a1, a2 = its accumulator row): computeCov2DCUDA
@@ -276,11 +281,47 @@ __device__ __forceinline__ void cta_zero_run(float* __restrict__ base, long long
 }
 
 // `cl` = s_slot[threadIdx.x]; `count` = number of visible rows of the CTA
+// One run of zeros by TMA: `bytes` (a multiple of 16) from the 16 KB zero buffer in shared memory, 16 KB at a time.
+__device__ __forceinline__ bool tma_zero_run(float* base, long long row0, int nf, int rows, uint32_t zsrc) {
+    if (!base || nf <= 0) return true;
+    float* p = base + row0 * nf;
+    if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+    long long bytes = (long long)rows * nf * 4;
+    for (char* d = reinterpret_cast<char*>(p); bytes > 0; d += 16384, bytes -= 16384)
+        tma_store(d, zsrc, (uint32_t)(bytes < 16384 ? bytes : 16384));
+    return true;
+}
+
 template <int NT, int RS>
 __device__ __forceinline__ void cta_write_block(const int P, const int M, const long long row0, const float* s_row,
-                                                const int* s_slot, const int cl, const int count, const GsGradPtrs& g) {
+                                                const int* s_slot, const int cl, const int count, const GsGradPtrs& g,
+                                                float* zero_smem = nullptr) {
     const int tid = threadIdx.x;
     const long long i = row0 + tid;
+    __shared__ int s_misaligned;
+    if (count == 0 && row0 + NT <= P && zero_smem) {
+        // no visible row in this CTA (the common case when only a few per cent of the Gaussians are on screen): the NT
+        // rows of every output are one contiguous run -> the TMA streams zeros out of a 16 KB shared-memory buffer
+        // (eight bulk stores per CTA instead of ~4000 store instructions)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int f = tid; f < 1024; f += NT) reinterpret_cast<float4*>(zero_smem)[f] = z4;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t z = smem_u32(zero_smem);
+            const int M3z = g.dsh ? M * 3 : 0;
+            bool ok = ((NT * 4) & 15) == 0;
+            ok = ok && tma_zero_run(g.dmeans3D, row0, 3, NT, z) && tma_zero_run(g.dmeans2D, row0, 3, NT, z) &&
+                 tma_zero_run(g.dscales, row0, 3, NT, z) && tma_zero_run(g.dcolors, row0, 3, NT, z) &&
+                 tma_zero_run(g.dcov3D, row0, 6, NT, z) && tma_zero_run(g.dopacity, row0, 1, NT, z) &&
+                 tma_zero_run(g.drots, row0, 4, NT, z) && tma_zero_run(g.dsh, row0, M3z, NT, z);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source buffer is shared memory
+            s_misaligned = ok ? 0 : 1;
+        }
+        __syncthreads();
+        if (!s_misaligned) return;
+    }
     if (count == 0 && row0 + NT <= P) {
         // no visible row in this CTA (the common case when only a few per cent of the Gaussians are on screen):
         // the NT rows of every output are one contiguous run -> straight 128-bit zero stores, no index maths
@@ -380,7 +421,7 @@ k_grad_write(const int P, const int M, const int* __restrict__ radii, const floa
         for (int k = 0; k < kRow / 4; k++) dstr[k] = __ldg(src + k);
     }
     __syncthreads();
-    cta_write_block<kT, kRow>(P, M, row0, s_row, s_slot, cl, s_count, g);
+    cta_write_block<kT, kRow>(P, M, row0, s_row, s_slot, cl, s_count, g, s_row);   // s_row doubles as the zero buffer
 }
 
 // ---- dense regime (more than half of the Gaussians visible -- LucidDreamer's own workload: every Gaussian comes from a
@@ -400,15 +441,10 @@ struct DenseStage {                    // byte offsets inside one stage
 };
 constexpr int kDenseSmem = 2 * DenseStage::bytes;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tma_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tma_store(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-
 __global__ void __launch_bounds__(kDT, 3)
 k_grad_dense(const GsView v, const float* __restrict__ means3D, const float* __restrict__ shs,
              const float* __restrict__ scales, const float* __restrict__ rotations, const int* __restrict__ radii,

@@ -178,7 +178,7 @@ k_l1_loss_grad(const float* __restrict__ color /*[3,H,W]*/, const uint8_t* __res
 
 void gs_launch_l1_loss_grad(const float* color, const uint8_t* target, int H, int W, float weight, float* dL_dcolor,
                             float* loss, int num_sms, cudaStream_t s) {
-    cudaMemsetAsync(loss, 0, sizeof(float), s);
+    gs_launch_clear_words(reinterpret_cast<uint32_t*>(loss), 1, s);
     k_l1_loss_grad<<<num_sms * 8, 256, 0, s>>>(color, target, H, W, weight, dL_dcolor, loss);
 }
 
@@ -187,7 +187,7 @@ void gs_launch_photometric(const float* img, const float* gt, int H, int W, floa
                            float* dL_dimg, float* loss3, cudaStream_t s) {
     float* sums = (float*)scratch;
     float* maps = (float*)((char*)scratch + 256);
-    cudaMemsetAsync(sums, 0, 2 * sizeof(float), s);
+    gs_launch_clear_words(reinterpret_cast<uint32_t*>(sums), 2, s);
     dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, 3);
     k_photo_fwd<<<grid, kTile * kTile, 0, s>>>(img, gt, H, W, maps, sums);
     k_photo_finish<<<1, 1, 0, s>>>(sums, H, W, lambda_dssim, loss3);

@@ -80,19 +80,18 @@ __device__ __forceinline__ void cta_for_each_candidate(const CandShared& s, uint
     if (total == 0) return;
     uint32_t q = threadIdx.x;
     int c = 0;
-    if (q < total) {
-        int lo = 0, hi = CH;                             // largest c with cum[c] <= q (binary search once ...)
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s.cum[mid] <= q) lo = mid; else hi = mid;
-        }
-        c = lo;
-    }
     for (uint32_t base = 0; base < total; base += kThreads, q += kThreads) {
         const bool valid = q < total;
         int r = 0, tx = 0, ty = 0;
         if (valid) {
-            while (s.cum[c + 1] <= q) c++;               // ... then the slot only ever advances
+            // largest c with cum[c] <= q: binary search in [c, CH) -- consecutive rounds are kThreads candidates apart,
+            // i.e. ~100 Gaussians when the rects are small, far too many for a linear advance
+            int lo = c, hi = CH;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s.cum[mid] <= q) lo = mid; else hi = mid;
+            }
+            c = lo;
             r = (int)(q - s.cum[c]);
             const int w = s.rw[c];
             const int yy = r / w, xx = r - yy * w;

@@ -22,9 +22,9 @@ namespace {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kWarpKeys = 256;       // 2 x 2 KB of u64 keys per warp
-constexpr int kMidThreads = 128;
+constexpr int kMidThreads = 256;
 constexpr int kMidKeys = 2048;       // 2 x 16 KB static shared memory
-constexpr int kBigThreads = 512;
+constexpr int kBigThreads = 1024;
 constexpr int kBigKeys = 8192;       // 2 x 64 KB dynamic shared memory
 
 // sorts the 32 keys held one per lane (ascending across lanes); keys are unique
