@@ -11,6 +11,8 @@
 //                 dense [P,*] intermediates (dL_dconic, dL_dcov3D, dL_dcolors never exist as dense tensors unless
 //                 the caller asks for them).  HBM-bound: ~248 B written + 4 B read per Gaussian; every store is a
 //                 fully coalesced 128-bit (dL_dsh, rotations) or 32-bit row-contiguous store.
+#include <cstdlib>
+
 #include "gs_common.cuh"
 
 namespace {
@@ -424,6 +426,86 @@ k_grad_write(const int P, const int M, const int* __restrict__ radii, const floa
     cta_write_block<kT, kRow>(P, M, row0, s_row, s_slot, cl, s_count, g, s_row);   // s_row doubles as the zero buffer
 }
 
+// ---- the common input mode (SH with 16 stored coefficients, scales + rotations, 16-byte aligned outputs): the block's
+// slice of all six dense gradient tensors is ASSEMBLED IN SHARED MEMORY -- zeros, plus the expanded rows of the few
+// visible Gaussians -- and leaves the SM as six TMA bulk stores.  Replaces ~60 global store instructions per thread by
+// ~16 shared-memory stores; the HBM write stream is issued by the copy engine of the SM at full width.
+constexpr int kWT = 128;               // rows per block
+struct WriteImg {                      // byte offsets of the block image in shared memory
+    static constexpr int sh = 0, m3 = 24576, m2 = 26112, sc = 27648, op = 29184, rot = 29696, bytes = 31744;
+};
+
+__global__ void __launch_bounds__(kWT)
+k_grad_write_tma(const int P, const int* __restrict__ radii, const float4* __restrict__ acc,
+                 const float* __restrict__ gout, const GsGradPtrs g, const GsDevStatus* __restrict__ status,
+                 const bool dense_elsewhere) {
+    if (dense_elsewhere && gs_dense_regime(status, P)) return;
+    __shared__ __align__(128) unsigned char img[WriteImg::bytes];
+    const int tid = threadIdx.x;
+    const int nblk = (P + kWT - 1) / kWT;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {        // persistent grid: an early exit costs one wave
+    const long long row0 = (long long)blk * kWT, i = row0 + tid;
+    const bool full = row0 + kWT <= P;
+    const bool vis = i < P && radii[i] > 0;
+    float4 o[11];
+    if (vis) {                                             // the row's compact gradients (k_grad_vis), in flight early
+        const uint32_t slot = __float_as_uint(__ldg(reinterpret_cast<const float*>(acc + (size_t)3 * i + 2) + 3));
+        const float4* src = reinterpret_cast<const float4*>(gout + (size_t)slot * kRow);
+#pragma unroll
+        for (int k = 0; k < 11; k++) o[k] = __ldg(src + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 11; k++) o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float bs[16] = {o[4].x, o[4].y, o[4].z, o[4].w, o[5].x, o[5].y, o[5].z, o[5].w,
+                          o[6].x, o[6].y, o[6].z, o[6].w, o[7].x, o[7].y, o[7].z, o[7].w};
+    const float dR[3] = {o[3].y, o[3].z, o[3].w};
+    if (full) {
+        // every thread writes its own row of every tensor (zeros for an invisible row): conflict-free, no second pass
+        float4* d4 = reinterpret_cast<float4*>(img + WriteImg::sh) + tid * 12;
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            float w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int e = 4 * j + u; w[u] = bs[e / 3] * dR[e % 3]; }
+            d4[j] = make_float4(w[0], w[1], w[2], w[3]);
+        }
+        float* m3 = reinterpret_cast<float*>(img + WriteImg::m3) + tid * 3;
+        float* m2 = reinterpret_cast<float*>(img + WriteImg::m2) + tid * 3;
+        float* sc = reinterpret_cast<float*>(img + WriteImg::sc) + tid * 3;
+        m3[0] = o[0].x; m3[1] = o[0].y; m3[2] = o[0].z;
+        m2[0] = o[0].w; m2[1] = o[1].x; m2[2] = 0.f;
+        sc[0] = o[1].z; sc[1] = o[1].w; sc[2] = o[2].x;
+        reinterpret_cast<float*>(img + WriteImg::op)[tid] = o[1].y;
+        reinterpret_cast<float4*>(img + WriteImg::rot)[tid] = make_float4(o[2].y, o[2].z, o[2].w, o[3].x);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t base = smem_u32(img);
+            tma_store(g.dsh + row0 * 48, base + WriteImg::sh, 24576);
+            tma_store(g.dmeans3D + row0 * 3, base + WriteImg::m3, 1536);
+            tma_store(g.dmeans2D + row0 * 3, base + WriteImg::m2, 1536);
+            tma_store(g.dscales + row0 * 3, base + WriteImg::sc, 1536);
+            tma_store(g.dopacity + row0, base + WriteImg::op, 512);
+            tma_store(g.drots + row0 * 4, base + WriteImg::rot, 2048);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the image is read before it is rebuilt
+        }
+        __syncthreads();
+        continue;
+    }
+    if (i < P) {                                           // last, partial block: plain stores
+        g.dmeans3D[3 * i] = o[0].x; g.dmeans3D[3 * i + 1] = o[0].y; g.dmeans3D[3 * i + 2] = o[0].z;
+        g.dmeans2D[3 * i] = o[0].w; g.dmeans2D[3 * i + 1] = o[1].x; g.dmeans2D[3 * i + 2] = 0.f;
+        g.dopacity[i] = o[1].y;
+        g.dscales[3 * i] = o[1].z; g.dscales[3 * i + 1] = o[1].w; g.dscales[3 * i + 2] = o[2].x;
+        g.drots[4 * i] = o[2].y; g.drots[4 * i + 1] = o[2].z; g.drots[4 * i + 2] = o[2].w; g.drots[4 * i + 3] = o[3].x;
+#pragma unroll
+        for (int e = 0; e < 48; e++) g.dsh[i * 48 + e] = bs[e / 3] * dR[e % 3];
+    }
+  }
+}
+
 // ---- dense regime (more than half of the Gaussians visible -- LucidDreamer's own workload: every Gaussian comes from a
 // pixel of a training view, luciddreamer.py:370-374): ONE persistent kernel over all P rows replaces k_grad_vis +
 // k_grad_write, built as a TMA pipeline.  A CTA owns blocks of 128 CONSECUTIVE Gaussians; everything such a block reads
@@ -805,6 +887,14 @@ void gs_grad_write_init() {
 }
 void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
                           const GsDevStatus* status, bool dense_elsewhere, cudaStream_t s) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (M == 16 && g.dsh && g.dmeans3D && g.dmeans2D && g.dscales && g.dopacity && g.drots && !g.dcolors && !g.dcov3D &&
+        al16(g.dsh) && al16(g.dmeans3D) && al16(g.dmeans2D) && al16(g.dscales) && al16(g.dopacity) && al16(g.drots) &&
+        !getenv("GS_NO_TMA")) {
+        const int need = (P + kWT - 1) / kWT;
+        k_grad_write_tma<<<need < 148 * 7 * 2 ? need : 148 * 7 * 2, kWT, 0, s>>>(P, radii, acc, gout, g, status, dense_elsewhere);
+        return;
+    }
     const int grid = (P + kT - 1) / kT;
     k_grad_write<<<grid, kT, kT * kRow * sizeof(float), s>>>(P, M, radii, acc, gout, g, status, dense_elsewhere);
 }

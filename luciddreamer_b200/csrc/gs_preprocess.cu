@@ -84,14 +84,17 @@ __device__ __forceinline__ void cta_for_each_candidate(const CandShared& s, uint
         const bool valid = q < total;
         int r = 0, tx = 0, ty = 0;
         if (valid) {
-            // largest c with cum[c] <= q: binary search in [c, CH) -- consecutive rounds are kThreads candidates apart,
-            // i.e. ~100 Gaussians when the rects are small, far too many for a linear advance
-            int lo = c, hi = CH;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s.cum[mid] <= q) lo = mid; else hi = mid;
+            // largest c with cum[c] <= q.  Consecutive rounds are kThreads candidates apart: a step or two when the rects
+            // are large, ~100 Gaussians when they are small -- a few linear steps, then a binary search in [c, CH)
+            for (int k = 0; k < 3 && s.cum[c + 1] <= q; k++) c++;
+            if (s.cum[c + 1] <= q) {
+                int lo = c, hi = CH;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s.cum[mid] <= q) lo = mid; else hi = mid;
+                }
+                c = lo;
             }
-            c = lo;
             r = (int)(q - s.cum[c]);
             const int w = s.rw[c];
             const int yy = r / w, xx = r - yy * w;
