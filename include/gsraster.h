@@ -207,6 +207,13 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
 int gs_backward_blend(GsContext* ctx, const GsFrame* f, const void* geom_buffer, const void* binning_buffer,
                       int64_t pair_capacity, const void* image_buffer, const float* dL_dout_color,
                       gs_stream_t stream);
+/* Optional, BEFORE gs_backward_blend, for hosts that have the gradient outputs allocated by then: zero-fills them on a
+ * side stream of the context beside the tile pass; gs_backward_gradients (same ctx, same outputs) then joins that
+ * stream and writes only the rows of the visible Gaussians.  A no-op (GS_OK) when the outputs do not qualify: all six of
+ * dL_dmeans3D / dL_dmeans2D / dL_dsh (M = 16) / dL_dopacity / dL_dscales / dL_drotations wanted, bases 16-byte aligned,
+ * P a multiple of 4, no peer reduce.  gs_backward calls it itself. */
+int gs_backward_prefill(GsContext* ctx, const GsFrame* f, const void* image_buffer, const GsGrads* grads,
+                        gs_stream_t stream);
 int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii, const void* geom_buffer,
                           const void* image_buffer, void* grad_scratch, size_t grad_scratch_bytes,
                           const GsGrads* grads, gs_stream_t stream);

@@ -77,6 +77,7 @@ SYMBOLS = [
     ("gs_backward", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(GsGrads),
                               C.c_void_p]),
+    ("gs_backward_prefill", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.POINTER(GsGrads), C.c_void_p]),
     ("gs_backward_blend", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     ("gs_backward_gradients", C.c_int, [C.c_void_p, C.POINTER(GsFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -109,6 +109,10 @@ struct GsContext {
     cudaEvent_t events[kSlots];
     unsigned slot_gen[kSlots];     // generation of the ticket that currently owns the slot
     std::atomic<unsigned> next;
+    cudaStream_t aux;              // side stream of gs_backward_prefill (zero-fill beside the tile pass)
+    cudaEvent_t aux_fork, aux_join;
+    bool aux_ready;
+    const void* prefilled;         // dL_dsh pointer of the outputs the most recent prefill was issued for
     cudaStream_t vstreams[kMaxViewStreams];   // internal streams of gs_forward_views (created on first use)
     cudaEvent_t vfork, vjoin[kMaxViewStreams];
     bool vstreams_ready;
@@ -158,6 +162,8 @@ int gs_context_create(int device, GsContext** out) {
     c->last_visible = -1;
     c->profile = 0;
     c->vstreams_ready = false;
+    c->aux_ready = false;
+    c->prefilled = nullptr;
     for (int i = 0; i < kSlots; i++) c->slot_gen[i] = 0;
     for (int i = 0; i < kNumKernels; i++) c->pev_used[i] = false;
     for (int i = 0; i < 2 * kNumKernels; i++) cudaEventCreate(&c->pev[i]);
@@ -197,6 +203,7 @@ void gs_context_destroy(GsContext* c) {
     if (!c) return;
     for (int i = 0; i < kSlots; i++) cudaEventDestroy(c->events[i]);
     for (int i = 0; i < 2 * kNumKernels; i++) cudaEventDestroy(c->pev[i]);
+    if (c->aux_ready) { cudaEventDestroy(c->aux_fork); cudaEventDestroy(c->aux_join); cudaStreamDestroy(c->aux); }
     if (c->vstreams_ready) {
         cudaEventDestroy(c->vfork);
         for (int i = 0; i < kMaxViewStreams; i++) { cudaEventDestroy(c->vjoin[i]); cudaStreamDestroy(c->vstreams[i]); }
@@ -391,6 +398,60 @@ size_t gs_backward_scratch_bytes(int64_t num_visible) {
     return gs_align_up((size_t)(num_visible > 0 ? num_visible : 1) * GS_GOUT_FLOATS * sizeof(float), 256);
 }
 
+static GsGradPtrs grad_ptrs(const GsFrame* f, const GsGrads* grads) {
+    GsGradPtrs g;
+    g.dmeans3D = grads->dL_dmeans3D; g.dmeans2D = grads->dL_dmeans2D; g.dsh = f->shs ? grads->dL_dsh : nullptr;
+    g.dcolors = grads->dL_dcolors; g.dopacity = grads->dL_dopacity;
+    g.dscales = grads->dL_dscales; g.drots = grads->dL_drotations; g.dcov3D = grads->dL_dcov3D;
+    return g;
+}
+
+// the dense-regime kernel (k_grad_dense) covers the reference's own input mode: SH degree <= 3 stored as 16 coefficients,
+// scales + rotations, all six gradients wanted; its bulk copies need 16-byte aligned bases (gsraster.h)
+static bool dense_eligible(const GsFrame* f, const GsGrads* grads, const GsGradPtrs& g) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return grads->peer_world <= 0 && f->shs && f->M == 16 && !f->cov3D_precomp && f->scales && f->rotations &&
+           !grads->dL_dcolors && !grads->dL_dcov3D && g.dmeans3D && g.dmeans2D && g.dsh && g.dopacity && g.dscales &&
+           g.drots && al16(f->means3D) && al16(f->scales) && al16(g.dmeans3D) && al16(g.dmeans2D) && al16(g.dsh) &&
+           al16(g.dopacity) && al16(g.dscales) && al16(g.drots) && !getenv("GS_NO_DENSE");
+}
+
+// Optional, before gs_backward_blend: zero-fills the dense gradient outputs on a side stream of the context, BESIDE the
+// tile pass (which is issue bound and leaves the memory system idle).  gs_backward_gradients then waits for the fill and
+// lets the per-Gaussian kernel write the visible rows straight into the outputs -- the streaming writer of the sparse
+// regime disappears from the critical path.  Returns GS_OK without doing anything when the outputs do not qualify
+// (other input modes, misaligned bases, peer reduce): gs_backward_gradients falls back to its own writer.
+int gs_backward_prefill(GsContext* ctx, const GsFrame* f, const void* image_buffer, const GsGrads* grads, gs_stream_t stream) {
+    if (!ctx || !grads) return fail(GS_EINVAL, "ctx / grads is NULL");
+    int rc = check_frame(f);
+    if (rc) return rc;
+    ctx->prefilled = nullptr;
+    if (f->P == 0 || !image_buffer || grads->peer_world > 0 || (f->P & 3) || f->cov3D_precomp || !f->scales || !f->rotations ||
+        getenv("GS_NO_PREFILL"))
+        return GS_OK;
+    const GsGradPtrs g = grad_ptrs(f, grads);
+    if (!gs_grads_tma_ok(f->shs ? f->M : 0, g)) return GS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!ctx->aux_ready) {
+        int prev = 0;
+        GS_CUDA(cudaGetDevice(&prev));
+        GS_CUDA(cudaSetDevice(ctx->device));
+        GS_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        GS_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+        GS_CUDA(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
+        GS_CUDA(cudaSetDevice(prev));
+        ctx->aux_ready = true;
+    }
+    GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
+    GS_CUDA(cudaEventRecord(ctx->aux_fork, s));            // the outputs were allocated in `stream` order before this call
+    GS_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->aux_fork, 0));
+    // in the dense regime k_grad_dense writes every row itself: the fill exits on the device (only if that kernel will run)
+    gs_launch_fill_zero(f->P, ctx->num_sms, g, il.status, dense_eligible(f, grads, g), ctx->aux);
+    GS_CUDA(cudaEventRecord(ctx->aux_join, ctx->aux));
+    ctx->prefilled = grads->dL_dsh;
+    return GS_OK;
+}
+
 // Backward, first half: reverse tile traversal into the per-Gaussian accumulators.  Needs no gradient outputs,
 // so a host can enqueue it before it has allocated them.
 int gs_backward_blend(GsContext* ctx, const GsFrame* f, const void* geom_buffer, const void* binning_buffer,
@@ -424,24 +485,22 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
     const GsView v = make_view(f);
     GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
     GsGeomLayout gl = gs_geom_layout(const_cast<void*>(geom_buffer), f->P);
-    GsGradPtrs g;
-    g.dmeans3D = grads->dL_dmeans3D; g.dmeans2D = grads->dL_dmeans2D; g.dsh = f->shs ? grads->dL_dsh : nullptr;
-    g.dcolors = grads->dL_dcolors; g.dopacity = grads->dL_dopacity;
-    g.dscales = grads->dL_dscales; g.drots = grads->dL_drotations; g.dcov3D = grads->dL_dcov3D;
+    const GsGradPtrs g = grad_ptrs(f, grads);
     float* gout = (float*)grad_scratch;
+    // gs_backward_prefill ran for these outputs: join the side stream, the per-Gaussian kernel scatters final rows
+    const bool prefilled = ctx && ctx->prefilled && ctx->prefilled == (const void*)grads->dL_dsh && grads->peer_world <= 0;
+    if (prefilled) {
+        GS_CUDA(cudaStreamWaitEvent(s, ctx->aux_join, 0));
+        ctx->prefilled = nullptr;
+    }
     // When most Gaussians are visible (decided on the device from num_visible) ONE dense kernel does the whole
     // per-Gaussian backward and the compact pair below returns at once; otherwise the other way round.  The dense
     // kernel covers the reference's own input mode (SH degree <= 3 stored as 16 coefficients, scales + rotations).
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    const bool dense_ok = grads->peer_world <= 0 && f->shs && f->M == 16 && !f->cov3D_precomp && f->scales && f->rotations &&
-                          !grads->dL_dcolors && !grads->dL_dcov3D && g.dmeans3D && g.dmeans2D && g.dsh && g.dopacity &&
-                          g.dscales && g.drots && al16(f->means3D) && al16(f->scales) && al16(g.dmeans3D) &&
-                          al16(g.dmeans2D) && al16(g.dsh) && al16(g.dopacity) && al16(g.dscales) && al16(g.drots) &&
-                          !getenv("GS_NO_DENSE");          // bulk copies need 16-byte aligned bases (gsraster.h)
+    const bool dense_ok = dense_eligible(f, grads, g);
     GS_TIMED(ctx, 7, s, gs_launch_grad_vis(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs,
                                            f->cov3D_precomp ? nullptr : f->scales,
                                            f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec, gl.acc,
-                                           gl.vis_list, il.status, gout, dense_ok, s));
+                                           gl.vis_list, il.status, gout, dense_ok, prefilled, g, s));
     if ((rc = debug_sync(f, s, "grad_vis"))) return rc;
     if (grads->peer_world > 0) {
         // data-parallel shared-model step: the five parameter gradients are reduced straight into every rank's
@@ -454,8 +513,10 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
                                                         grads->peer_epoch_begin, grads->peer_epoch_end, s));
         return debug_sync(f, s, "grad_reduce_peers");
     }
-    GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, il.status, dense_ok, s));
-    if ((rc = debug_sync(f, s, "grad_write"))) return rc;
+    if (!prefilled) {
+        GS_TIMED(ctx, 9, s, gs_launch_grad_write(f->P, v.M, radii, gl.acc, gout, g, il.status, dense_ok, s));
+        if ((rc = debug_sync(f, s, "grad_write"))) return rc;
+    }
     // a scratch buffer sized from the true visible count (synchronising hosts) can prove the sparse regime: no launch
     const long long nvis_bound = (long long)(grad_scratch_bytes / (GS_GOUT_FLOATS * sizeof(float)));
     if (dense_ok && 2 * nvis_bound > (long long)f->P) {
@@ -475,7 +536,9 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
                 const GsGrads* grads, gs_stream_t stream) {
     (void)dL_dout_depth;                                 // depth gradient disabled in the reference
     if (!grads) return fail(GS_EINVAL, "grads is NULL");
-    int rc = gs_backward_blend(ctx, f, geom_buffer, binning_buffer, pair_capacity, image_buffer, dL_dout_color, stream);
+    int rc = ctx ? gs_backward_prefill(ctx, f, image_buffer, grads, stream) : GS_OK;
+    if (rc) return rc;
+    rc = gs_backward_blend(ctx, f, geom_buffer, binning_buffer, pair_capacity, image_buffer, dL_dout_color, stream);
     if (rc) return rc;
     return gs_backward_gradients(ctx, f, radii, geom_buffer, image_buffer, grad_scratch, grad_scratch_bytes, grads, stream);
 }

@@ -326,7 +326,10 @@ void gs_launch_blend_bwd_r1(const GsView& v, const uint32_t* tile_off, const uin
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
                         const uint32_t* vis_list, const GsDevStatus* status, float* gout, bool dense_elsewhere,
-                        cudaStream_t s);
+                        bool scatter, GsGradPtrs g, cudaStream_t s);
+bool gs_grads_tma_ok(int M, const GsGradPtrs& g);
+void gs_launch_fill_zero(int P, int num_sms, const GsGradPtrs& g, const GsDevStatus* status, bool dense_elsewhere,
+                         cudaStream_t s);
 void gs_launch_grad_dense(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                           const float* rotations, const int* radii, float4* acc, const GsDevStatus* status, GsGradPtrs g,
                           cudaStream_t s);

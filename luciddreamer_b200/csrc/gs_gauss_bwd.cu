@@ -230,7 +230,7 @@ k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __res
            const float* __restrict__ scales, const float* __restrict__ rotations,
            const float* __restrict__ cov3D_precomp, const float4* __restrict__ rec, float4* __restrict__ acc,
            const uint32_t* __restrict__ vis_list, const GsDevStatus* __restrict__ status, float* __restrict__ gout,
-           const bool dense_elsewhere) {
+           const bool dense_elsewhere, const bool scatter, const GsGradPtrs g) {
     if (dense_elsewhere && gs_dense_regime(status, v.P)) return;
     __shared__ GsCam cam;
     gs_load_cam(v, &cam);
@@ -248,9 +248,60 @@ k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __res
 #pragma unroll
             for (int k = 0; k < 48; k++) cf[k] = k < na3 ? __ldg(sh + k) : 0.f;
         };
-        grad_row(v, cam, i, a0, a1, a2, clamped, means3D, shs != nullptr, scales, rotations, cov3D_precomp, fill,
-                 reinterpret_cast<float4*>(gout + (size_t)c * kRow));
+        if (!scatter) {
+            grad_row(v, cam, i, a0, a1, a2, clamped, means3D, shs != nullptr, scales, rotations, cov3D_precomp, fill,
+                     reinterpret_cast<float4*>(gout + (size_t)c * kRow));
+            continue;
+        }
+        // the dense outputs were zero-filled beside the tile pass (k_fill_zero): the final rows go straight into them
+        float4 o[11];
+        grad_row(v, cam, i, a0, a1, a2, clamped, means3D, true, scales, rotations, cov3D_precomp, fill, o);
+        g.dmeans3D[3 * i] = o[0].x; g.dmeans3D[3 * i + 1] = o[0].y; g.dmeans3D[3 * i + 2] = o[0].z;
+        g.dmeans2D[3 * i] = o[0].w; g.dmeans2D[3 * i + 1] = o[1].x;
+        g.dopacity[i] = o[1].y;
+        g.dscales[3 * i] = o[1].z; g.dscales[3 * i + 1] = o[1].w; g.dscales[3 * i + 2] = o[2].x;
+        reinterpret_cast<float4*>(g.drots)[i] = make_float4(o[2].y, o[2].z, o[2].w, o[3].x);
+        const float bs[16] = {o[4].x, o[4].y, o[4].z, o[4].w, o[5].x, o[5].y, o[5].z, o[5].w,
+                              o[6].x, o[6].y, o[6].z, o[6].w, o[7].x, o[7].y, o[7].z, o[7].w};
+        const float dR[3] = {o[3].y, o[3].z, o[3].w};
+        float4* d4 = reinterpret_cast<float4*>(g.dsh + (size_t)i * 48);
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            float w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int e = 4 * j + u; w[u] = bs[e / 3] * dR[e % 3]; }
+            d4[j] = make_float4(w[0], w[1], w[2], w[3]);
+        }
     }
+}
+
+// Zero-fill of the six dense gradient tensors by TMA, issued on a side stream BESIDE the tile pass of the backward
+// (gs_backward_prefill): a persistent grid of single-warp CTAs, each streaming 16 KB bulk stores out of one zeroed
+// shared-memory page.  No loads, no index arithmetic; in the dense regime (k_grad_dense writes every row) it exits.
+struct FillRuns { char* p[6]; long long bytes[6]; };
+
+__global__ void __launch_bounds__(32)
+k_fill_zero(const FillRuns runs, const GsDevStatus* __restrict__ status, const int P, const bool dense_elsewhere) {
+    if (dense_elsewhere && gs_dense_regime(status, P)) return;
+    __shared__ __align__(128) float4 zero[1024];           // 16 KB
+    for (int f = threadIdx.x; f < 1024; f += 32) zero[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const uint32_t z = smem_u32(zero);
+    long long base = 0;
+    for (int r = 0; r < 6; r++) {
+        const long long nchunk = (runs.bytes[r] + 16383) / 16384;
+        // chunks are numbered across the six runs; CTA b takes chunks b, b + grid, ...
+        long long first = ((long long)blockIdx.x - base % gridDim.x + gridDim.x) % gridDim.x;
+        for (long long c = first; c < nchunk; c += gridDim.x) {
+            const long long off = c * 16384, left = runs.bytes[r] - off;
+            tma_store(runs.p[r] + off, z, (uint32_t)(left < 16384 ? left : 16384));
+        }
+        base += nchunk;
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Store phase shared by k_grad_write and k_grad_dense.  One CTA of NT threads = NT consecutive rows; s_slot[row] =
@@ -866,11 +917,30 @@ void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* a
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
                         const uint32_t* vis_list, const GsDevStatus* status, float* gout, bool dense_elsewhere,
-                        cudaStream_t s) {
+                        bool scatter, GsGradPtrs g, cudaStream_t s) {
     const int need = (v.P + kVisT - 1) / kVisT;
     const int grid = need < num_sms * 8 ? need : num_sms * 8;
     k_grad_vis<<<grid, kVisT, 0, s>>>(v, means3D, shs, scales, rotations, cov3D_precomp, rec, acc, vis_list, status, gout,
-                                      dense_elsewhere);
+                                      dense_elsewhere, scatter, g);
+}
+// true when the outputs qualify for the TMA paths (k_grad_write_tma / k_fill_zero + scatter): the reference's own input
+// mode (16 stored SH coefficients, scales + rotations), all six tensors wanted, 16-byte aligned
+bool gs_grads_tma_ok(int M, const GsGradPtrs& g) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return M == 16 && g.dsh && g.dmeans3D && g.dmeans2D && g.dscales && g.dopacity && g.drots && !g.dcolors && !g.dcov3D &&
+           al16(g.dsh) && al16(g.dmeans3D) && al16(g.dmeans2D) && al16(g.dscales) && al16(g.dopacity) && al16(g.drots) &&
+           !getenv("GS_NO_TMA");
+}
+void gs_launch_fill_zero(int P, int num_sms, const GsGradPtrs& g, const GsDevStatus* status, bool dense_elsewhere,
+                         cudaStream_t s) {
+    FillRuns r;
+    r.p[0] = (char*)g.dsh;      r.bytes[0] = (long long)P * 192;
+    r.p[1] = (char*)g.dmeans3D; r.bytes[1] = (long long)P * 12;
+    r.p[2] = (char*)g.dmeans2D; r.bytes[2] = (long long)P * 12;
+    r.p[3] = (char*)g.dscales;  r.bytes[3] = (long long)P * 12;
+    r.p[4] = (char*)g.dopacity; r.bytes[4] = (long long)P * 4;
+    r.p[5] = (char*)g.drots;    r.bytes[5] = (long long)P * 16;
+    k_fill_zero<<<num_sms * 2, 32, 0, s>>>(r, status, P, dense_elsewhere);
 }
 // the dense-regime twin of (k_grad_vis, k_grad_write): returns at once on the device unless most Gaussians are visible
 void gs_launch_grad_dense(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
@@ -887,10 +957,7 @@ void gs_grad_write_init() {
 }
 void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, const float* gout, GsGradPtrs g,
                           const GsDevStatus* status, bool dense_elsewhere, cudaStream_t s) {
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    if (M == 16 && g.dsh && g.dmeans3D && g.dmeans2D && g.dscales && g.dopacity && g.drots && !g.dcolors && !g.dcov3D &&
-        al16(g.dsh) && al16(g.dmeans3D) && al16(g.dmeans2D) && al16(g.dscales) && al16(g.dopacity) && al16(g.drots) &&
-        !getenv("GS_NO_TMA")) {
+    if (gs_grads_tma_ok(M, g)) {
         const int need = (P + kWT - 1) / kWT;
         k_grad_write_tma<<<need < 148 * 7 * 2 ? need : 148 * 7 * 2, kWT, 0, s>>>(P, radii, acc, gout, g, status, dense_elsewhere);
         return;

@@ -154,8 +154,6 @@ backward(int64_t ctx_ptr, const c10::optional<at::Tensor>& bg, const at::Tensor&
     const int64_t P = fr.P, M = fr.M;
     const at::Tensor gc = prep(grad_color, fr.dev, fr.keep);
     TORCH_CHECK(gc.defined() && gc.numel() == 3 * H * W, "dL_dout_color must be [3, H, W]");
-    // the tile pass goes to the GPU first; the allocations below overlap with it
-    GS_OK_OR_THROW(gs_backward_blend(ctx, &fr.f, geom.data_ptr(), binning.data_ptr(), cap, img.data_ptr(), fp(gc), s));
     // all gradients are views of ONE flat allocation, in bucket order [means3D | sh | opacity | scales | rotations |
     // means2D]; segment starts stay 256-byte aligned (128-bit stores in the kernels); every row is overwritten
     const int64_t w[6] = {3, 3 * M, 1, 3, 4, 3};
@@ -176,6 +174,9 @@ backward(int64_t ctx_ptr, const c10::optional<at::Tensor>& bg, const at::Tensor&
     g.dL_drotations = fr.f.rotations ? drot.data_ptr<float>() : nullptr;
     g.dL_dcolors = dcol.defined() ? dcol.data_ptr<float>() : nullptr;
     g.dL_dcov3D = dcov.defined() ? dcov.data_ptr<float>() : nullptr;
+    // zero-fill of the outputs on the context's side stream, beside the tile pass (no-op when they do not qualify)
+    GS_OK_OR_THROW(gs_backward_prefill(ctx, &fr.f, img.data_ptr(), &g, s));
+    GS_OK_OR_THROW(gs_backward_blend(ctx, &fr.f, geom.data_ptr(), binning.data_ptr(), cap, img.data_ptr(), fp(gc), s));
     const int64_t nscr = (int64_t)gs_backward_scratch_bytes(num_visible >= 0 ? num_visible : P);
     at::Tensor scratch = at::empty({nscr}, f32.dtype(at::kByte));
     GS_OK_OR_THROW(gs_backward_gradients(ctx, &fr.f, radii.data_ptr<int32_t>(), geom.data_ptr(), img.data_ptr(),
