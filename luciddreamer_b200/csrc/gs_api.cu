@@ -436,7 +436,12 @@ int gs_backward_prefill(GsContext* ctx, const GsFrame* f, const void* image_buff
         int prev = 0;
         GS_CUDA(cudaGetDevice(&prev));
         GS_CUDA(cudaSetDevice(ctx->device));
-        GS_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        // highest priority: the block scheduler hands freed SM resources to the fill's single-warp CTAs first; at equal
+        // priority they would wait until the tile pass (8 160 CTAs, launched into the caller's stream at the same moment)
+        // has nothing left to dispatch, i.e. run AFTER it (measured: +0.12 ms per step in the eager loop)
+        int pr_least = 0, pr_greatest = 0;
+        GS_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+        GS_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, pr_greatest));
         GS_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
         GS_CUDA(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
         GS_CUDA(cudaSetDevice(prev));
