@@ -940,7 +940,8 @@ void gs_launch_fill_zero(int P, int num_sms, const GsGradPtrs& g, const GsDevSta
     r.p[3] = (char*)g.dscales;  r.bytes[3] = (long long)P * 12;
     r.p[4] = (char*)g.dopacity; r.bytes[4] = (long long)P * 4;
     r.p[5] = (char*)g.drots;    r.bytes[5] = (long long)P * 16;
-    k_fill_zero<<<num_sms * 2, 32, 0, s>>>(r, status, P, dense_elsewhere);
+    static const int ctas = getenv("GS_FILL_CTAS") ? atoi(getenv("GS_FILL_CTAS")) : 0;   // tuning knob (experiments)
+    k_fill_zero<<<ctas > 0 ? ctas : num_sms * 4, 32, 0, s>>>(r, status, P, dense_elsewhere);
 }
 // the dense-regime twin of (k_grad_vis, k_grad_write): returns at once on the device unless most Gaussians are visible
 void gs_launch_grad_dense(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
