@@ -103,11 +103,12 @@ typedef struct GsGrads {
     void* const* peer_buckets;   /* HOST array of peer_world device pointers */
     void* peer_multicast;
     const int64_t* peer_seg_off; /* HOST array [5] */
-    /* Optional device-side barriers around the peer adds (replace the two host-launched barriers of the step):
-     * peer_signals[r] = rank r's signal words (peer-mapped uint32[64], zero-initialised, symmetric), peer_rank = this
-     * rank.  peer_epoch_begin != 0: the kernel first tells every rank "my bucket is zeroed" and adds only after all
-     * ranks said so for this epoch; peer_epoch_end != 0: the kernel ends only after every rank's adds of this epoch
-     * have landed.  Epochs increase by one per optimisation step.  NULL / 0: the caller synchronises the ranks. */
+    /* Optional cross-rank barriers around the peer adds, run by the library as one-warp kernels (instead of two
+     * barriers issued by the host): peer_signals[r] = rank r's signal words (peer-mapped uint32[64], zero-initialised,
+     * symmetric), peer_rank = this rank.  peer_epoch_begin != 0: "every rank has cleared its bucket" is awaited before
+     * the adds -- gs_backward puts that wait on a side stream beside the tile pass; peer_epoch_end != 0: the call's
+     * stream continues only after every rank's adds of this epoch have landed.  Epochs increase by one per
+     * optimisation step.  NULL / 0: the caller synchronises the ranks. */
     void* const* peer_signals;   /* HOST array of peer_world device pointers, or NULL */
     int32_t peer_rank;
     uint32_t peer_epoch_begin;

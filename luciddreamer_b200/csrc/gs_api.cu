@@ -113,6 +113,7 @@ struct GsContext {
     cudaEvent_t aux_fork, aux_join;
     bool aux_ready;
     const void* prefilled;         // dL_dsh pointer of the outputs the most recent prefill was issued for
+    bool peer_barrier_pending;     // the "every bucket is cleared" barrier of this step runs on `aux`
     cudaStream_t vstreams[kMaxViewStreams];   // internal streams of gs_forward_views (created on first use)
     cudaEvent_t vfork, vjoin[kMaxViewStreams];
     bool vstreams_ready;
@@ -164,6 +165,7 @@ int gs_context_create(int device, GsContext** out) {
     c->vstreams_ready = false;
     c->aux_ready = false;
     c->prefilled = nullptr;
+    c->peer_barrier_pending = false;
     for (int i = 0; i < kSlots; i++) c->slot_gen[i] = 0;
     for (int i = 0; i < kNumKernels; i++) c->pev_used[i] = false;
     for (int i = 0; i < 2 * kNumKernels; i++) cudaEventCreate(&c->pev[i]);
@@ -416,6 +418,24 @@ static bool dense_eligible(const GsFrame* f, const GsGrads* grads, const GsGradP
            al16(g.dopacity) && al16(g.dscales) && al16(g.drots) && !getenv("GS_NO_DENSE");
 }
 
+static int ensure_aux(GsContext* ctx) {
+    if (ctx->aux_ready) return GS_OK;
+    int prev = 0;
+    GS_CUDA(cudaGetDevice(&prev));
+    GS_CUDA(cudaSetDevice(ctx->device));
+    // highest priority: the block scheduler hands freed SM resources to the side stream's small CTAs first; at equal
+    // priority they would wait until the tile pass (8 160 CTAs, launched into the caller's stream at the same moment)
+    // has nothing left to dispatch, i.e. run AFTER it (measured: +0.12 ms per step in the eager loop)
+    int pr_least = 0, pr_greatest = 0;
+    GS_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+    GS_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, pr_greatest));
+    GS_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+    GS_CUDA(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
+    GS_CUDA(cudaSetDevice(prev));
+    ctx->aux_ready = true;
+    return GS_OK;
+}
+
 // Optional, before gs_backward_blend: zero-fills the dense gradient outputs on a side stream of the context, BESIDE the
 // tile pass (which is issue bound and leaves the memory system idle).  gs_backward_gradients then waits for the fill and
 // lets the per-Gaussian kernel write the visible rows straight into the outputs -- the streaming writer of the sparse
@@ -432,21 +452,7 @@ int gs_backward_prefill(GsContext* ctx, const GsFrame* f, const void* image_buff
     const GsGradPtrs g = grad_ptrs(f, grads);
     if (!gs_grads_tma_ok(f->shs ? f->M : 0, g)) return GS_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!ctx->aux_ready) {
-        int prev = 0;
-        GS_CUDA(cudaGetDevice(&prev));
-        GS_CUDA(cudaSetDevice(ctx->device));
-        // highest priority: the block scheduler hands freed SM resources to the fill's single-warp CTAs first; at equal
-        // priority they would wait until the tile pass (8 160 CTAs, launched into the caller's stream at the same moment)
-        // has nothing left to dispatch, i.e. run AFTER it (measured: +0.12 ms per step in the eager loop)
-        int pr_least = 0, pr_greatest = 0;
-        GS_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
-        GS_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, pr_greatest));
-        GS_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
-        GS_CUDA(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
-        GS_CUDA(cudaSetDevice(prev));
-        ctx->aux_ready = true;
-    }
+    if ((rc = ensure_aux(ctx))) return rc;
     GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
     GS_CUDA(cudaEventRecord(ctx->aux_fork, s));            // the outputs were allocated in `stream` order before this call
     GS_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->aux_fork, 0));
@@ -511,11 +517,22 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
         // data-parallel shared-model step: the five parameter gradients are reduced straight into every rank's
         // bucket (peer stores / NVSwitch multicast); only dL_dmeans2D is written locally
         if (grads->peer_world > GS_MAX_PEERS || !grads->peer_buckets) return fail(GS_EINVAL, "bad peer arguments");
+        const bool sync = ctx && grads->peer_signals;
+        if (sync && grads->peer_epoch_begin) {
+            // nobody adds into a bucket before every rank has cleared its own: one-warp barrier kernel, normally already
+            // done -- gs_backward put it on the side stream beside the tile pass
+            if (ctx->peer_barrier_pending) GS_CUDA(cudaStreamWaitEvent(s, ctx->aux_join, 0));
+            else gs_launch_peer_barrier((uint32_t* const*)grads->peer_signals, grads->peer_world, grads->peer_rank, 0,
+                                        grads->peer_epoch_begin, s);
+            ctx->peer_barrier_pending = false;
+        }
         GS_TIMED(ctx, 9, s, gs_launch_grad_reduce_peers(f->P, v.M, radii, gl.acc, gout, grads->dL_dmeans2D,
                                                         (float* const*)grads->peer_buckets, grads->peer_world,
-                                                        (float*)grads->peer_multicast, (const long long*)grads->peer_seg_off,
-                                                        (uint32_t* const*)grads->peer_signals, grads->peer_rank,
-                                                        grads->peer_epoch_begin, grads->peer_epoch_end, s));
+                                                        (float*)grads->peer_multicast, (const long long*)grads->peer_seg_off, s));
+        // the step's result is complete on this rank when every rank's adds have landed
+        if (sync && grads->peer_epoch_end)
+            gs_launch_peer_barrier((uint32_t* const*)grads->peer_signals, grads->peer_world, grads->peer_rank, 1,
+                                   grads->peer_epoch_end, s);
         return debug_sync(f, s, "grad_reduce_peers");
     }
     if (!prefilled) {
@@ -543,6 +560,17 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
     if (!grads) return fail(GS_EINVAL, "grads is NULL");
     int rc = ctx ? gs_backward_prefill(ctx, f, image_buffer, grads, stream) : GS_OK;
     if (rc) return rc;
+    if (ctx && grads->peer_world > 0 && grads->peer_signals && grads->peer_epoch_begin) {
+        // shared-model step: the "every bucket is cleared" barrier waits on the side stream while the tile pass runs
+        if ((rc = ensure_aux(ctx))) return rc;
+        cudaStream_t s = (cudaStream_t)stream;
+        GS_CUDA(cudaEventRecord(ctx->aux_fork, s));
+        GS_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->aux_fork, 0));
+        gs_launch_peer_barrier((uint32_t* const*)grads->peer_signals, grads->peer_world, grads->peer_rank, 0,
+                               grads->peer_epoch_begin, ctx->aux);
+        GS_CUDA(cudaEventRecord(ctx->aux_join, ctx->aux));
+        ctx->peer_barrier_pending = true;
+    }
     rc = gs_backward_blend(ctx, f, geom_buffer, binning_buffer, pair_capacity, image_buffer, dL_dout_color, stream);
     if (rc) return rc;
     return gs_backward_gradients(ctx, f, radii, geom_buffer, image_buffer, grad_scratch, grad_scratch_bytes, grads, stream);

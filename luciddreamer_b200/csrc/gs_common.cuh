@@ -338,8 +338,8 @@ void gs_launch_grad_write(int P, int M, const int* radii, const float4* acc, con
                           const GsDevStatus* status, bool dense_elsewhere, cudaStream_t s);
 void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* acc, const float* gout, float* dmeans2D,
                                  float* const* peers, int world, float* mc, const long long* seg_off,
-                                 uint32_t* const* signals, int rank, uint32_t epoch_begin, uint32_t epoch_end,
                                  cudaStream_t s);
+void gs_launch_peer_barrier(uint32_t* const* signals, int world, int rank, int channel, uint32_t epoch, cudaStream_t s);
 void gs_launch_l1_loss_grad(const float* color, const uint8_t* target, int H, int W, float weight, float* dL_dcolor,
                             float* loss, int num_sms, cudaStream_t s);
 void gs_launch_photometric(const float* img, const float* gt, int H, int W, float lambda_dssim, void* scratch,

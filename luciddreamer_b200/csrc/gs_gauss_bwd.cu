@@ -733,12 +733,10 @@ k_grad_dense(const GsView v, const float* __restrict__ means3D, const float* __r
 // 2 x 59 x P all-reduce; rows of invisible Gaussians are never touched.  dL_dmeans2D stays local (it feeds the
 // per-view densification statistic, scene/gaussian_model.py:405-407).
 struct GsPeerArgs {
-    // Cross-rank barriers folded into the kernel (no separate barrier launches): sig[r] = rank r's signal words
-    // (peer-mapped uint32 array): [0, 16) "bucket of rank j is zeroed" epochs, [16, 32) "rank j's adds are done" epochs,
-    // [32] the local block ticket.  epoch_begin / epoch_end = 0: no barrier on that side of this launch.
+    // sig[r] = rank r's signal words (peer-mapped uint32 array): [0, 16) "bucket of rank j is cleared" epochs,
+    // [16, 32) "rank j's adds have landed" epochs (k_peer_barrier)
     uint32_t* sig[GS_MAX_PEERS];
     int rank;
-    uint32_t epoch_begin, epoch_end;
     float* peers[GS_MAX_PEERS];       // bucket base of every rank (peer-mapped), [0, world)
     float* mc;                        // multicast address of the bucket, or nullptr
     int world;
@@ -819,30 +817,17 @@ k_grad_reduce_peers(const int P, const int M, const int* __restrict__ radii, con
         }
     }
     const int nv = s_count;
-    // ---- barrier in: nobody adds into a bucket before every rank has zeroed its own (signalled by its block 0)
-    if (pa.epoch_begin) {
-        if (blockIdx.x == 0 && tid < pa.world) st_release_sys(pa.sig[tid] + pa.rank, pa.epoch_begin);
-        if (nv > 0) {
-            if (tid < pa.world) while ((int)(ld_acquire_sys(pa.sig[pa.rank] + tid) - pa.epoch_begin) < 0) {}
-            __syncthreads();
-        }
-    }
     if (nv > 0) peer_reduce_rows(pa, s_row, s_rowidx, nv, M, row0);
-    // ---- barrier out: the kernel does not end before every rank's adds have landed (last block of each rank signals)
-    if (pa.epoch_end) {
-        if (nv > 0) __threadfence_system();                  // my reductions are performed before the ticket below
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t* mine = pa.sig[pa.rank];
-            const unsigned t = atomicAdd(mine + 32, 1u);
-            if (t == gridDim.x - 1) {
-                mine[32] = 0u;                               // re-armed for the next launch
-                __threadfence_system();
-                for (int r = 0; r < pa.world; r++) st_release_sys(pa.sig[r] + 16 + pa.rank, pa.epoch_end);
-                for (int r = 0; r < pa.world; r++)
-                    while ((int)(ld_acquire_sys(mine + 16 + r) - pa.epoch_end) < 0) {}
-            }
-        }
+}
+
+// Cross-rank barrier of the shared-model step, one warp: tell every rank `epoch` on channel `base` (0: "my bucket is
+// cleared", 16: "my adds have landed" -- stream order puts the reduce kernel in front of it), then wait until every rank
+// has said so.  Signal words are peer-mapped (GsGrads.peer_signals); release / acquire at system scope.
+__global__ void k_peer_barrier(const GsPeerArgs pa, const int base, const uint32_t epoch) {
+    const int tid = threadIdx.x;
+    if (tid < pa.world) {
+        st_release_sys(pa.sig[tid] + base + pa.rank, epoch);
+        while ((int)(ld_acquire_sys(pa.sig[pa.rank] + base + tid) - epoch) < 0) {}
     }
 }
 
@@ -898,20 +883,27 @@ __device__ __forceinline__ void peer_reduce_rows(const GsPeerArgs& pa, const flo
 
 }  // namespace
 
-void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* acc, const float* gout, float* dmeans2D,
-                                 float* const* peers, int world, float* mc, const long long* seg_off,
-                                 uint32_t* const* signals, int rank, uint32_t epoch_begin, uint32_t epoch_end,
-                                 cudaStream_t s) {
+static GsPeerArgs peer_args(float* const* peers, int world, float* mc, const long long* seg_off, uint32_t* const* signals,
+                            int rank) {
     GsPeerArgs pa;
-    for (int r = 0; r < GS_MAX_PEERS; r++) pa.peers[r] = r < world ? peers[r] : nullptr;
+    for (int r = 0; r < GS_MAX_PEERS; r++) pa.peers[r] = (peers && r < world) ? peers[r] : nullptr;
     for (int r = 0; r < GS_MAX_PEERS; r++) pa.sig[r] = (signals && r < world) ? signals[r] : nullptr;
     pa.rank = rank;
-    pa.epoch_begin = signals ? epoch_begin : 0u;
-    pa.epoch_end = signals ? epoch_end : 0u;
     pa.mc = mc; pa.world = world;
-    pa.off_m3 = seg_off[0]; pa.off_sh = seg_off[1]; pa.off_op = seg_off[2]; pa.off_sc = seg_off[3]; pa.off_rot = seg_off[4];
+    pa.off_m3 = pa.off_sh = pa.off_op = pa.off_sc = pa.off_rot = 0;
+    if (seg_off) { pa.off_m3 = seg_off[0]; pa.off_sh = seg_off[1]; pa.off_op = seg_off[2]; pa.off_sc = seg_off[3]; pa.off_rot = seg_off[4]; }
+    return pa;
+}
+void gs_launch_grad_reduce_peers(int P, int M, const int* radii, const float4* acc, const float* gout, float* dmeans2D,
+                                 float* const* peers, int world, float* mc, const long long* seg_off,
+                                 cudaStream_t s) {
+    const GsPeerArgs pa = peer_args(peers, world, mc, seg_off, nullptr, 0);
     const int grid = (P + kT - 1) / kT;
     k_grad_reduce_peers<<<grid, kT, kT * kRow * sizeof(float), s>>>(P, M, radii, acc, gout, dmeans2D, pa);
+}
+void gs_launch_peer_barrier(uint32_t* const* signals, int world, int rank, int channel, uint32_t epoch, cudaStream_t s) {
+    const GsPeerArgs pa = peer_args(nullptr, world, nullptr, nullptr, signals, rank);
+    k_peer_barrier<<<1, 32, 0, s>>>(pa, channel ? 16 : 0, epoch);
 }
 
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
