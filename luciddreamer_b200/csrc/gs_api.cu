@@ -418,14 +418,6 @@ static bool dense_eligible(const GsFrame* f, const GsGrads* grads, const GsGradP
            al16(g.dopacity) && al16(g.dscales) && al16(g.drots) && !getenv("GS_NO_DENSE");
 }
 
-// shared-model step in the reference's own input mode: k_grad_vis adds the rows into the peers' buckets itself
-static bool peers_direct(const GsFrame* f, const GsGrads* grads) {
-    return grads->peer_world > 0 && grads->peer_world <= GS_MAX_PEERS && grads->peer_buckets && grads->peer_seg_off && f->shs &&
-           f->M == 16 && !f->cov3D_precomp && f->scales && f->rotations && grads->dL_dmeans2D && !(f->P & 3) &&
-           !(reinterpret_cast<uintptr_t>(grads->dL_dmeans2D) & 15) && !((grads->peer_seg_off[1] | grads->peer_seg_off[4]) & 3) &&
-           !getenv("GS_NO_PEERS_DIRECT");
-}
-
 static int ensure_aux(GsContext* ctx) {
     if (ctx->aux_ready) return GS_OK;
     int prev = 0;
@@ -516,26 +508,6 @@ int gs_backward_gradients(GsContext* ctx, const GsFrame* f, const int32_t* radii
     // per-Gaussian backward and the compact pair below returns at once; otherwise the other way round.  The dense
     // kernel covers the reference's own input mode (SH degree <= 3 stored as 16 coefficients, scales + rotations).
     const bool dense_ok = dense_eligible(f, grads, g);
-    const bool direct = ctx && ctx->prefilled == (const void*)grads->dL_dmeans2D && peers_direct(f, grads);
-    if (direct) {
-        // the barrier "every bucket is cleared" and the zero-fill of dL_dmeans2D ran on the side stream: join, then the
-        // per-Gaussian kernel adds its rows into every rank's bucket and the closing barrier follows
-        GS_CUDA(cudaStreamWaitEvent(s, ctx->aux_join, 0));
-        ctx->prefilled = nullptr;
-        const bool sync = grads->peer_signals != nullptr;
-        if (sync && grads->peer_epoch_begin && !ctx->peer_barrier_pending)
-            gs_launch_peer_barrier((uint32_t* const*)grads->peer_signals, grads->peer_world, grads->peer_rank, 0,
-                                   grads->peer_epoch_begin, s);
-        ctx->peer_barrier_pending = false;
-        GS_TIMED(ctx, 7, s, gs_launch_grad_vis_peers(v, ctx->num_sms, f->means3D, f->shs, f->scales, f->rotations, gl.rec, gl.acc,
-                                                     gl.vis_list, il.status, grads->dL_dmeans2D,
-                                                     (float* const*)grads->peer_buckets, grads->peer_world,
-                                                     (float*)grads->peer_multicast, (const long long*)grads->peer_seg_off, s));
-        if (sync && grads->peer_epoch_end)
-            gs_launch_peer_barrier((uint32_t* const*)grads->peer_signals, grads->peer_world, grads->peer_rank, 1,
-                                   grads->peer_epoch_end, s);
-        return debug_sync(f, s, "grad_vis_peers");
-    }
     GS_TIMED(ctx, 7, s, gs_launch_grad_vis(v, ctx ? ctx->num_sms : 148, f->means3D, f->shs,
                                            f->cov3D_precomp ? nullptr : f->scales,
                                            f->cov3D_precomp ? nullptr : f->rotations, f->cov3D_precomp, gl.rec, gl.acc,
@@ -598,19 +570,6 @@ int gs_backward(GsContext* ctx, const GsFrame* f, const int32_t* radii, const vo
                                grads->peer_epoch_begin, ctx->aux);
         GS_CUDA(cudaEventRecord(ctx->aux_join, ctx->aux));
         ctx->peer_barrier_pending = true;
-    }
-    if (ctx && peers_direct(f, grads)) {
-        // ... and so does the zero-fill of the one dense output of this mode (dL_dmeans2D stays local)
-        if ((rc = ensure_aux(ctx))) return rc;
-        cudaStream_t s = (cudaStream_t)stream;
-        GsImageLayout il = gs_image_layout(const_cast<void*>(image_buffer), f->W, f->H);
-        if (!ctx->peer_barrier_pending) {
-            GS_CUDA(cudaEventRecord(ctx->aux_fork, s));
-            GS_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->aux_fork, 0));
-        }
-        gs_launch_fill_zero_run(grads->dL_dmeans2D, (long long)f->P * 3, ctx->num_sms, il.status, ctx->aux);
-        GS_CUDA(cudaEventRecord(ctx->aux_join, ctx->aux));
-        ctx->prefilled = grads->dL_dmeans2D;
     }
     rc = gs_backward_blend(ctx, f, geom_buffer, binning_buffer, pair_capacity, image_buffer, dL_dout_color, stream);
     if (rc) return rc;

@@ -327,11 +327,6 @@ void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, cons
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
                         const uint32_t* vis_list, const GsDevStatus* status, float* gout, bool dense_elsewhere,
                         bool scatter, GsGradPtrs g, cudaStream_t s);
-void gs_launch_grad_vis_peers(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
-                              const float* rotations, const float4* rec, float4* acc, const uint32_t* vis_list,
-                              const GsDevStatus* status, float* dmeans2D, float* const* peers, int world, float* mc,
-                              const long long* seg_off, cudaStream_t s);
-void gs_launch_fill_zero_run(float* p, long long floats, int num_sms, const GsDevStatus* status, cudaStream_t s);
 bool gs_grads_tma_ok(int M, const GsGradPtrs& g);
 void gs_launch_fill_zero(int P, int num_sms, const GsGradPtrs& g, const GsDevStatus* status, bool dense_elsewhere,
                          cudaStream_t s);

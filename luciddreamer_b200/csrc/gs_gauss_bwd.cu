@@ -12,7 +12,6 @@
 //                 the caller asks for them).  HBM-bound: ~248 B written + 4 B read per Gaussian; every store is a
 //                 fully coalesced 128-bit (dL_dsh, rotations) or 32-bit row-contiguous store.
 #include <cstdlib>
-#include <cstring>
 
 #include "gs_common.cuh"
 
@@ -26,44 +25,6 @@ constexpr int kRow = GS_GOUT_FLOATS;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tma_store(void* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-
-// Fused "final gradient -> peer reduce" for the shared-model data-parallel step (SURVEY.md 8e): instead of writing
-// a dense local gradient and all-reducing 59 floats x P over NCCL, every rank adds the rows of its VISIBLE
-// Gaussians straight into every rank's (pre-zeroed, symmetric) gradient bucket with red.global.add.f32 over
-// NVLink peer mappings -- or with ONE multimem.red per element through the NVSwitch multicast address when the
-// buckets are bound to a multicast object.  Traffic is 59 floats x P_vis per rank and peer instead of a dense
-// 2 x 59 x P all-reduce; rows of invisible Gaussians are never touched.  dL_dmeans2D stays local (it feeds the
-// per-view densification statistic, scene/gaussian_model.py:405-407).
-struct GsPeerArgs {
-    // sig[r] = rank r's signal words (peer-mapped uint32 array): [0, 16) "bucket of rank j is cleared" epochs,
-    // [16, 32) "rank j's adds have landed" epochs (k_peer_barrier)
-    uint32_t* sig[GS_MAX_PEERS];
-    int rank;
-    float* peers[GS_MAX_PEERS];       // bucket base of every rank (peer-mapped), [0, world)
-    float* mc;                        // multicast address of the bucket, or nullptr
-    int world;
-    long long off_m3, off_sh, off_op, off_sc, off_rot;   // segment offsets inside the bucket, in floats
-};
-
-__device__ __forceinline__ void peer_add(const GsPeerArgs& pa, long long off, float v) {
-    if (v == 0.f) return;
-    if (pa.mc) {
-        asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(pa.mc + off), "f"(v) : "memory");
-    } else {
-        for (int r = 0; r < pa.world; r++) atomicAdd(pa.peers[r] + off, v);
-    }
-}
-// 128-bit variant (off must be a multiple of 4 floats and the buckets 16-byte aligned)
-__device__ __forceinline__ void peer_add4(const GsPeerArgs& pa, long long off, float4 v) {
-    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
-    if (pa.mc) {
-        asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pa.mc + off), "f"(v.x),
-                     "f"(v.y), "f"(v.z), "f"(v.w)
-                     : "memory");
-    } else {
-        for (int r = 0; r < pa.world; r++) atomicAdd(reinterpret_cast<float4*>(pa.peers[r] + off), v);
-    }
 }
 
 constexpr int kVisT = 64;              // small CTAs: P_vis is often only a few 10^4, spread it over all SMs
@@ -269,10 +230,7 @@ k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __res
            const float* __restrict__ scales, const float* __restrict__ rotations,
            const float* __restrict__ cov3D_precomp, const float4* __restrict__ rec, float4* __restrict__ acc,
            const uint32_t* __restrict__ vis_list, const GsDevStatus* __restrict__ status, float* __restrict__ gout,
-           const bool dense_elsewhere, const int mode, const GsGradPtrs g, const GsPeerArgs pa) {
-    // mode 0: compact 44-float rows into gout (k_grad_write / k_grad_reduce_peers expand them); 1: final rows straight into
-    // the zero-filled dense outputs; 2: shared-model step -- the five parameter gradients are ADDED straight into every
-    // rank's bucket (multimem.red / peer atomics), dL_dmeans2D into the zero-filled local tensor
+           const bool dense_elsewhere, const bool scatter, const GsGradPtrs g) {
     if (dense_elsewhere && gs_dense_regime(status, v.P)) return;
     __shared__ GsCam cam;
     gs_load_cam(v, &cam);
@@ -290,32 +248,9 @@ k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __res
 #pragma unroll
             for (int k = 0; k < 48; k++) cf[k] = k < na3 ? __ldg(sh + k) : 0.f;
         };
-        if (mode == 0) {
+        if (!scatter) {
             grad_row(v, cam, i, a0, a1, a2, clamped, means3D, shs != nullptr, scales, rotations, cov3D_precomp, fill,
                      reinterpret_cast<float4*>(gout + (size_t)c * kRow));
-            continue;
-        }
-        if (mode == 2) {
-            float4 o[11];
-            grad_row(v, cam, i, a0, a1, a2, clamped, means3D, true, scales, rotations, cov3D_precomp, fill, o);
-            g.dmeans2D[3 * i] = o[0].w; g.dmeans2D[3 * i + 1] = o[1].x;
-            const long long gi = (long long)i;
-            peer_add(pa, pa.off_m3 + gi * 3, o[0].x); peer_add(pa, pa.off_m3 + gi * 3 + 1, o[0].y);
-            peer_add(pa, pa.off_m3 + gi * 3 + 2, o[0].z);
-            peer_add(pa, pa.off_op + gi, o[1].y);
-            peer_add(pa, pa.off_sc + gi * 3, o[1].z); peer_add(pa, pa.off_sc + gi * 3 + 1, o[1].w);
-            peer_add(pa, pa.off_sc + gi * 3 + 2, o[2].x);
-            peer_add4(pa, pa.off_rot + gi * 4, make_float4(o[2].y, o[2].z, o[2].w, o[3].x));
-            const float bs[16] = {o[4].x, o[4].y, o[4].z, o[4].w, o[5].x, o[5].y, o[5].z, o[5].w,
-                                  o[6].x, o[6].y, o[6].z, o[6].w, o[7].x, o[7].y, o[7].z, o[7].w};
-            const float dR[3] = {o[3].y, o[3].z, o[3].w};
-#pragma unroll
-            for (int j = 0; j < 12; j++) {
-                float w[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) { const int e = 4 * j + u; w[u] = bs[e / 3] * dR[e % 3]; }
-                peer_add4(pa, pa.off_sh + gi * 48 + 4 * j, make_float4(w[0], w[1], w[2], w[3]));
-            }
             continue;
         }
         // the dense outputs were zero-filled beside the tile pass (k_fill_zero): the final rows go straight into them
@@ -790,6 +725,44 @@ k_grad_dense(const GsView v, const float* __restrict__ means3D, const float* __r
     }
 }
 
+// Fused "final gradient -> peer reduce" for the shared-model data-parallel step (SURVEY.md 8e): instead of writing
+// a dense local gradient and all-reducing 59 floats x P over NCCL, every rank adds the rows of its VISIBLE
+// Gaussians straight into every rank's (pre-zeroed, symmetric) gradient bucket with red.global.add.f32 over
+// NVLink peer mappings -- or with ONE multimem.red per element through the NVSwitch multicast address when the
+// buckets are bound to a multicast object.  Traffic is 59 floats x P_vis per rank and peer instead of a dense
+// 2 x 59 x P all-reduce; rows of invisible Gaussians are never touched.  dL_dmeans2D stays local (it feeds the
+// per-view densification statistic, scene/gaussian_model.py:405-407).
+struct GsPeerArgs {
+    // sig[r] = rank r's signal words (peer-mapped uint32 array): [0, 16) "bucket of rank j is cleared" epochs,
+    // [16, 32) "rank j's adds have landed" epochs (k_peer_barrier)
+    uint32_t* sig[GS_MAX_PEERS];
+    int rank;
+    float* peers[GS_MAX_PEERS];       // bucket base of every rank (peer-mapped), [0, world)
+    float* mc;                        // multicast address of the bucket, or nullptr
+    int world;
+    long long off_m3, off_sh, off_op, off_sc, off_rot;   // segment offsets inside the bucket, in floats
+};
+
+__device__ __forceinline__ void peer_add(const GsPeerArgs& pa, long long off, float v) {
+    if (v == 0.f) return;
+    if (pa.mc) {
+        asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(pa.mc + off), "f"(v) : "memory");
+    } else {
+        for (int r = 0; r < pa.world; r++) atomicAdd(pa.peers[r] + off, v);
+    }
+}
+// 128-bit variant (off must be a multiple of 4 floats and the buckets 16-byte aligned)
+__device__ __forceinline__ void peer_add4(const GsPeerArgs& pa, long long off, float4 v) {
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
+    if (pa.mc) {
+        asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pa.mc + off), "f"(v.x),
+                     "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    } else {
+        for (int r = 0; r < pa.world; r++) atomicAdd(reinterpret_cast<float4*>(pa.peers[r] + off), v);
+    }
+}
+
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -933,38 +906,14 @@ void gs_launch_peer_barrier(uint32_t* const* signals, int world, int rank, int c
     k_peer_barrier<<<1, 32, 0, s>>>(pa, channel ? 16 : 0, epoch);
 }
 
-static GsPeerArgs peer_args(float* const* peers, int world, float* mc, const long long* seg_off, uint32_t* const* signals,
-                            int rank);
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
                         const uint32_t* vis_list, const GsDevStatus* status, float* gout, bool dense_elsewhere,
                         bool scatter, GsGradPtrs g, cudaStream_t s) {
     const int need = (v.P + kVisT - 1) / kVisT;
     const int grid = need < num_sms * 8 ? need : num_sms * 8;
-    GsPeerArgs pa;
-    memset(&pa, 0, sizeof(pa));
     k_grad_vis<<<grid, kVisT, 0, s>>>(v, means3D, shs, scales, rotations, cov3D_precomp, rec, acc, vis_list, status, gout,
-                                      dense_elsewhere, scatter ? 1 : 0, g, pa);
-}
-// shared-model step, common input mode: the per-Gaussian kernel adds the rows into every rank's bucket itself
-void gs_launch_grad_vis_peers(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
-                              const float* rotations, const float4* rec, float4* acc, const uint32_t* vis_list,
-                              const GsDevStatus* status, float* dmeans2D, float* const* peers, int world, float* mc,
-                              const long long* seg_off, cudaStream_t s) {
-    const int need = (v.P + kVisT - 1) / kVisT;
-    const int grid = need < num_sms * 8 ? need : num_sms * 8;
-    const GsPeerArgs pa = peer_args(peers, world, mc, seg_off, nullptr, 0);
-    GsGradPtrs g;
-    memset(&g, 0, sizeof(g));
-    g.dmeans2D = dmeans2D;
-    k_grad_vis<<<grid, kVisT, 0, s>>>(v, means3D, shs, scales, rotations, nullptr, rec, acc, vis_list, status, nullptr, false, 2,
-                                      g, pa);
-}
-void gs_launch_fill_zero_run(float* p, long long floats, int num_sms, const GsDevStatus* status, cudaStream_t s) {
-    FillRuns r;
-    for (int k = 0; k < 6; k++) { r.p[k] = nullptr; r.bytes[k] = 0; }
-    r.p[0] = (char*)p; r.bytes[0] = floats * 4;
-    k_fill_zero<<<num_sms, 32, 0, s>>>(r, status, 0, false);
+                                      dense_elsewhere, scatter, g);
 }
 // true when the outputs qualify for the TMA paths (k_grad_write_tma / k_fill_zero + scatter): the reference's own input
 // mode (16 stored SH coefficients, scales + rotations), all six tensors wanted, 16-byte aligned
