@@ -662,19 +662,25 @@ def shared_model_leg(scene, cam, cot, dev, D, steps, warmup, world):
     out = {"nccl_allreduce": {"ms_per_step": ms_nccl, "value": world * rays / ms_nccl / 1e3, "unit": "Mrays/s",
                               "bytes_reduced_per_rank": dense.nbytes()}}
     try:
-        symm = MV.SymmGradBucket(P, M, dev)
+        best = None
+        for key, mc in (("fused_peer_reduce", True), ("fused_peer_stores", False)):
+            symm = MV.SymmGradBucket(P, M, dev, use_multicast=mc)
+            if not mc or symm.peers["mc"]:
+                def step_fused():
+                    symm.begin_step()
+                    MV.view_step(params, rs, cot, bucket=symm, means2D_grad=dm2)
+                    symm.end_step()
 
-        def step_fused():
-            symm.begin_step()
-            MV.view_step(params, rs, cot, bucket=symm, means2D_grad=dm2)
-            symm.end_step()
-
-        ms_f = timed(step_fused)
-        torch.cuda.synchronize()
-        err = float(((symm.flat - dense.flat).norm() / dense.flat.norm().clamp_min(1e-30)).item())
-        out["fused_peer_reduce"] = {"ms_per_step": ms_f, "value": world * rays / ms_f / 1e3, "unit": "Mrays/s",
-                                    "multicast": bool(symm.peers["mc"]), "rel_err_vs_nccl": err}
-        out["ms_per_step"], out["value"], out["unit"] = ms_f, world * rays / ms_f / 1e3, "Mrays/s"
+                ms_f = timed(step_fused)
+                torch.cuda.synchronize()
+                err = float(((symm.flat - dense.flat).norm() / dense.flat.norm().clamp_min(1e-30)).item())
+                out[key] = {"ms_per_step": ms_f, "value": world * rays / ms_f / 1e3, "unit": "Mrays/s",
+                            "multicast": bool(symm.peers["mc"]), "rel_err_vs_nccl": err}
+                if best is None or ms_f < best:
+                    best = ms_f
+            del symm
+            torch.cuda.empty_cache()
+        out["ms_per_step"], out["value"], out["unit"] = best, world * rays / best / 1e3, "Mrays/s"
     except Exception as ex:                     # symmetric memory unavailable: the NCCL leg is the result
         out["fused_peer_reduce"] = {"unavailable": str(ex)[:200]}
         out["ms_per_step"], out["value"], out["unit"] = ms_nccl, world * rays / ms_nccl / 1e3, "Mrays/s"
