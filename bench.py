@@ -123,9 +123,12 @@ def alg_bytes(P, Pv, pairs, N, G, M):
         "k_tile_sort_big": 0,
         "k_blend_fwd": 4 * pairs + 48 * Pv + 24 * N,
         "k_blend_bwd": 20 * N + 4 * pairs + 48 * Pv + 72 * Pv,
-        "k_grad_vis": 0 if dense else Pv * (4 + 96 + 16 + 12 + 12 + 16 + 12 * M + 176),
-        "k_grad_write": 0 if dense else 4 * P + (12 + 12 + 12 * M + 4 + 12 + 16) * P + Pv * (16 + 176),
+        "k_grad_vis": 0 if dense else Pv * (4 + 96 + 16 + 12 + 12 + 16 + 12 * M + 12 + 12 + 12 * M + 4 + 12 + 16),
+        "k_grad_write": 0,                               # replaced by k_fill_zero + the scatter of k_grad_vis (sparse regime)
         "k_grad_dense": (4 * P + Pv * (96 + 4 + 12 + 12 + 16 + 12 * M) + (12 + 12 + 12 * M + 4 + 12 + 16) * P) if dense else 0,
+        # zero-fill of the dense gradient tensors beside the tile pass (gs_backward_prefill); its time is measured while
+        # k_blend_bwd runs next to it
+        "k_fill_zero": 0 if dense else (12 + 12 + 12 * M + 4 + 12 + 16) * P,
     }
 
 

@@ -295,7 +295,7 @@ int gs_debug_export_binning(const GsFrame* f, const void* binning_buffer, int64_
  * SURVEY.md section 5).  When enabled, every kernel launch is bracketed by CUDA events on the launching stream;
  * gs_profile_read waits for them and returns the duration in ms of each kernel of the most recent forward /
  * backward (-1 = not launched).  Kernel i is named gs_profile_kernel_name(i), i < gs_profile_num_kernels(). */
-#define GS_NUM_KERNELS 11
+#define GS_NUM_KERNELS 12
 int gs_profile_enable(GsContext* ctx, int on);
 int gs_profile_num_kernels(void);
 const char* gs_profile_kernel_name(int i);

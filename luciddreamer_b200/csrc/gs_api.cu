@@ -95,7 +95,7 @@ constexpr int kNumKernels = GS_NUM_KERNELS;
 static const char* const kKernelNames[kNumKernels] = {"k_project", "k_tile_scan", "k_shade_emit", "k_tile_sort",
                                                       "k_tile_sort_big", "k_blend_fwd", "k_blend_bwd", "k_grad_vis",
                                                       "k_count_tiles", "k_grad_write",   // slot 9 also times
-                                                      "k_grad_dense"};                   // k_grad_reduce_peers
+                                                      "k_grad_dense", "k_fill_zero"};    // k_grad_reduce_peers
 
 struct GsContext {
     int device;
@@ -457,7 +457,7 @@ int gs_backward_prefill(GsContext* ctx, const GsFrame* f, const void* image_buff
     GS_CUDA(cudaEventRecord(ctx->aux_fork, s));            // the outputs were allocated in `stream` order before this call
     GS_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->aux_fork, 0));
     // in the dense regime k_grad_dense writes every row itself: the fill exits on the device (only if that kernel will run)
-    gs_launch_fill_zero(f->P, ctx->num_sms, g, il.status, dense_eligible(f, grads, g), ctx->aux);
+    GS_TIMED(ctx, 11, ctx->aux, gs_launch_fill_zero(f->P, ctx->num_sms, g, il.status, dense_eligible(f, grads, g), ctx->aux));
     GS_CUDA(cudaEventRecord(ctx->aux_join, ctx->aux));
     ctx->prefilled = grads->dL_dsh;
     return GS_OK;

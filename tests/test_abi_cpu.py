@@ -47,7 +47,7 @@ def test_errors_are_codes_not_crashes():
     f.P, f.W, f.H = -1, 4, 4
     assert L.gs_forward_render(None, C.byref(f), None, None, None, 0, None, None, None, 0, None) == -1
     assert L.gs_mark_visible(-1, None, None, None, None, None) == -1
-    assert L.gs_profile_num_kernels() == 11
+    assert L.gs_profile_num_kernels() == 12
 
 
 def test_reference_message_for_missing_inputs():

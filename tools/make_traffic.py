@@ -39,7 +39,7 @@ def main():
     tj[scene] = {k: sum(v) / len(v) for k, v in traffic.items()}
     tj[scene + "_warp_inst"] = {k: sum(v) / len(v) for k, v in inst.items()}
     tj["sources_sha"] = sources_sha()
-    tj["source"] = f"{os.path.basename(rep)} (ncu --set full --clock-control none --import-source on; per launch, mean over the launches captured)"
+    tj["source_" + scene] = f"{os.path.basename(rep)} (ncu --set full --clock-control none --import-source on; per launch, mean over the launches captured)"
     json.dump(tj, open(path, "w"), indent=1)
     print(json.dumps(tj, indent=1))
 
