@@ -571,6 +571,34 @@ SHAPED = [
 ]
 
 
+def graphed_steps(impl, cam, cot, ncams, seed, steps, warmup):
+    """forward+backward of `impl` captured once (static pair capacity, camera read from a device buffer) and replayed; with
+    ncams > 0 a jittered training camera is copied into that buffer before every replay (device-to-device, 35 floats)."""
+    from luciddreamer_b200.graphs import GraphedStep
+    dev = impl.dev
+    cams = [cam] + ([syn.make_camera(cam.image_width, cam.image_height, c2w=m) for m in syn.jitter_poses(ncams, seed)] if ncams else [])
+    table = torch.stack([torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.campos.reshape(-1)]) for c in cams]).to(dev)
+    d_cam = table[0].clone()
+    impl.rasts = None
+    impl.bind_camera(d_cam)
+    g = GraphedStep(lambda: impl.step(cot), warmup=2, headroom=2.5)
+    order = np.random.RandomState(99).randint(0, len(cams), size=warmup + steps)
+
+    def run(k0, n):
+        for k in range(k0, k0 + n):
+            if ncams:
+                d_cam.copy_(table[order[k]], non_blocking=True)
+            g.replay()
+    run(0, warmup)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(warmup, steps)
+    e1.record(); torch.cuda.synchronize()
+    g.check()
+    return e0.elapsed_time(e1) / steps
+
+
 def shaped_legs(impl_cls, dev, D=3, steps=10, warmup=3, only=None):
     """`next` rows of the measurement: forward+backward on the reference's real workload shape and on
     BASELINE config 2, same protocol as the headline (CUDA events, parameters resident in HBM).  The product arm and the
@@ -594,6 +622,11 @@ def shaped_legs(impl_cls, dev, D=3, steps=10, warmup=3, only=None):
                          "P_vis": st["P_vis"], "pairs": st["pairs"], "random_cameras": s["cams"], "steps": steps}
             if hasattr(impl, "profile"):
                 out[name]["kernels_ms"] = impl.profile(cot, n=3)
+                try:                                 # the same step as ONE CUDA graph (graphs.GraphedStep), camera rewritten per step
+                    out[name]["graph_ms_per_step"] = graphed_steps(impl, cam, cot, s["cams"], s["seed"], steps, warmup)
+                    out[name]["graph_value"] = W * H / out[name]["graph_ms_per_step"] / 1e3
+                except Exception as ex:
+                    out[name]["graph_error"] = str(ex)[:200]
             del impl, scene, cot
             torch.cuda.empty_cache()
         except Exception as ex:                      # a `next` row must never take the headline line down

@@ -285,15 +285,21 @@ def test_capacity_growth_and_many_views_in_flight():
 
 
 @pytest.mark.skipif(not __import__("oracle.ref_cuda", fromlist=["x"]).available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("scale_mult", [1.0, 4.0])
+@pytest.mark.parametrize("scale_mult", [1.0, 4.0, "frustum", "frustum_shuffled"])
 def test_full_size_against_live_reference(scale_mult):
-    """BASELINE config 3 (1 M Gaussians, 1080p, SH 3) against the reference CUDA library on the same GPU."""
+    """BASELINE config 3 (1 M Gaussians, 1080p, SH 3; normal and x4 scales) and the LucidDreamer-shaped scene (1 M Gaussians
+    all inside the frustum at 512x512: dense regime, strip geometry, long tile lists; raster and random memory order)
+    against the reference CUDA library on the same GPU."""
     from luciddreamer_b200 import synthetic as syn
     from luciddreamer_b200.rasterizer import _C
     from oracle import ref_cuda
     d = dev()
     P, W, H, D = 1_000_000, 1920, 1080, 3
-    sc = {k: v.to(d) for k, v in syn.make_scene(P, 1003, scale_mult=scale_mult).items()}
+    if isinstance(scale_mult, str):
+        W, H = 512, 512
+        sc = {k: v.to(d) for k, v in syn.make_frustum_scene(P, 2001, W, H, raster=(scale_mult == "frustum")).items()}
+    else:
+        sc = {k: v.to(d) for k, v in syn.make_scene(P, 1003, scale_mult=scale_mult).items()}
     cam = syn.make_camera(W, H)
     cot = syn.make_cotangent(H, W, 1003).to(d)
     bg = torch.zeros(3, device=d)
@@ -313,8 +319,11 @@ def test_full_size_against_live_reference(scale_mult):
     torch.cuda.synchronize()
     assert nr == R
     gold = dict(color=rcol.cpu().numpy(), depth=rdep.cpu().numpy(), radii=rrad.cpu().numpy())
-    info = util.assert_forward_close(color.cpu().numpy(), depth.cpu().numpy(), radii.cpu().numpy(), gold, what="config 3")
-    print("config-3 forward parity:", info)
+    # dense scene: every pixel sits behind ~50 thin splats and terminates; 4x the (pixel, splat) decisions per pixel of
+    # config 3, so 4x the allowance for isolated branch flips (1 pixel in 5 000)
+    info = util.assert_forward_close(color.cpu().numpy(), depth.cpu().numpy(), radii.cpu().numpy(), gold, what=f"config 3 / {scale_mult}",
+                                     flip_div=5000 if isinstance(scale_mult, str) else 20000)
+    print(f"forward parity at full size ({scale_mult}):", info)
     mine = dict(zip(cases.GRAD_NAMES, [t.cpu().numpy() for t in g]))
     ref = dict(zip(cases.GRAD_NAMES, [t.cpu().numpy() for t in rg[:8]]))
     errs = util.assert_grads_close(mine, ref, names={"dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dscales",
