@@ -603,8 +603,7 @@ k_blend_bwd(const GsView v, const uint32_t* __restrict__ tile_off, const uint32_
 
 }  // namespace
 
-int g_gs_blend_variant = 0;           // GS_BLEND_VARIANT=1 selects the round-1 kernels (A/B measurements only);
-                                      // 2 / 3 force the 16x8 / 16x4 warp geometry of the current ones
+int g_gs_blend_variant = 0;           // GS_BLEND_VARIANT=2 / 3 force the 16x8 / 16x4 warp geometry (A/B measurements)
 int g_gs_num_sms = 148;
 
 // 16x4 strips (4 warps per tile) when 16x8 blocks would leave the SMs with fewer than ~20 resident warps
@@ -617,7 +616,6 @@ static bool use_strips(const GsView& v) {
 void gs_launch_blend_fwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const GsDevStatus* status, long long capacity, float* final_T, uint32_t* n_contrib,
                          float* out_color, float* out_depth, cudaStream_t s) {
-    if (g_gs_blend_variant == 1) { gs_launch_blend_fwd_r1(v, tile_off, list, rec, status, capacity, final_T, n_contrib, out_color, out_depth, s); return; }
     dim3 grid(v.gx, v.gy);
     // CTAs per SM the register allocation aims at: 14 (72 registers, 28 warps per SM) measured 3 % faster than 12 (80
     // registers) on config 3; GS_BLEND_OCC_FWD=12 keeps the other build for A/B runs
@@ -632,7 +630,6 @@ void gs_launch_blend_fwd(const GsView& v, const uint32_t* tile_off, const uint32
 void gs_launch_blend_bwd(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
                          const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float4* acc,
                          const GsDevStatus* status, long long capacity, cudaStream_t s) {
-    if (g_gs_blend_variant == 1) { gs_launch_blend_bwd_r1(v, tile_off, list, rec, final_T, n_contrib, dL_dpix, acc, s); return; }
     dim3 grid(v.gx, v.gy);
     // 13 CTAs per SM (72 registers, no spills; shared memory then limits at 13): 3 % faster than 10 (87 registers)
     static const int occ = getenv("GS_BLEND_OCC_BWD") ? atoi(getenv("GS_BLEND_OCC_BWD")) : 13;

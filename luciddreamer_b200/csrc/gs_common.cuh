@@ -317,12 +317,6 @@ void gs_launch_blend_bwd(const GsView& v, const uint32_t* tile_off, const uint32
                          const GsDevStatus* status, long long capacity, cudaStream_t s);
 extern int g_gs_blend_variant;
 extern int g_gs_num_sms;
-void gs_launch_blend_fwd_r1(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
-                            const GsDevStatus* status, long long capacity, float* final_T, uint32_t* n_contrib,
-                            float* out_color, float* out_depth, cudaStream_t s);
-void gs_launch_blend_bwd_r1(const GsView& v, const uint32_t* tile_off, const uint32_t* list, const float4* rec,
-                            const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, float4* acc,
-                            cudaStream_t s);
 void gs_launch_grad_vis(const GsView& v, int num_sms, const float* means3D, const float* shs, const float* scales,
                         const float* rotations, const float* cov3D_precomp, const float4* rec, float4* acc,
                         const uint32_t* vis_list, const GsDevStatus* status, float* gout, bool dense_elsewhere,

@@ -12,7 +12,7 @@ def sources_sha():
     h = hashlib.sha256()
     d = os.path.join(ROOT, "luciddreamer_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")) and not f.startswith("gs_blend_r1"):
+        if f.endswith((".cu", ".cuh")):
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "luciddreamer_b200", "csrc")
 WATCH = ["FFMA2", "FMUL2", "FADD2", "FFMA", "FMUL", "FADD", "MUFU.EX2", "MUFU.RCP", "FSEL", "FSETP", "FMNMX3", "FMNMX", "SEL",
          "SHFL", "VOTE", "MATCH", "LDS", "STS", "LDG", "STG", "RED", "ATOM", "UBLKCP", "SYNCS", "BAR", "FCHK", "CALL"]
-for obj in sorted(f for f in os.listdir(CSRC) if f.endswith(".o") and not f.startswith("gs_blend_r1")):
+for obj in sorted(f for f in os.listdir(CSRC) if f.endswith(".o")):
     out = subprocess.run(["cuobjdump", "-sass", os.path.join(CSRC, obj)], capture_output=True, text=True).stdout
     fn, counts = None, collections.OrderedDict()
     for line in out.splitlines():
