@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 evidence session (1 GPU): GPU test suite, sanitizers, launch lists (ours + reference), ncu --set full of one
+# Evidence session (1 GPU), the source of profiles/r02_*: GPU test suite, sanitizers, launch lists (ours + reference), ncu --set full of one
 # config-3 step and one LucidDreamer-shaped step, the default bench line and the reference arm.
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
