@@ -5,8 +5,11 @@ One `vertex` element of float32 properties in this order (construct_list_of_attr
     x y z | nx ny nz (zeros) | f_dc_0..2 | f_rest_0..(3*(M-1)-1) | opacity | scale_0..2 | rot_0..3
 with the SH features stored CHANNEL-major (features.transpose(1, 2).flatten(1): f_rest_k = rest[:, k % (M-1), k // (M-1)]).
 All values are the RAW parameters (logit opacity, log scale, un-normalised quaternion).  The reference goes through the
-`plyfile` package (not in this image); the file layout it produces for such an element is the plain PLY one restated
-here: an ASCII header, then P packed little-endian records -- read and written with one numpy structured-array call."""
+`plyfile` package (plyfile==0.8.1, not in this image); the file layout it produces for such an element is the plain PLY
+one restated here: an ASCII header, then P packed little-endian records -- read and written with one numpy
+structured-array call.  Pinned by tests/golden/ref_save_ply_*.ply + ply_golden.npz: files written and read back by the
+reference's own save_ply / load_ply (executed from /root/reference over a restated plyfile container writer,
+tests/golden/make_ply_golden.py); save_ply here must reproduce those bytes, load_ply those tensors."""
 from __future__ import annotations
 
 from typing import Dict

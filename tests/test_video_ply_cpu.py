@@ -44,6 +44,26 @@ def test_ply_header_and_record_layout(tmp_path):
     np.testing.assert_array_equal(rec[:, 58:62], m["rotation"].numpy())
 
 
+@pytest.mark.parametrize("tag,deg", [("d3", 3), ("d1", 1)])
+def test_ply_bytes_match_the_reference_writer_and_reader(tmp_path, tag, deg):
+    """Fixtures made by running the reference's own save_ply / load_ply (tests/golden/make_ply_golden.py): our writer
+    produces the same BYTES for the same model, our reader returns what the reference's reader returned for that file."""
+    g = np.load(os.path.join(HERE, "golden", "ply_golden.npz"))
+    ref_file = os.path.join(HERE, "golden", f"ref_save_ply_{tag}.ply")
+    key = dict(xyz="_xyz", features_dc="_features_dc", features_rest="_features_rest", opacity="_opacity",
+               scaling="_scaling", rotation="_rotation")
+    m = {k: torch.from_numpy(g[f"{tag}_in{v}"]) for k, v in key.items()}
+    path = str(tmp_path / "ours.ply")
+    ply.save_ply(path, **m)
+    assert open(path, "rb").read() == open(ref_file, "rb").read()
+    back = ply.load_ply(ref_file, max_sh_degree=deg, device="cpu")
+    assert int(g[f"{tag}_active_sh_degree"]) == deg
+    for k, v in key.items():
+        want = g[f"{tag}_loaded{v}"]
+        assert tuple(back[k].shape) == want.shape and back[k].dtype == torch.float32
+        np.testing.assert_array_equal(back[k].numpy(), want)
+
+
 @pytest.mark.parametrize("P", [0, 1, 1000])
 def test_ply_round_trip(tmp_path, P):
     m = _model(P, seed=P)
