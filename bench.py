@@ -116,8 +116,8 @@ def alg_bytes(P, Pv, pairs, N, G, M):
     dense = 2 * Pv > P                    # the device picks k_grad_dense over (k_grad_vis, k_grad_write) on this test
     return {
         "k_project": 12 * P + 4 * P + Pv * (12 + 16 + 4 + 32 + 4),
-        "k_count_tiles": Pv * (4 + 32 + 4) + 4 * pairs,
-        "k_tile_scan": 12 * G,
+        "k_count_tiles": Pv * (4 + 32 + 4) + 4 * pairs + 12 * G,   # + the scan of the G tile counts by its last CTA
+        "k_tile_scan": 0,                                # a launch of its own only for empty models / GS_SCAN_KERNEL=1
         "k_shade_emit": Pv * (4 + 32 + 12 + 12 * M + 4 + 32 + 48) + 12 * pairs,
         "k_tile_sort": 8 * pairs + 4 * pairs,
         "k_tile_sort_big": 0,
@@ -171,11 +171,11 @@ class Ours:
         self.settings = R.GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
                                                         self.bg, 1.0, self.vm, self.pm, D, self.cp, False, False)
         self.rast = R.GaussianRasterizer(self.settings)
-        # k_project, k_count_tiles, k_tile_scan, k_shade_emit, k_tile_sort, k_tile_sort_mid, k_tile_sort_big, k_blend_fwd,
-        # k_blend_bwd, k_grad_vis, k_grad_write (profiles/r01_launches_ours.csv) -- our kernels only, no torch kernels
-        # k_clear_words, k_project, k_count_tiles, k_tile_scan, k_shade_emit, k_tile_sort, k_tile_sort_mid, k_tile_sort_big,
-        # k_blend_fwd | k_blend_bwd, k_grad_vis, k_grad_write (+ k_grad_dense unless the host can prove the sparse regime)
-        self.kernels_per_step = 12
+        # our kernels only, no torch kernels (profiles/r02_launches_ours.csv + the fold of the tile scan):
+        # k_clear_words, k_project, k_count_tiles (its last CTA scans the tile histogram), k_shade_emit, k_tile_sort,
+        # k_tile_sort_mid, k_tile_sort_big, k_blend_fwd, k_fill_zero (side stream) | k_blend_bwd, k_grad_vis
+        # (+ k_grad_dense unless the host can prove the sparse regime)
+        self.kernels_per_step = 11
         self.last = None
         self.rasts, self.order, self.k = None, None, 0
 

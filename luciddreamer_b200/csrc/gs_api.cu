@@ -253,18 +253,25 @@ int gs_forward_preprocess(GsContext* ctx, const GsFrame* f, void* geom_buffer, v
     host_slot->overflow = 0;                             // cleared; kernel writes 0xC0FFEE when done
     // zero tile histogram + status in one memset (they are adjacent)
     gs_launch_clear_words(il.tile_cnt, ((size_t)((char*)il.status - (char*)il.tile_cnt) + sizeof(GsDevStatus)) / 4, s);
+    GsDevStatus* dev_slot = nullptr;
+    GS_CUDA(cudaHostGetDevicePointer((void**)&dev_slot, host_slot, 0));
+    bool scanned = false;
     if (f->P > 0) {
         GsGeomLayout gl = gs_geom_layout(geom_buffer, f->P);
         GS_TIMED(ctx, 0, s, gs_launch_project(v, f->means3D, f->opacities, f->scales, f->rotations, f->cov3D_precomp,
-                                              radii, gl.rec, gl.vis_list, il.status, s));
+                                              radii, gl.rec, gl.vis_list, il.status,
+                                              2 * ctx->last_visible.load() > (long long)f->P, s));
         if ((rc = debug_sync(f, s, "project"))) return rc;
-        GS_TIMED(ctx, 8, s, gs_launch_count_tiles(v, ctx->num_sms, radii, gl.rec, gl.vis_list, gl.hitmask, il.tile_cnt, il.status, s));
+        // the tile histogram; its last CTA also scans it and mirrors the totals to the host slot
+        GS_TIMED(ctx, 8, s, gs_launch_count_tiles(v, ctx->num_sms, radii, gl.rec, gl.vis_list, gl.hitmask, il.tile_cnt, il.status,
+                                                  il.tile_off, dev_slot, s));
         if ((rc = debug_sync(f, s, "count_tiles"))) return rc;
+        scanned = gs_scan_folded();
     }
-    GsDevStatus* dev_slot = nullptr;
-    GS_CUDA(cudaHostGetDevicePointer((void**)&dev_slot, host_slot, 0));
-    GS_TIMED(ctx, 1, s, gs_launch_tile_scan(G, il.tile_cnt, il.tile_off, il.status, dev_slot, s));
-    if ((rc = debug_sync(f, s, "tile_scan"))) return rc;
+    if (!scanned) {
+        GS_TIMED(ctx, 1, s, gs_launch_tile_scan(G, il.tile_cnt, il.tile_off, il.status, dev_slot, s));
+        if ((rc = debug_sync(f, s, "tile_scan"))) return rc;
+    }
     if (!capturing) GS_CUDA(cudaEventRecord(ctx->events[slot], s));
     return GS_OK;
 }

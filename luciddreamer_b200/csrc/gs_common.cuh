@@ -27,7 +27,7 @@ struct GsDevStatus {         // lives at the end of the image buffer
     unsigned int overflow;             // set by k_emit when num_pairs > capacity at render time
     unsigned int n_big;                // tiles queued for k_tile_sort_big
     unsigned int n_mid;                // tiles queued for k_tile_sort_mid
-    unsigned int pad;
+    unsigned int pad;                  // ticket counter of k_count_tiles (last CTA out scans the histogram)
 };
 
 struct GsImageLayout {
@@ -294,9 +294,11 @@ struct GsGradPtrs {
 };
 void gs_launch_project(const GsView& v, const float* means3D, const float* opacities, const float* scales,
                        const float* rotations, const float* cov3D_precomp, int* radii, float4* rec,
-                       uint32_t* vis_list, GsDevStatus* status, cudaStream_t s);
+                       uint32_t* vis_list, GsDevStatus* status, bool dense_hint, cudaStream_t s);
+bool gs_scan_folded();   // true: the last CTA of k_count_tiles scans the tile histogram, no k_tile_scan launch follows
 void gs_launch_count_tiles(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
-                           uint32_t* hitmask, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s);
+                           uint32_t* hitmask, uint32_t* tile_cnt, GsDevStatus* status, uint32_t* tile_off,
+                           GsDevStatus* host_slot, cudaStream_t s);
 void gs_preprocess_init();
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status,
                          GsDevStatus* host_slot, cudaStream_t s);

@@ -243,10 +243,22 @@ k_grad_vis(const GsView v, const float* __restrict__ means3D, const float* __res
         aa[0] = z4; aa[1] = z4; aa[2] = make_float4(0.f, a2.y, 0.f, a2.w);  // re-arm; keep the clamp bits + compact slot
         const uint32_t clamped = __float_as_uint(a2.y);
         const float* sh = shs ? shs + (size_t)i * v.M * 3 : nullptr;
-        // scalar loads: rows need not be 16-byte aligned
+        // 128-bit loads when the rows are 16-byte aligned (M * 3 a multiple of 4, base aligned like every input --
+        // gsraster.h; k_shade_emit reads them the same way), scalar loads otherwise
+        const bool sh_v4 = (v.M * 3) % 4 == 0;
         auto fill = [&](float* cf, int na3) {
+            if (sh_v4) {
+                const float4* s4 = reinterpret_cast<const float4*>(sh);
 #pragma unroll
-            for (int k = 0; k < 48; k++) cf[k] = k < na3 ? __ldg(sh + k) : 0.f;
+                for (int k = 0; k < 12; k++) {
+                    const float4 t = 4 * k < na3 ? __ldg(s4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    cf[4 * k] = t.x; cf[4 * k + 1] = 4 * k + 1 < na3 ? t.y : 0.f;
+                    cf[4 * k + 2] = 4 * k + 2 < na3 ? t.z : 0.f; cf[4 * k + 3] = 4 * k + 3 < na3 ? t.w : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 48; k++) cf[k] = k < na3 ? __ldg(sh + k) : 0.f;
+            }
         };
         if (!scatter) {
             grad_row(v, cam, i, a0, a1, a2, clamped, means3D, shs != nullptr, scales, rotations, cov3D_precomp, fill,

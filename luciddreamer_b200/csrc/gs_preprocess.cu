@@ -27,6 +27,7 @@ constexpr int kThreads = 256;
 constexpr int kChunkMax = 256;        // Gaussians per CTA round in the vis-list kernels: 256 when many are visible (every
 constexpr int kChunkMin = 64;         // thread owns one), 64 when only a few 10^4 are (small chunks keep all SMs busy; the
                                       // candidate walk uses all threads either way).  Chosen on the device from num_visible.
+constexpr int kFoldK = 16;           // tiles per thread when the last CTA of k_count_tiles scans the histogram (two rounds at 1080p)
 constexpr int kBitRect = 32;          // rects of up to 32 tiles: the histogram pass hands its hit decisions to the emission
                                       // pass as a bit mask (one word per visible Gaussian), so the exact test runs once
 
@@ -116,74 +117,219 @@ __device__ __forceinline__ int tile_peers(const bool hit, const uint32_t tile, i
     return __popc(peers & ((1u << lane) - 1u));
 }
 
+// The exact per-Gaussian geometry of preprocessCUDA (forward.cu:155-232,249-255) for Gaussian i.
+struct Projected {
+    bool vis;
+    int radius;
+    float4 q0, q1;
+};
+__device__ __forceinline__ Projected project_exact(const int i, const GsView& v, const GsCam& cam,
+                                                   const float* __restrict__ means3D, const float* __restrict__ opacities,
+                                                   const float* __restrict__ scales, const float* __restrict__ rotations,
+                                                   const float* __restrict__ cov3D_precomp) {
+    Projected o;
+    o.vis = false; o.radius = 0;
+    o.q0 = make_float4(0.f, 0.f, 0.f, 0.f); o.q1 = o.q0;
+    const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    const float3 p_view = gs_xf4x3(p, cam.vm);
+    if (p_view.z > GS_NEAR) {                           // only the near plane culls (auxiliary.h:154)
+        const float4 p_hom = gs_xf4x4(p, cam.pm);
+        const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        const float ppx = p_hom.x * p_w, ppy = p_hom.y * p_w;
+        float c6[6];
+        if (cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * i + k];
+        } else {
+            const float3 s = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
+            const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
+            gs_cov3d(s, v.scale_modifier, q, c6);
+        }
+        GsCov2D cc;
+        gs_cov2d(p, v, cam.vm, c6, cc);
+        const float det = cc.a * cc.c - cc.b * cc.b;
+        if (det != 0.0f) {
+            const float det_inv = 1.f / det;
+            const float3 conic = make_float3(cc.c * det_inv, -cc.b * det_inv, cc.a * det_inv);
+            const float mid = 0.5f * (cc.a + cc.c);
+            const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+            const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+            const float rad = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+            const float px = gs_ndc2pix(ppx, v.W), py = gs_ndc2pix(ppy, v.H);
+            const int4 rect = gs_rect(px, py, (int)rad, v.gx, v.gy);
+            if ((rect.z - rect.x) * (rect.w - rect.y) != 0) {
+                o.vis = true;
+                o.radius = (int)rad;
+                const float opac = opacities[i];
+                // alpha >= 1/255  <=>  power >= -ln(255 * opacity); slack keeps the test conservative
+                const float thr = -logf(255.0f * opac) - GS_CULL_SLACK;
+                o.q0 = make_float4(px, py, conic.x, conic.y);
+                o.q1 = make_float4(conic.z, opac, p_view.z, thr);        // k_shade_emit re-packs q1/q2
+            }
+        }
+    }
+    return o;
+}
+
+// Warp-aggregated append of the visible Gaussians to the compact list + their records.  Whole warps must call.
+__device__ __forceinline__ void append_visible(const Projected& o, const int i, float4* __restrict__ rec,
+                                               uint32_t* __restrict__ vis_list, GsDevStatus* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, o.vis);
+    if (!m) return;
+    unsigned long long base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&status->num_visible, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (o.vis) {
+        const uint32_t slot = (uint32_t)base + __popc(m & ((1u << lane) - 1u));
+        vis_list[slot] = (uint32_t)i;
+        float4* rr = rec + (size_t)GS_REC_V4 * i;
+        rr[0] = o.q0;
+        rr[1] = o.q1;
+    }
+}
+
+// One thread per Gaussian, exact path for all of them (the first version of the pass; GS_PROJECT_V1=1 selects it).
 __global__ void __launch_bounds__(kThreads)
+k_project_v1(const GsView v, const float* __restrict__ means3D, const float* __restrict__ opacities,
+             const float* __restrict__ scales, const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
+             int* __restrict__ radii, float4* __restrict__ rec, uint32_t* __restrict__ vis_list,
+             GsDevStatus* __restrict__ status) {
+    __shared__ GsCam cam;
+    gs_load_cam(v, &cam);
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    Projected o;
+    o.vis = false; o.radius = 0;
+    if (i < v.P) {
+        o = project_exact(i, v, cam, means3D, opacities, scales, rotations, cov3D_precomp);
+        radii[i] = o.radius;
+    }
+    append_visible(o, i, rec, vis_list, status);
+}
+
+// Conservative screen test ahead of the exact path: true only when the exact path is CERTAIN to end with an empty tile
+// rect (radius 0), from an upper bound on the splat's pixel radius that needs no covariance product:
+//   cov2D = A Sigma A^T + 0.3 I with A = J.V3 (2x3);  |a-0.3| <= |A0|^2 s, |c-0.3| <= |A1|^2 s, |b| <= |A0||A1| s with
+//   s = ||Sigma||_2 <= ||M||_F^2 = sum_i (mod s_i)^2 |col_i R|^2   (Sigma = M^T M, M = S R^T; holds for un-normalised q),
+//   or <= ||Sigma||_F for a precomputed covariance (symmetric or not, definite or not);
+//   lambda1 = mid + sqrt(max(0.1, ((a-c)/2)^2 + b^2)) <= max(a,c) + |b| + 0.3163 <= 1.5 (|A0|^2+|A1|^2) s + 0.62.
+// The 1 % / +1 / +1e-5|px| slacks cover float rounding (incl. the cancellation in mid^2 - det) and the reference's
+// double-precision ndc2Pix; NaN or infinite intermediates never reject.  Most Gaussians behind the near-plane cut are
+// far outside the image (93 % at BASELINE config 3), so the 600-instruction exact path runs for a few per CTA.
+__device__ __forceinline__ bool surely_offscreen(const int i, const float3 p, const float3 t, const GsView& v,
+                                                 const GsCam& cam, const float* __restrict__ scales,
+                                                 const float* __restrict__ rotations,
+                                                 const float* __restrict__ cov3D_precomp) {
+    const float4 h = gs_xf4x4(p, cam.pm);
+    const float iw = 1.0f / (h.w + 0.0000001f);
+    const float px = ((h.x * iw + 1.0f) * (float)v.W - 1.0f) * 0.5f;
+    const float py = ((h.y * iw + 1.0f) * (float)v.H - 1.0f) * 0.5f;
+    const float iz = 1.0f / t.z;
+    const float limx = 1.3f * v.tan_fovx, limy = 1.3f * v.tan_fovy;
+    const float cx = fminf(limx, fmaxf(-limx, t.x * iz)), cy = fminf(limy, fmaxf(-limy, t.y * iz));
+    const float J00 = v.focal_x * iz, J02 = -J00 * cx, J11 = v.focal_y * iz, J12 = -J11 * cy;
+    float nA = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float a0 = cam.vm[4 * j] * J00 + cam.vm[2 + 4 * j] * J02;
+        const float a1 = cam.vm[1 + 4 * j] * J11 + cam.vm[2 + 4 * j] * J12;
+        nA += a0 * a0 + a1 * a1;
+    }
+    float nS;
+    if (cov3D_precomp) {
+        float c[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) c[k] = cov3D_precomp[6 * i + k];
+        nS = sqrtf(c[0] * c[0] + c[3] * c[3] + c[5] * c[5] + 2.f * (c[1] * c[1] + c[2] * c[2] + c[4] * c[4]));
+    } else {
+        const float3 s = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
+        const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
+        float R[3][3];
+        gs_quat_R(q, R);
+        const float sv[3] = {v.scale_modifier * s.x, v.scale_modifier * s.y, v.scale_modifier * s.z};
+        nS = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) nS += sv[k] * sv[k] * (R[0][k] * R[0][k] + R[1][k] * R[1][k] + R[2][k] * R[2][k]);
+    }
+    const float L = 1.52f * nA * nS + 1.0f;
+    if (!(L < 1e30f)) return false;                      // overflow or NaN: let the exact path decide
+    const float Rb = 3.f * sqrtf(L) + 2.f;
+    const float sx = Rb + 1e-5f * fabsf(px), sy = Rb + 1e-5f * fabsf(py);
+    // gs_rect: empty when (px + r + 15) / 16 truncates to <= 0 or (px - r) / 16 to >= gx (same in y)
+    return (px + sx + 15.f < 0.f) || (px - sx >= 16.f * (float)v.gx) || (py + sy + 15.f < 0.f) || (py - sy >= 16.f * (float)v.gy);
+}
+
+// Persistent CTAs, two kinds of rounds: (1) cull round over a block of 256 Gaussians -- every thread tests its own by the
+// near plane and the conservative screen test, survivors go into a shared-memory queue; (2) as soon as the queue holds a
+// CTA's worth (and once more at the end) the exact path runs over queued Gaussians with every lane busy.  Far from the
+// view most blocks queue a handful, so the 600-instruction exact path runs once per ~25 cull rounds instead of once per
+// block with one warp; inside the view every block fills the queue and the kernel degenerates to v1 plus the test.
+constexpr int kProjQueue = 2 * kThreads;
+__global__ void __launch_bounds__(kThreads, 5)
 k_project(const GsView v, const float* __restrict__ means3D, const float* __restrict__ opacities,
           const float* __restrict__ scales, const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
           int* __restrict__ radii, float4* __restrict__ rec, uint32_t* __restrict__ vis_list,
           GsDevStatus* __restrict__ status) {
     __shared__ GsCam cam;
+    __shared__ int s_wcnt[kThreads / 32];
+    __shared__ uint32_t s_q[kProjQueue];
     gs_load_cam(v, &cam);
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool vis = false;
-    int my_radius = 0;
-    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nblocks = (v.P + kThreads - 1) / kThreads;
+    int nq = 0;                                          // queue length, kept identically by every thread
 
-    if (i < v.P) {
-        const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
-        const float3 p_view = gs_xf4x3(p, cam.vm);
-        if (p_view.z > GS_NEAR) {                       // only the near plane culls (auxiliary.h:154)
-            const float4 p_hom = gs_xf4x4(p, cam.pm);
-            const float p_w = 1.0f / (p_hom.w + 0.0000001f);
-            const float ppx = p_hom.x * p_w, ppy = p_hom.y * p_w;
-            float c6[6];
-            if (cov3D_precomp) {
+    // exact path over the n queued Gaussians s_q[from .. from + n), n <= kThreads
+    auto drain = [&](const int from, const int n) {
+        if (wid * 32 < n) {                              // warp-uniform
+            Projected o;
+            o.vis = false; o.radius = 0;
+            int i = 0;
+            if (tid < n) {
+                i = (int)s_q[from + tid];
+                o = project_exact(i, v, cam, means3D, opacities, scales, rotations, cov3D_precomp);
+                radii[i] = o.radius;
+            }
+            append_visible(o, i, rec, vis_list, status);
+        }
+    };
+
+    int b = blockIdx.x;
+    float3 p = make_float3(0.f, 0.f, 0.f);
+    if (b < nblocks && b * kThreads + tid < v.P) {
+        const int i = b * kThreads + tid;
+        p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    }
+    for (; b < nblocks; b += gridDim.x) {
+        const int i = b * kThreads + tid;
+        // next block's means in flight while this one is tested
+        const int in = (b + (int)gridDim.x) * kThreads + tid;
+        float3 pn = make_float3(0.f, 0.f, 0.f);
+        if (b + (int)gridDim.x < nblocks && in < v.P) pn = make_float3(means3D[3 * in], means3D[3 * in + 1], means3D[3 * in + 2]);
+        bool cand = false;
+        if (i < v.P) {
+            const float3 t = gs_xf4x3(p, cam.vm);
+            // the exact path repeats the near-plane test on its own evaluation of z; this one only has to be no stricter
+            const float zerr = 2e-6f * (fabsf(cam.vm[2] * p.x) + fabsf(cam.vm[6] * p.y) + fabsf(cam.vm[10] * p.z) + fabsf(cam.vm[14]));
+            if (!(t.z <= GS_NEAR - zerr))                // NaN stays a candidate
+                cand = !(t.z > 0.5f * GS_NEAR && surely_offscreen(i, p, t, v, cam, scales, rotations, cov3D_precomp));
+            if (!cand) radii[i] = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0) s_wcnt[wid] = __popc(m);
+        __syncthreads();                                 // counts visible; the previous drain has finished reading s_q
+        int before = 0, total = 0;
 #pragma unroll
-                for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * i + k];
-            } else {
-                const float3 s = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
-                const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
-                gs_cov3d(s, v.scale_modifier, q, c6);
-            }
-            GsCov2D cc;
-            gs_cov2d(p, v, cam.vm, c6, cc);
-            const float det = cc.a * cc.c - cc.b * cc.b;
-            if (det != 0.0f) {
-                const float det_inv = 1.f / det;
-                const float3 conic = make_float3(cc.c * det_inv, -cc.b * det_inv, cc.a * det_inv);
-                const float mid = 0.5f * (cc.a + cc.c);
-                const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-                const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
-                const float rad = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
-                const float px = gs_ndc2pix(ppx, v.W), py = gs_ndc2pix(ppy, v.H);
-                const int4 rect = gs_rect(px, py, (int)rad, v.gx, v.gy);
-                if ((rect.z - rect.x) * (rect.w - rect.y) != 0) {
-                    vis = true;
-                    my_radius = (int)rad;
-                    const float opac = opacities[i];
-                    // alpha >= 1/255  <=>  power >= -ln(255 * opacity); slack keeps the test conservative
-                    const float thr = -logf(255.0f * opac) - GS_CULL_SLACK;
-                    q0 = make_float4(px, py, conic.x, conic.y);
-                    q1 = make_float4(conic.z, opac, p_view.z, thr);      // k_shade_count re-packs q1/q2
-                }
-            }
+        for (int w = 0; w < kThreads / 32; w++) { const int c = s_wcnt[w]; if (w < wid) before += c; total += c; }
+        if (cand) s_q[nq + before + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+        nq += total;
+        __syncthreads();                                 // queue entries visible; s_wcnt free for the next round
+        if (nq >= kThreads) {
+            nq -= kThreads;
+            drain(nq, kThreads);                         // the newest kThreads entries; the older nq stay queued
         }
-        radii[i] = my_radius;
+        p = pn;
     }
-    // warp-aggregated append to the compact visible list
-    const unsigned m = __ballot_sync(0xffffffffu, vis);
-    if (m) {
-        unsigned long long base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(&status->num_visible, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (vis) {
-            const uint32_t slot = (uint32_t)base + __popc(m & ((1u << lane) - 1u));
-            vis_list[slot] = (uint32_t)i;
-            float4* rr = rec + (size_t)GS_REC_V4 * i;
-            rr[0] = q0;
-            rr[1] = q1;
-        }
-    }
+    drain(0, nq);
 }
 
 // Loads one Gaussian's SH coefficients with every load in flight before the first use, evaluates the colour.
@@ -206,10 +352,91 @@ __device__ __forceinline__ void sh_to_rgb(const float* __restrict__ sh, float x,
     for (int k = 1; k < NA; k++) { cr = cr + bs[k] * c[3 * k]; cg = cg + bs[k] * c[3 * k + 1]; cb = cb + bs[k] * c[3 * k + 2]; }
 }
 
-__global__ void __launch_bounds__(kThreads)
+// Exclusive scan of the G tile counts by ONE CTA of T threads.  Every thread owns K consecutive tiles (128-bit loads,
+// all in flight), scans them in registers, and the block scans the per-thread totals; G <= T * K needs one round (8160
+// tiles at 1080p).  Resets the counts to zero so the same array serves as the emission cursors, and mirrors the totals
+// to a pinned host slot.  The counts were produced by L2 atomics of other CTAs: read past L1.
+template <int T, int K>
+__device__ __forceinline__ void cta_tile_scan(const int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_off,
+                                              GsDevStatus* __restrict__ status, GsDevStatus* host_slot, uint32_t* s_warp,
+                                              uint32_t* s_carry) {
+    static_assert(K % 4 == 0 && T % 32 == 0 && T <= 1024, "scan shape");
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) *s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < G; base += T * K) {
+        const int t0 = base + tid * K;                   // tile_cnt / tile_off are 256-byte aligned, t0 % 4 == 0
+        uint32_t cv[K];
+        if (t0 + K <= G) {
+#pragma unroll
+            for (int k = 0; k < K; k += 4) {
+                const uint4 a = __ldcg(reinterpret_cast<const uint4*>(tile_cnt + t0 + k));
+                cv[k] = a.x; cv[k + 1] = a.y; cv[k + 2] = a.z; cv[k + 3] = a.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) cv[k] = (t0 + k < G) ? __ldcg(tile_cnt + t0 + k) : 0u;
+        }
+        uint32_t tot = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) { const uint32_t c = cv[k]; cv[k] = tot; tot += c; }   // exclusive, local
+        uint32_t x = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = lane < T / 32 ? s_warp[lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            if (lane < T / 32) s_warp[lane] = w;         // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = *s_carry;
+        const uint32_t excl = carry + (x - tot) + (wid ? s_warp[wid - 1] : 0u);
+        if (t0 + K <= G) {
+#pragma unroll
+            for (int k = 0; k < K; k += 4) {
+                *reinterpret_cast<uint4*>(tile_off + t0 + k) = make_uint4(excl + cv[k], excl + cv[k + 1], excl + cv[k + 2], excl + cv[k + 3]);
+                *reinterpret_cast<uint4*>(tile_cnt + t0 + k) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (t0 + k < G) { tile_off[t0 + k] = excl + cv[k]; tile_cnt[t0 + k] = 0u; }
+        }
+        __syncthreads();
+        if (tid == T - 1) *s_carry = excl + tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint32_t total = *s_carry;
+        tile_off[G] = total;
+        status->num_pairs = total;
+        if (host_slot) {
+            host_slot->num_rendered = *reinterpret_cast<volatile unsigned long long*>(&status->num_rendered);
+            host_slot->num_pairs = total;
+            host_slot->num_visible = *reinterpret_cast<volatile unsigned long long*>(&status->num_visible);
+            __threadfence_system();
+            host_slot->overflow = 0xC0FFEEu;            // "written" marker, checked by gs_forward_counts
+        }
+    }
+}
+
+// the scan as a kernel of its own: empty models (no k_count_tiles launch) and GS_SCAN_KERNEL=1
+constexpr int kScanT = 1024, kScanK = 8;
+__global__ void __launch_bounds__(kScanT)
+k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_off, GsDevStatus* __restrict__ status,
+            GsDevStatus* host_slot) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    cta_tile_scan<kScanT, kScanK>(G, tile_cnt, tile_off, status, host_slot, s_warp, &s_carry);
+}
+
+__global__ void __launch_bounds__(kThreads, 6)
 k_count_tiles(const GsView v, const int* __restrict__ radii, const float4* __restrict__ rec,
               const uint32_t* __restrict__ vis_list, uint32_t* __restrict__ hitmask, uint32_t* __restrict__ tile_cnt,
-              GsDevStatus* __restrict__ status) {
+              GsDevStatus* __restrict__ status, uint32_t* __restrict__ tile_off, GsDevStatus* host_slot, const bool scan_here) {
     __shared__ CandShared S;
     const uint32_t nvis = (uint32_t)status->num_visible;
     const int CH = vis_chunk(nvis);
@@ -242,74 +469,22 @@ k_count_tiles(const GsView v, const int* __restrict__ radii, const float4* __res
         __syncthreads();
     }
     if (threadIdx.x == 0 && rendered) atomicAdd(&status->num_rendered, rendered);
-}
-
-// Exclusive scan of the G tile counts (single CTA: G is ~8k at 1080p, one round).  Every thread owns 8 consecutive
-// tiles (two 128-bit loads), scans them in registers, and the block scans the per-thread totals.  Resets the counts
-// to zero so the same array serves as the emission cursors, and mirrors the totals to a pinned host slot.
-constexpr int kScanT = 1024, kScanK = 8;
-__global__ void __launch_bounds__(kScanT)
-k_tile_scan(int G, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ tile_off, GsDevStatus* __restrict__ status,
-            GsDevStatus* host_slot) {
+    if (!scan_here) return;
+    // The last CTA to finish scans the histogram (k_tile_scan's work without its launch): every CTA publishes its
+    // atomics, then takes a ticket.
+    __shared__ bool s_last;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    __threadfence();
+    __syncthreads();                                     // this CTA's tile_cnt atomics are all issued and ordered
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&status->pad, 1u) == gridDim.x - 1;
+        __threadfence();
+    }
     __syncthreads();
-    for (int base = 0; base < G; base += kScanT * kScanK) {
-        const int t0 = base + tid * kScanK;              // tile_cnt / tile_off are 256-byte aligned, t0 % 8 == 0
-        uint32_t cv[kScanK];
-        if (t0 + kScanK <= G) {
-            const uint4 a = *reinterpret_cast<const uint4*>(tile_cnt + t0);
-            const uint4 b = *reinterpret_cast<const uint4*>(tile_cnt + t0 + 4);
-            cv[0] = a.x; cv[1] = a.y; cv[2] = a.z; cv[3] = a.w; cv[4] = b.x; cv[5] = b.y; cv[6] = b.z; cv[7] = b.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < kScanK; k++) cv[k] = (t0 + k < G) ? tile_cnt[t0 + k] : 0u;
-        }
-        uint32_t tot = 0;
-#pragma unroll
-        for (int k = 0; k < kScanK; k++) { const uint32_t c = cv[k]; cv[k] = tot; tot += c; }   // exclusive, local
-        uint32_t x = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-            s_warp[lane] = w;                            // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t carry = s_carry;
-        const uint32_t excl = carry + (x - tot) + (wid ? s_warp[wid - 1] : 0u);
-        if (t0 + kScanK <= G) {
-            *reinterpret_cast<uint4*>(tile_off + t0) = make_uint4(excl + cv[0], excl + cv[1], excl + cv[2], excl + cv[3]);
-            *reinterpret_cast<uint4*>(tile_off + t0 + 4) = make_uint4(excl + cv[4], excl + cv[5], excl + cv[6], excl + cv[7]);
-            *reinterpret_cast<uint4*>(tile_cnt + t0) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(tile_cnt + t0 + 4) = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-#pragma unroll
-            for (int k = 0; k < kScanK; k++)
-                if (t0 + k < G) { tile_off[t0 + k] = excl + cv[k]; tile_cnt[t0 + k] = 0u; }
-        }
-        __syncthreads();
-        if (tid == kScanT - 1) s_carry = excl + tot;
-        __syncthreads();
-    }
-    if (tid == 0) {
-        const uint32_t total = s_carry;
-        tile_off[G] = total;
-        status->num_pairs = total;
-        if (host_slot) {
-            host_slot->num_rendered = status->num_rendered;
-            host_slot->num_pairs = total;
-            host_slot->num_visible = status->num_visible;
-            __threadfence_system();
-            host_slot->overflow = 0xC0FFEEu;            // "written" marker, checked by gs_forward_counts
-        }
-    }
+    if (!s_last) return;
+    cta_tile_scan<kThreads, kFoldK>(v.gx * v.gy, tile_cnt, tile_off, status, host_slot, s_warp, &s_carry);
 }
 
 // After the scan (off the host's critical path): SH -> RGB for the visible Gaussians, final record + zeroed
@@ -497,16 +672,26 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means3D, const f
 
 void gs_launch_project(const GsView& v, const float* means3D, const float* opacities, const float* scales,
                        const float* rotations, const float* cov3D_precomp, int* radii, float4* rec,
-                       uint32_t* vis_list, GsDevStatus* status, cudaStream_t s) {
+                       uint32_t* vis_list, GsDevStatus* status, bool dense_hint, cudaStream_t s) {
     const int grid = (v.P + kThreads - 1) / kThreads;
-    k_project<<<grid, kThreads, 0, s>>>(v, means3D, opacities, scales, rotations, cov3D_precomp, radii, rec, vis_list,
-                                       status);
+    // most of the model was inside the previous view of this context: the screen pre-test would reject next to nothing
+    // -- skip it (same results either way)
+    static const bool v1 = getenv("GS_PROJECT_CULL") == nullptr;      // experimental kernel only on request
+    const int pgrid = grid < g_gs_num_sms * 5 ? grid : g_gs_num_sms * 5;      // persistent: 5 CTAs of 48 registers per SM
+    if (v1 || dense_hint) k_project_v1<<<grid, kThreads, 0, s>>>(v, means3D, opacities, scales, rotations, cov3D_precomp, radii, rec, vis_list, status);
+    else k_project<<<pgrid, kThreads, 0, s>>>(v, means3D, opacities, scales, rotations, cov3D_precomp, radii, rec, vis_list, status);
+}
+bool gs_scan_folded() {
+    static const bool separate = getenv("GS_SCAN_KERNEL") != nullptr;
+    return !separate;
 }
 void gs_launch_count_tiles(const GsView& v, int num_sms, const int* radii, const float4* rec, const uint32_t* vis_list,
-                           uint32_t* hitmask, uint32_t* tile_cnt, GsDevStatus* status, cudaStream_t s) {
+                           uint32_t* hitmask, uint32_t* tile_cnt, GsDevStatus* status, uint32_t* tile_off,
+                           GsDevStatus* host_slot, cudaStream_t s) {
     const int need = (v.P + kChunkMin - 1) / kChunkMin;
     const int grid = need < num_sms * 8 ? need : num_sms * 8;
-    k_count_tiles<<<grid, kThreads, 0, s>>>(v, radii, rec, vis_list, hitmask, tile_cnt, status);
+    k_count_tiles<<<grid, kThreads, 0, s>>>(v, radii, rec, vis_list, hitmask, tile_cnt, status, tile_off, host_slot,
+                                            gs_scan_folded());
 }
 void gs_launch_tile_scan(int G, uint32_t* tile_cnt, uint32_t* tile_off, GsDevStatus* status, GsDevStatus* host_slot,
                          cudaStream_t s) {

@@ -1,0 +1,119 @@
+"""The conservative screen test that k_project runs ahead of the exact per-Gaussian path (csrc/gs_preprocess.cu:
+surely_offscreen) may only reject Gaussians whose exact path ends with an empty tile rect.  The device code needs a GPU;
+its ARITHMETIC is restated here in numpy float32, operation for operation, and checked against the radii of the reference
+fixtures and of the CPU oracle on every parity case plus adversarial inputs (un-normalised quaternions, huge and tiny
+scales, scale modifiers, precomputed covariances, rotated / off-centre cameras): no Gaussian with radius > 0 may be
+rejected.  The GPU parity tests then check the kernel itself (radii and pair counts are compared exactly there)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import util
+from oracle import oracle
+
+f32 = np.float32
+NEAR = f32(0.2)
+
+
+def surely_offscreen_np(means, scales, rots, cov6, vm, pm, tanx, tany, W, H, mod):
+    """-> (candidate_by_z, rejected) per Gaussian; float32 throughout like the kernel."""
+    means = means.astype(f32)
+    vm = vm.astype(f32).reshape(-1); pm = pm.astype(f32).reshape(-1)          # flat, element [k] as the kernel indexes it
+    x, y, z = means[:, 0], means[:, 1], means[:, 2]
+    tx = vm[0] * x + vm[4] * y + vm[8] * z + vm[12]
+    ty = vm[1] * x + vm[5] * y + vm[9] * z + vm[13]
+    tz = vm[2] * x + vm[6] * y + vm[10] * z + vm[14]
+    zerr = f32(2e-6) * (np.abs(vm[2] * x) + np.abs(vm[6] * y) + np.abs(vm[10] * z) + np.abs(vm[14]))
+    by_z = ~(tz <= NEAR - zerr)
+    with np.errstate(all="ignore"):
+        hx = pm[0] * x + pm[4] * y + pm[8] * z + pm[12]
+        hy = pm[1] * x + pm[5] * y + pm[9] * z + pm[13]
+        hw = pm[3] * x + pm[7] * y + pm[11] * z + pm[15]
+        iw = f32(1.0) / (hw + f32(0.0000001))
+        px = ((hx * iw + f32(1.0)) * f32(W) - f32(1.0)) * f32(0.5)
+        py = ((hy * iw + f32(1.0)) * f32(H) - f32(1.0)) * f32(0.5)
+        iz = f32(1.0) / tz
+        limx, limy = f32(1.3) * f32(tanx), f32(1.3) * f32(tany)
+        cx = np.minimum(limx, np.maximum(-limx, tx * iz)); cy = np.minimum(limy, np.maximum(-limy, ty * iz))
+        fx, fy = f32(W / (2.0 * tanx)), f32(H / (2.0 * tany))
+        J00 = fx * iz; J02 = -J00 * cx; J11 = fy * iz; J12 = -J11 * cy
+        nA = np.zeros_like(tz)
+        for j in range(3):
+            a0 = vm[4 * j] * J00 + vm[2 + 4 * j] * J02
+            a1 = vm[1 + 4 * j] * J11 + vm[2 + 4 * j] * J12
+            nA = nA + (a0 * a0 + a1 * a1)
+        if cov6 is not None:
+            c = cov6.astype(f32)
+            nS = np.sqrt(c[:, 0] ** 2 + c[:, 3] ** 2 + c[:, 5] ** 2 + f32(2) * (c[:, 1] ** 2 + c[:, 2] ** 2 + c[:, 4] ** 2))
+        else:
+            q = rots.astype(f32); r, qx, qy, qz = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+            R = [[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - r * qz), 2 * (qx * qz + r * qy)],
+                 [2 * (qx * qy + r * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - r * qx)],
+                 [2 * (qx * qz - r * qy), 2 * (qy * qz + r * qx), 1 - 2 * (qx * qx + qy * qy)]]
+            sv = f32(mod) * scales.astype(f32)
+            nS = np.zeros_like(tz)
+            for k in range(3):
+                nS = nS + sv[:, k] * sv[:, k] * (R[0][k] * R[0][k] + R[1][k] * R[1][k] + R[2][k] * R[2][k])
+        L = f32(1.52) * nA * nS + f32(1.0)
+        ok = L < f32(1e30)
+        Rb = f32(3.0) * np.sqrt(L) + f32(2.0)
+        sx = Rb + f32(1e-5) * np.abs(px); sy = Rb + f32(1e-5) * np.abs(py)
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        off = (px + sx + f32(15) < 0) | (px - sx >= f32(16 * gx)) | (py + sy + f32(15) < 0) | (py - sy >= f32(16 * gy))
+    rejected = by_z & (tz > f32(0.5) * NEAR) & ok & off
+    return by_z, rejected
+
+
+def _check(inp, radii, what):
+    case, cam = inp["case"], inp["cam"]
+    npy = lambda t: None if t is None else t.numpy()
+    by_z, rej = surely_offscreen_np(npy(inp["means3D"]), npy(inp["scales"]), npy(inp["rotations"]), npy(inp["cov3D_precomp"]),
+                                    cam.viewmatrix.numpy(), cam.projmatrix.numpy(), cam.tanfovx, cam.tanfovy,
+                                    cam.image_width, cam.image_height, case.scale_modifier)
+    vis = np.asarray(radii) > 0
+    assert not (vis & ~by_z).any(), f"{what}: near-plane pre-test dropped {int((vis & ~by_z).sum())} visible Gaussians"
+    assert not (vis & rej).any(), f"{what}: screen pre-test rejected {int((vis & rej).sum())} visible Gaussians"
+    inv = by_z & ~vis
+    return int(rej.sum()), int(inv.sum())
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=lambda c: c.name)
+def test_precull_never_rejects_what_the_reference_keeps(case):
+    inp = cases.build_inputs(case)
+    rej, inv = _check(inp, util.load_golden(case.name)["radii"], case.name)
+    print(f"{case.name}: off-screen {inv}, rejected early {rej}")
+    if inv > 100 and case.scene == "shell" and not case.pose and case.scale_mult <= 2.0:
+        assert rej > 0.7 * inv, f"{case.name}: only {rej} of {inv} off-screen Gaussians rejected -- the bound is too loose to pay"
+
+
+@pytest.mark.parametrize("case", cases.EXTRA_CASES, ids=lambda c: c.name)
+def test_precull_never_rejects_what_the_oracle_keeps(case):
+    inp = cases.build_inputs(case)
+    f = oracle.rasterize_gaussians(*cases.binding_args(inp))
+    _check(inp, f.radii, case.name)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_precull_on_adversarial_inputs(seed):
+    """Un-normalised quaternions (|q| from 1e-3 to 30), scales over 8 decades, means on and around the frustum border,
+    a scale modifier, odd image sizes: the oracle's radii decide."""
+    g = torch.Generator().manual_seed(900 + seed)
+    P = 6000
+    W, H = [(100, 70), (64, 64), (333, 17), (16, 16), (1920, 1080), (31, 250)][seed]
+    case = cases.Case(f"adv{seed}", P, W, H, 0, 900 + seed, scale_modifier=[1.0, 0.01, 7.5, 1.0, 2.0, 1.0][seed], golden=False)
+    inp = cases.build_inputs(case)
+    cam = inp["cam"]
+    # means: a fan that straddles the image border at every depth, some behind / on the near plane
+    z = torch.exp(torch.empty(P).uniform_(-2.5, 4.0, generator=g))
+    z[: P // 20] = 0.2 + torch.empty(P // 20).uniform_(-1e-6, 1e-6, generator=g)
+    u = torch.empty(P).uniform_(-1.6, 1.6, generator=g) * cam.tanfovx
+    v = torch.empty(P).uniform_(-1.6, 1.6, generator=g) * cam.tanfovy
+    inp["means3D"] = torch.stack([u * z, v * z, z], 1).contiguous()
+    inp["scales"] = (torch.exp(torch.empty(P, 3).uniform_(-12.0, 6.0, generator=g)) * z[:, None] * 0.01).contiguous()
+    q = torch.randn(P, 4, generator=g)
+    inp["rotations"] = (q * torch.exp(torch.empty(P, 1).uniform_(-7.0, 3.4, generator=g))).contiguous()
+    f = oracle.rasterize_gaussians(*cases.binding_args(inp))
+    rej, inv = _check(inp, f.radii, case.name)
+    print(f"{case.name}: visible {int((np.asarray(f.radii) > 0).sum())}, off-screen {inv}, rejected early {rej}")
+    assert int((np.asarray(f.radii) > 0).sum()) > 100 and (rej > 100 or W * H <= 256)      # the case exercises both outcomes
