@@ -208,33 +208,30 @@ k_project_v1(const GsView v, const float* __restrict__ means3D, const float* __r
 }
 
 // Conservative screen test ahead of the exact path: true only when the exact path is CERTAIN to end with an empty tile
-// rect (radius 0), from an upper bound on the splat's pixel radius that needs no covariance product:
+// rect (radius 0), from an upper bound on the splat's pixel radius that needs no matrix product:
 //   cov2D = A Sigma A^T + 0.3 I with A = J.V3 (2x3);  |a-0.3| <= |A0|^2 s, |c-0.3| <= |A1|^2 s, |b| <= |A0||A1| s with
-//   s = ||Sigma||_2 <= ||M||_F^2 = sum_i (mod s_i)^2 |col_i R|^2   (Sigma = M^T M, M = S R^T; holds for un-normalised q),
-//   or <= ||Sigma||_F for a precomputed covariance (symmetric or not, definite or not);
-//   lambda1 = mid + sqrt(max(0.1, ((a-c)/2)^2 + b^2)) <= max(a,c) + |b| + 0.3163 <= 1.5 (|A0|^2+|A1|^2) s + 0.62.
-// The 1 % / +1 / +1e-5|px| slacks cover float rounding (incl. the cancellation in mid^2 - det) and the reference's
-// double-precision ndc2Pix; NaN or infinite intermediates never reject.  Most Gaussians behind the near-plane cut are
-// far outside the image (93 % at BASELINE config 3), so the 600-instruction exact path runs for a few per CTA.
+//   s = ||Sigma||_2;  lambda1 = mid + sqrt(max(0.1, ((a-c)/2)^2 + b^2)) <= max(a,c) + |b| + 0.3163 <= 1.5 ||A||_F^2 s + 0.62;
+//   ||A||_F <= ||J||_F ||V3||_2, and ||V3||_2^2 <= vnorm2 = (tr G^8)^(1/8) with G = V3^T V3 (1.147 for a rigid view matrix);
+//   s = ||M||_2^2 (Sigma = M^T M, M = S R^T) <= (mod s_max)^2 ||R||_2^2, and for the UN-normalised quaternion the
+//   reference feeds in, R(q) = (1 - n) I + n R(q/|q|) with n = |q|^2, so ||R||_2 <= |1 - n| + n (= 1 for a unit q);
+//   a precomputed covariance (symmetric or not, definite or not): s <= ||Sigma||_F.
+// About 1.3x loose in radius -- most Gaussians behind the near-plane cut are far outside the image anyway (93 % at
+// BASELINE config 3).  The 1 % / +2 / +1e-5|px| slacks cover float rounding (incl. the cancellation in mid^2 - det) and
+// the reference's double-precision ndc2Pix; NaN or infinite intermediates never reject.
 __device__ __forceinline__ bool surely_offscreen(const int i, const float3 p, const float3 t, const GsView& v,
-                                                 const GsCam& cam, const float* __restrict__ scales,
-                                                 const float* __restrict__ rotations,
+                                                 const GsCam& cam, const float vnorm2, const float3 s, const float4 q,
                                                  const float* __restrict__ cov3D_precomp) {
-    const float4 h = gs_xf4x4(p, cam.pm);
-    const float iw = 1.0f / (h.w + 0.0000001f);
-    const float px = ((h.x * iw + 1.0f) * (float)v.W - 1.0f) * 0.5f;
-    const float py = ((h.y * iw + 1.0f) * (float)v.H - 1.0f) * 0.5f;
+    const float hx = cam.pm[0] * p.x + cam.pm[4] * p.y + cam.pm[8] * p.z + cam.pm[12];
+    const float hy = cam.pm[1] * p.x + cam.pm[5] * p.y + cam.pm[9] * p.z + cam.pm[13];
+    const float hw = cam.pm[3] * p.x + cam.pm[7] * p.y + cam.pm[11] * p.z + cam.pm[15];
+    const float iw = 1.0f / (hw + 0.0000001f);
+    const float px = ((hx * iw + 1.0f) * (float)v.W - 1.0f) * 0.5f;
+    const float py = ((hy * iw + 1.0f) * (float)v.H - 1.0f) * 0.5f;
     const float iz = 1.0f / t.z;
     const float limx = 1.3f * v.tan_fovx, limy = 1.3f * v.tan_fovy;
     const float cx = fminf(limx, fmaxf(-limx, t.x * iz)), cy = fminf(limy, fmaxf(-limy, t.y * iz));
-    const float J00 = v.focal_x * iz, J02 = -J00 * cx, J11 = v.focal_y * iz, J12 = -J11 * cy;
-    float nA = 0.f;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const float a0 = cam.vm[4 * j] * J00 + cam.vm[2 + 4 * j] * J02;
-        const float a1 = cam.vm[1 + 4 * j] * J11 + cam.vm[2 + 4 * j] * J12;
-        nA += a0 * a0 + a1 * a1;
-    }
+    const float J00 = v.focal_x * iz, J11 = v.focal_y * iz;
+    const float nJ = J00 * J00 * (1.0f + cx * cx) + J11 * J11 * (1.0f + cy * cy);     // J = [J00 0 -J00 cx; 0 J11 -J11 cy]
     float nS;
     if (cov3D_precomp) {
         float c[6];
@@ -242,16 +239,11 @@ __device__ __forceinline__ bool surely_offscreen(const int i, const float3 p, co
         for (int k = 0; k < 6; k++) c[k] = cov3D_precomp[6 * i + k];
         nS = sqrtf(c[0] * c[0] + c[3] * c[3] + c[5] * c[5] + 2.f * (c[1] * c[1] + c[2] * c[2] + c[4] * c[4]));
     } else {
-        const float3 s = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
-        const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
-        float R[3][3];
-        gs_quat_R(q, R);
-        const float sv[3] = {v.scale_modifier * s.x, v.scale_modifier * s.y, v.scale_modifier * s.z};
-        nS = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; k++) nS += sv[k] * sv[k] * (R[0][k] * R[0][k] + R[1][k] * R[1][k] + R[2][k] * R[2][k]);
+        const float n = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+        const float sm = v.scale_modifier * fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z))) * (fabsf(1.0f - n) + n);
+        nS = sm * sm;
     }
-    const float L = 1.52f * nA * nS + 1.0f;
+    const float L = 1.52f * (nJ * vnorm2) * nS + 1.0f;
     if (!(L < 1e30f)) return false;                      // overflow or NaN: let the exact path decide
     const float Rb = 3.f * sqrtf(L) + 2.f;
     const float sx = Rb + 1e-5f * fabsf(px), sy = Rb + 1e-5f * fabsf(py);
@@ -265,7 +257,7 @@ __device__ __forceinline__ bool surely_offscreen(const int i, const float3 p, co
 // view most blocks queue a handful, so the 600-instruction exact path runs once per ~25 cull rounds instead of once per
 // block with one warp; inside the view every block fills the queue and the kernel degenerates to v1 plus the test.
 constexpr int kProjQueue = 2 * kThreads;
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, 4)
 k_project(const GsView v, const float* __restrict__ means3D, const float* __restrict__ opacities,
           const float* __restrict__ scales, const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
           int* __restrict__ radii, float4* __restrict__ rec, uint32_t* __restrict__ vis_list,
@@ -277,6 +269,30 @@ k_project(const GsView v, const float* __restrict__ means3D, const float* __rest
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nblocks = (v.P + kThreads - 1) / kThreads;
     int nq = 0;                                          // queue length, kept identically by every thread
+    // upper bound of ||V3||_2^2 of the view matrix for surely_offscreen: (tr G^8)^(1/8), G = V3^T V3
+    float vnorm2;
+    {
+        float G[3][3], G2[3][3], G4[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                G[a][c] = cam.vm[4 * a] * cam.vm[4 * c] + cam.vm[1 + 4 * a] * cam.vm[1 + 4 * c] + cam.vm[2 + 4 * a] * cam.vm[2 + 4 * c];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) G2[a][c] = G[a][0] * G[0][c] + G[a][1] * G[1][c] + G[a][2] * G[2][c];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) G4[a][c] = G2[a][0] * G2[0][c] + G2[a][1] * G2[1][c] + G2[a][2] * G2[2][c];
+        float t8 = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) t8 += G4[a][c] * G4[a][c];
+        vnorm2 = sqrtf(sqrtf(sqrtf(t8))) * 1.001f;
+    }
 
     // exact path over the n queued Gaussians s_q[from .. from + n), n <= kThreads
     auto drain = [&](const int from, const int n) {
@@ -293,25 +309,34 @@ k_project(const GsView v, const float* __restrict__ means3D, const float* __rest
         }
     };
 
+    // One cull round ahead, every thread has its Gaussian's mean, scale and rotation in flight (unconditionally: the
+    // round itself is then a pure ALU chain; the bytes of the half behind the near plane are cheap next to the latency).
+    struct Row { float3 p, s; float4 q; };
+    auto load_row = [&](const int i) {
+        Row r;
+        r.p = make_float3(0.f, 0.f, 0.f); r.s = r.p; r.q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < v.P) {
+            r.p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+            if (!cov3D_precomp) {
+                r.s = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
+                r.q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
+            }
+        }
+        return r;
+    };
     int b = blockIdx.x;
-    float3 p = make_float3(0.f, 0.f, 0.f);
-    if (b < nblocks && b * kThreads + tid < v.P) {
-        const int i = b * kThreads + tid;
-        p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
-    }
+    Row cur = load_row(b < nblocks ? b * kThreads + tid : v.P);
     for (; b < nblocks; b += gridDim.x) {
         const int i = b * kThreads + tid;
-        // next block's means in flight while this one is tested
-        const int in = (b + (int)gridDim.x) * kThreads + tid;
-        float3 pn = make_float3(0.f, 0.f, 0.f);
-        if (b + (int)gridDim.x < nblocks && in < v.P) pn = make_float3(means3D[3 * in], means3D[3 * in + 1], means3D[3 * in + 2]);
+        const Row nxt = load_row(b + (int)gridDim.x < nblocks ? (b + (int)gridDim.x) * kThreads + tid : v.P);
+        const float3 p = cur.p;
         bool cand = false;
         if (i < v.P) {
             const float3 t = gs_xf4x3(p, cam.vm);
             // the exact path repeats the near-plane test on its own evaluation of z; this one only has to be no stricter
             const float zerr = 2e-6f * (fabsf(cam.vm[2] * p.x) + fabsf(cam.vm[6] * p.y) + fabsf(cam.vm[10] * p.z) + fabsf(cam.vm[14]));
             if (!(t.z <= GS_NEAR - zerr))                // NaN stays a candidate
-                cand = !(t.z > 0.5f * GS_NEAR && surely_offscreen(i, p, t, v, cam, scales, rotations, cov3D_precomp));
+                cand = !(t.z > 0.5f * GS_NEAR && surely_offscreen(i, p, t, v, cam, vnorm2, cur.s, cur.q, cov3D_precomp));
             if (!cand) radii[i] = 0;
         }
         const unsigned m = __ballot_sync(0xffffffffu, cand);
@@ -327,7 +352,7 @@ k_project(const GsView v, const float* __restrict__ means3D, const float* __rest
             nq -= kThreads;
             drain(nq, kThreads);                         // the newest kThreads entries; the older nq stay queued
         }
-        p = pn;
+        cur = nxt;
     }
     drain(0, nq);
 }
@@ -676,8 +701,8 @@ void gs_launch_project(const GsView& v, const float* means3D, const float* opaci
     const int grid = (v.P + kThreads - 1) / kThreads;
     // most of the model was inside the previous view of this context: the screen pre-test would reject next to nothing
     // -- skip it (same results either way)
-    static const bool v1 = getenv("GS_PROJECT_CULL") == nullptr;      // experimental kernel only on request
-    const int pgrid = grid < g_gs_num_sms * 5 ? grid : g_gs_num_sms * 5;      // persistent: 5 CTAs of 48 registers per SM
+    static const bool v1 = getenv("GS_PROJECT_V1") != nullptr;
+    const int pgrid = grid < g_gs_num_sms * 4 ? grid : g_gs_num_sms * 4;      // persistent: 4 CTAs of <= 64 registers per SM
     if (v1 || dense_hint) k_project_v1<<<grid, kThreads, 0, s>>>(v, means3D, opacities, scales, rotations, cov3D_precomp, radii, rec, vis_list, status);
     else k_project<<<pgrid, kThreads, 0, s>>>(v, means3D, opacities, scales, rotations, cov3D_precomp, radii, rec, vis_list, status);
 }

@@ -16,6 +16,16 @@ f32 = np.float32
 NEAR = f32(0.2)
 
 
+def view_norm2_np(vm):
+    """Upper bound of ||V3||_2^2: (tr G^8)^(1/8) with G = V3^T V3 (1.147 for a rigid view matrix)."""
+    V = np.array([[vm[4 * j + i] for j in range(3)] for i in range(3)], dtype=f32)     # V[i][j] = vm[i + 4 j]
+    G = (V.T @ V).astype(f32)
+    G2 = (G @ G).astype(f32)
+    G4 = (G2 @ G2).astype(f32)
+    t8 = f32((G4 * G4).sum())
+    return f32(np.sqrt(np.sqrt(np.sqrt(t8)))) * f32(1.001)
+
+
 def surely_offscreen_np(means, scales, rots, cov6, vm, pm, tanx, tany, W, H, mod):
     """-> (candidate_by_z, rejected) per Gaussian; float32 throughout like the kernel."""
     means = means.astype(f32)
@@ -37,24 +47,20 @@ def surely_offscreen_np(means, scales, rots, cov6, vm, pm, tanx, tany, W, H, mod
         limx, limy = f32(1.3) * f32(tanx), f32(1.3) * f32(tany)
         cx = np.minimum(limx, np.maximum(-limx, tx * iz)); cy = np.minimum(limy, np.maximum(-limy, ty * iz))
         fx, fy = f32(W / (2.0 * tanx)), f32(H / (2.0 * tany))
-        J00 = fx * iz; J02 = -J00 * cx; J11 = fy * iz; J12 = -J11 * cy
-        nA = np.zeros_like(tz)
-        for j in range(3):
-            a0 = vm[4 * j] * J00 + vm[2 + 4 * j] * J02
-            a1 = vm[1 + 4 * j] * J11 + vm[2 + 4 * j] * J12
-            nA = nA + (a0 * a0 + a1 * a1)
+        J00 = fx * iz; J11 = fy * iz
+        nJ = J00 * J00 * (f32(1.0) + cx * cx) + J11 * J11 * (f32(1.0) + cy * cy)
+        vnorm2 = view_norm2_np(vm)
         if cov6 is not None:
             c = cov6.astype(f32)
             nS = np.sqrt(c[:, 0] ** 2 + c[:, 3] ** 2 + c[:, 5] ** 2 + f32(2) * (c[:, 1] ** 2 + c[:, 2] ** 2 + c[:, 4] ** 2))
         else:
-            q = rots.astype(f32); r, qx, qy, qz = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-            R = [[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - r * qz), 2 * (qx * qz + r * qy)],
-                 [2 * (qx * qy + r * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - r * qx)],
-                 [2 * (qx * qz - r * qy), 2 * (qy * qz + r * qx), 1 - 2 * (qx * qx + qy * qy)]]
-            sv = f32(mod) * scales.astype(f32)
-            nS = np.zeros_like(tz)
-            for k in range(3):
-                nS = nS + sv[:, k] * sv[:, k] * (R[0][k] * R[0][k] + R[1][k] * R[1][k] + R[2][k] * R[2][k])
+            q = rots.astype(f32)
+            n = q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3]
+            d = np.abs(f32(1.0) - n) + n
+            sc = np.abs(scales.astype(f32))
+            sm = f32(mod) * np.maximum(sc[:, 0], np.maximum(sc[:, 1], sc[:, 2])) * d
+            nS = sm * sm
+        nA = nJ * vnorm2
         L = f32(1.52) * nA * nS + f32(1.0)
         ok = L < f32(1e30)
         Rb = f32(3.0) * np.sqrt(L) + f32(2.0)
