@@ -111,3 +111,23 @@ def test_gloo_world2_allreduce_and_densify_stats():
         assert np.allclose(r[4][1], res[0][3][1] + res[1][3][1])
         assert np.allclose(r[4][2], np.maximum(res[0][3][2], res[1][3][2]))
     assert sorted(res[0][5] + res[1][5]) == list(range(8))
+
+
+def test_pair_capacity_hint_is_a_decayed_maximum():
+    """a random camera per iteration (luciddreamer.py:291-292) must not re-render whenever a view has
+    more pairs than the PREVIOUS one -- the hint keeps the largest recent count and forgets it slowly."""
+    from luciddreamer_b200 import rasterizer as R
+    idx = 63                                        # a device index nothing else uses
+    R._cap_hint.pop(idx, None)
+    seq = [400_000, 100_000, 390_000, 120_000, 410_000, 90_000]
+    hints = []
+    for n in seq:
+        R._note_pairs(idx, n)
+        hints.append(R._cap_hint[idx])
+    assert hints[0] == 400_000 and hints[4] == 410_000
+    assert all(h >= n for h, n in zip(hints, seq))                      # never below the count just seen
+    assert hints[1] >= 0.97 * 400_000 - 1 and hints[5] >= 0.97 * 410_000 - 1      # a small view does not erase a large one
+    for _ in range(200):
+        R._note_pairs(idx, 100_000)
+    assert R._cap_hint[idx] == 100_000               # ... but the memory fades: 0.97^200 of 410 k is below 100 k
+    R._cap_hint.pop(idx, None); R._last_pairs.pop(idx, None)
