@@ -291,7 +291,10 @@ k_project(const GsView v, const float* __restrict__ means3D, const float* __rest
         for (int a = 0; a < 3; a++)
 #pragma unroll
             for (int c = 0; c < 3; c++) t8 += G4[a][c] * G4[a][c];
-        vnorm2 = sqrtf(sqrtf(sqrtf(t8))) * 1.001f;
+        // tr G = ||V3||_F^2 bounds it too; it takes over when G^8 leaves the float range (view matrices scaled by < 4e-3
+        // or > 1e2 -- nothing a camera produces, but an underflow to 0 must not turn into a radius bound of 0)
+        const float trG = G[0][0] + G[1][1] + G[2][2];
+        vnorm2 = (t8 > 1e-30f && t8 < 1e30f) ? fminf(trG, sqrtf(sqrtf(sqrtf(t8))) * 1.001f) : trG;
     }
 
     // exact path over the n queued Gaussians s_q[from .. from + n), n <= kThreads

@@ -17,13 +17,17 @@ NEAR = f32(0.2)
 
 
 def view_norm2_np(vm):
-    """Upper bound of ||V3||_2^2: (tr G^8)^(1/8) with G = V3^T V3 (1.147 for a rigid view matrix)."""
+    """Upper bound of ||V3||_2^2: (tr G^8)^(1/8) with G = V3^T V3 (1.147 for a rigid view matrix), tr G when G^8 leaves the
+    float range."""
     V = np.array([[vm[4 * j + i] for j in range(3)] for i in range(3)], dtype=f32)     # V[i][j] = vm[i + 4 j]
     G = (V.T @ V).astype(f32)
     G2 = (G @ G).astype(f32)
     G4 = (G2 @ G2).astype(f32)
     t8 = f32((G4 * G4).sum())
-    return f32(np.sqrt(np.sqrt(np.sqrt(t8)))) * f32(1.001)
+    trG = f32(G[0, 0] + G[1, 1] + G[2, 2])
+    if t8 > f32(1e-30) and t8 < f32(1e30):
+        return min(trG, f32(np.sqrt(np.sqrt(np.sqrt(t8)))) * f32(1.001))
+    return trG
 
 
 def surely_offscreen_np(means, scales, rots, cov6, vm, pm, tanx, tany, W, H, mod):
@@ -123,3 +127,41 @@ def test_precull_on_adversarial_inputs(seed):
     rej, inv = _check(inp, f.radii, case.name)
     print(f"{case.name}: visible {int((np.asarray(f.radii) > 0).sum())}, off-screen {inv}, rejected early {rej}")
     assert int((np.asarray(f.radii) > 0).sum()) > 100 and (rej > 100 or W * H <= 256)      # the case exercises both outcomes
+
+
+def test_view_norm_bound_holds_over_the_float_range():
+    rng = np.random.default_rng(5)
+    for k in range(200):
+        V = rng.standard_normal((3, 3)) * 10.0 ** rng.uniform(-7, 5)
+        if k % 4 == 0:                                                       # rigid rotations, scaled
+            V = np.linalg.qr(rng.standard_normal((3, 3)))[0] * 10.0 ** rng.uniform(-7, 5)
+        vm = np.zeros(16, f32)
+        for i in range(3):
+            for j in range(3):
+                vm[i + 4 * j] = V[i, j]
+        true = np.linalg.svd(vm.reshape(4, 4)[:3, :3].astype(np.float64), compute_uv=False)[0] ** 2
+        got = float(view_norm2_np(vm))
+        assert got >= true * (1 - 1e-5) or not np.isfinite(got), (k, got, true)
+        if 1e-2 < true < 1e3:
+            assert got <= 3.01 * true                                        # never looser than the Frobenius norm
+
+
+@pytest.mark.parametrize("unit", [1e3, 1e-3, 3e4])
+def test_precull_with_a_scaled_world(unit):
+    """The same scene in other length units: world coordinates and scales multiplied by `unit`, the 3x3 block of the view
+    matrix divided by it (view space, and so the image, unchanged).  At 1e3 and beyond G^8 underflows in float32."""
+    case = cases.BY_NAME["rot40_5k_128x72"]
+    inp = cases.build_inputs(case)
+    cam = inp["cam"]
+    vm = cam.viewmatrix.double().clone()
+    proj_t = torch.linalg.solve(vm, cam.projmatrix.double())                 # projmatrix = viewmatrix @ Proj^T
+    vm[:3, :3] /= unit
+    inp["cam"] = cam._replace(viewmatrix=vm.float().contiguous(), projmatrix=(vm @ proj_t).float().contiguous(),
+                              campos=(cam.campos.double() * unit).float().contiguous())
+    inp["means3D"] = (inp["means3D"].double() * unit).float().contiguous()
+    inp["scales"] = (inp["scales"].double() * unit).float().contiguous()
+    f = oracle.rasterize_gaussians(*cases.binding_args(inp))
+    base = util.load_golden(case.name)["radii"]
+    assert (np.asarray(f.radii) > 0).sum() > 0.9 * (base > 0).sum()          # it IS the same picture
+    rej, inv = _check(inp, f.radii, f"{case.name} x{unit}")
+    assert rej > 0.5 * inv
